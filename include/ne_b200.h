@@ -1,0 +1,309 @@
+/*
+ * ne_b200.h — C ABI of the B200-native path-tracing backend for NarvalEngine.
+ *
+ * This is the drop-in boundary. The reference has no plugin/FFI mechanism; its seams are
+ * two C++ types, and every entry point below names the reference interface it replaces:
+ *
+ *   Seam 2 (renderer)   OfflineEngine(Camera, SceneSettings, Scene*)            src/core/OfflineEngine.h:23-47
+ *                       OfflineEngine::renderTile / postProcessing / pixels     src/core/OfflineEngine.cpp:39-76
+ *   Seam 1 (integrator) Integrator::Li(Ray, Scene*)                             src/integrators/Integrator.h:13-25
+ *   Scene feed          SceneReader::loadScene -> Scene, Camera, SceneSettings  src/io/SceneReader.cpp:10-675
+ *                       ResourceManager::loadVDBasTexture / loadVolasTexture    src/core/ResourceManager.cpp:165-286
+ *
+ * Plain C: pointers + sizes only, no C++/torch types. The caller keeps ownership of every pointer in the
+ * descriptors; the library copies what it needs into HBM during ne_b200_scene_upload(). One context drives one
+ * GPU (one process per GPU; see INTEGRATION.md for the 8-GPU sample-index split). A context may be driven by
+ * one host thread at a time. All functions return NE_B200_OK (0) or a negative ne_b200_status and never abort
+ * (the reference LOG(FATAL)s in its loaders, SceneReader.cpp:24-41); the message is in ne_b200_last_error().
+ *
+ * There is NO CPU fallback: every entry point that computes runs CUDA kernels (sm_100a) and fails with
+ * NE_B200_ERR_CUDA when no device is present.
+ */
+#ifndef NE_B200_H
+#define NE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NE_B200_API_VERSION 1
+
+typedef enum ne_b200_status {
+	NE_B200_OK = 0,
+	NE_B200_ERR_INVALID = -1,     /* bad argument / malformed descriptor */
+	NE_B200_ERR_CUDA = -2,        /* CUDA runtime error or no device */
+	NE_B200_ERR_NOMEM = -3,
+	NE_B200_ERR_STATE = -4,       /* call order (render before upload, ...) */
+	NE_B200_ERR_UNSUPPORTED = -5  /* valid reference feature this build does not cover yet */
+} ne_b200_status;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Scene description (what SceneReader builds, in POD form).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* TextureLayout subset the CPU sampler understands: src/materials/Texture.cpp:37-87 */
+typedef enum ne_b200_tex_format {
+	NE_B200_TEX_R32F = 0, NE_B200_TEX_RG32F = 1, NE_B200_TEX_RGB32F = 2, NE_B200_TEX_RGBA32F = 3, NE_B200_TEX_RGBA8 = 4
+} ne_b200_tex_format;
+
+/* Texture::wrapTextureCoordinates, src/materials/Texture.cpp:88-109 (clamp is also the default) */
+typedef enum ne_b200_wrap { NE_B200_WRAP_CLAMP = 0, NE_B200_WRAP_MIRROR = 1 } ne_b200_wrap;
+
+/* 2-D material texture (Texture, src/materials/Texture.h:77-98). Row-major, index = width*y + x. */
+typedef struct ne_b200_texture {
+	int32_t width, height;
+	int32_t format;              /* ne_b200_tex_format */
+	int32_t wrap_u, wrap_v;      /* ne_b200_wrap */
+	const void* texels;
+} ne_b200_texture;
+
+/*
+ * Density grid of a GridMedia (src/materials/GridMedia.h:16-92), i.e. the Texture produced by
+ * ResourceManager::loadVolasTexture (.vol, ResourceManager.cpp:222-286) or loadVDBasTexture (.vdb, :165-220).
+ * Texture space: index = width*height*z + width*y + x (Math.h:104-106).
+ * Give EITHER `dense` (width*height*depth floats) OR `n_leaves` 8x8x8 leaf bricks exactly as an OpenVDB
+ * FloatGrid leaf iterator yields them: leaf_origin = 3 ints per leaf (multiples of 8, texture space),
+ * leaf_values = 512 floats per leaf with texture-x fastest: value(x,y,z) = leaf_values[512*l + 64*z + 8*y + x].
+ * (For a .vdb the reference swaps axes, Q29: texture x = vdb z, texture z = vdb x, so an OpenVDB leaf buffer,
+ * whose linear offset is (x<<6)|(y<<3)|z, is already in this order. INTEGRATION.md shows the loop.)
+ * Voxels not covered by any leaf are 0 (inactive background).
+ */
+typedef struct ne_b200_volume {
+	int32_t width, height, depth;
+	const float* dense;
+	int32_t n_leaves;
+	const int32_t* leaf_origin;
+	const float* leaf_values;
+} ne_b200_volume;
+
+/* Material kinds created by SceneReader::processMaterial, src/io/SceneReader.cpp:67-222 */
+typedef enum ne_b200_material_type {
+	NE_B200_MAT_MICROFACET = 0,   /* GlossyBSDF(GGX, Schlick 0.04) :76-140 */
+	NE_B200_MAT_EMITTER = 1,      /* DiffuseLight :141-155 */
+	NE_B200_MAT_VOLUME = 2,       /* GridMedia (volume >= 0) or HomogeneousMedia (volume < 0) + VolumeBSDF :187-219 */
+	NE_B200_MAT_DIRECTIONAL = 3,  /* DirectionalLight :156-168   (next) */
+	NE_B200_MAT_INFINITE = 4      /* InfiniteAreaLight :169-186  (next) */
+} ne_b200_material_type;
+
+typedef enum ne_b200_phase { NE_B200_PHASE_ISOTROPIC = 0, NE_B200_PHASE_HG = 1 } ne_b200_phase;
+
+typedef struct ne_b200_material {
+	int32_t type;                                  /* ne_b200_material_type */
+	/* microfacet: texture indices into scene.textures, -1 = absent (Material::sampleMaterial returns (0,0,0,1)) */
+	int32_t albedo_tex, roughness_tex, metallic_tex, normal_tex;
+	int32_t has_normal_flag;                       /* Material::hasTexture(NORMAL): true only if NORMAL was the LAST texture added (Q24, Material.h:38-44) */
+	/* emitter: radiance li (DiffuseLight::li). directional: le, direction. */
+	float li[3];
+	float direction[3];
+	/* volume */
+	float scattering[3], absorption[3];
+	float density_multiplier;                      /* JSON "density" */
+	int32_t phase;                                 /* ne_b200_phase */
+	float g;
+	int32_t volume;                                /* index into scene.volumes, or -1 */
+	int32_t env_tex;                               /* infinite area light map */
+} ne_b200_material;
+
+/* Primitive kinds created by SceneReader::processPrimitives, src/io/SceneReader.cpp:224-648 */
+typedef enum ne_b200_primitive_type {
+	NE_B200_PRIM_RECTANGLE = 0,   /* unit square z=0, corners (-.5,-.5,0),(.5,.5,0), normal (0,0,-1), uv (0,0)-(1,1) :385-513 */
+	NE_B200_PRIM_SPHERE = 1,      /* centre (0,0,0) OCS + radius; transform = translate(position) only :332-384 */
+	NE_B200_PRIM_POINT = 2,       /* vertex = position AND transform contains position (Q25) :268-331 */
+	NE_B200_PRIM_VOLUME = 3,      /* proxy AABB [-0.5,0.5]^3 whose material has a medium :515-645 */
+	NE_B200_PRIM_MESH = 4         /* obj/gltf: triangles + BVH, one material for all triangles :245-267, Model.cpp:159-370 */
+} ne_b200_primitive_type;
+
+typedef struct ne_b200_primitive {
+	int32_t type;                 /* ne_b200_primitive_type */
+	int32_t material;             /* index into scene.materials; -1 = none (mesh without material: paths end there) */
+	float to_world[16];           /* InstancedModel::transformToWCS, column-major as glm::mat4 */
+	float to_object[16];          /* InstancedModel::invTransformToWCS (= glm::inverse(to_world)); see ne_b200_make_transform */
+	float radius;                 /* sphere */
+	float point[3];               /* point: the vertex (JSON position) */
+	int32_t collision;            /* InstancedModel::isCollisionEnabled (spheres only in the JSON) */
+	/* mesh (type MESH): triangle soup in OCS. positions: 3 floats per vertex; uvs: 2 floats per vertex or NULL;
+	 * indices: 3 uint32 per triangle, in the order the importer lists the faces. */
+	int32_t n_vertices, n_triangles;
+	const float* positions;
+	const float* uvs;
+	const uint32_t* indices;
+} ne_b200_primitive;
+
+typedef struct ne_b200_scene_desc {
+	int32_t n_textures;   const ne_b200_texture* textures;
+	int32_t n_volumes;    const ne_b200_volume* volumes;
+	int32_t n_materials;  const ne_b200_material* materials;
+	/* In JSON order. Like SceneReader, primitives whose material is an emitter go to Scene::lights and the rest
+	 * to Scene::instancedModels, each list keeping this order (Scene.cpp:30-56 folds over both in list order). */
+	int32_t n_primitives; const ne_b200_primitive* primitives;
+	/* SceneEditor::sortAndGroup (SceneEditor.cpp:2039-2054): move models with a medium to the end of
+	 * instancedModels. The editor does this in init() only; 0 = keep the order given. */
+	int32_t sort_and_group;
+} ne_b200_scene_desc;
+
+/* The vectors Camera::getRayPassingThrough reads (src/core/Camera.cpp:140-144). */
+typedef struct ne_b200_camera {
+	float position[3], lower_left[3], horizontal[3], vertical[3], side[3], up[3];
+	float lens_radius;
+} ne_b200_camera;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side helpers restating glm / Camera arithmetic (pure host code, no GPU needed).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* getTransform(T, R_deg, S) = translate * eulerAngleXYZ(radians) * scale (src/utils/Math.h:848-859) and its
+ * glm::inverse (InstancedModel.cpp:11-22). Column-major. */
+int ne_b200_make_transform(const float position[3], const float rotation_deg[3], const float scale[3],
+                           float to_world[16], float to_object[16]);
+
+/* Camera::Camera(lookFrom, lookAt, up, vfov, aspect, aperture, focus), src/core/Camera.cpp:7-26.
+ * SceneReader passes up=(0,1,0), aperture=1e-4 and focus=3 for autoFocus (Q26, SceneReader.cpp:660-668). */
+int ne_b200_camera_make(const float look_from[3], const float look_at[3], const float up[3], float vfov_deg,
+                        float aspect, float aperture, float focus_distance, ne_b200_camera* out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Context, scene, render (replaces OfflineEngine, src/core/OfflineEngine.cpp).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct ne_b200_ctx ne_b200_ctx;
+
+const char* ne_b200_last_error(void);           /* thread-local, never NULL */
+int ne_b200_device_count(void);                 /* number of CUDA devices visible, 0 if none/driver missing */
+
+int ne_b200_create(int cuda_device, ne_b200_ctx** out);
+void ne_b200_destroy(ne_b200_ctx* ctx);
+
+/* Flatten + copy the scene into HBM: SoA primitive/instance tables in reference fold order, SoA triangles +
+ * binned-SAH BVH, brick-sparse density grids with per-brick majorants, emitter table. Replaces the Scene*
+ * handed to OfflineEngine's ctor. May be called again to replace the scene. */
+int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* scene);
+
+int ne_b200_camera_set(ne_b200_ctx* ctx, const ne_b200_camera* camera);
+
+/* ne_b200_render flags */
+#define NE_B200_RENDER_GLOBAL_MAJORANT 1u   /* track with the reference's single global majorant (GridMedia.cpp:56,82) instead of per-brick majorants */
+#define NE_B200_RENDER_MEGAKERNEL      2u   /* one thread per path, no queues (debug / A-B check of the wavefront) */
+
+/*
+ * Render samples [spp_begin, spp_end) of every pixel of a width x height frame and ADD their radiance into the
+ * context's fp32 linear accumulation buffer (OfflineEngine::renderTile's two hot loops, OfflineEngine.cpp:61-69,
+ * for the whole frame). Philox4x32-10 keyed (seed, pixel, sample): any sample range can be rendered on any
+ * GPU in any order and the sum is the same up to fp32 addition order. Asynchronous; ne_b200_wait() joins.
+ * The buffer is (re)allocated and zeroed when width/height change or after ne_b200_clear().
+ */
+int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int spp_end, int bounces,
+                   uint64_t seed, uint32_t flags);
+int ne_b200_wait(ne_b200_ctx* ctx);
+int ne_b200_clear(ne_b200_ctx* ctx);
+
+/* Device pointer of the linear accumulation buffer (width*height*3 floats, Σ radiance, row-major W*y+x, y=0
+ * top row) so the caller can ncclReduce it across ranks, and the sample count it holds. */
+int ne_b200_accum_buffer(ne_b200_ctx* ctx, void** device_ptr, size_t* n_floats, int* samples_accumulated);
+int ne_b200_set_samples_accumulated(ne_b200_ctx* ctx, int samples);
+
+/* rgb[W*H*3] = accumulation / samples (what `color / float(spp)` is at OfflineEngine.cpp:70). Host pointers. */
+int ne_b200_read_linear(ne_b200_ctx* ctx, float* rgb);
+/* rgb[W*H*3] = OfflineEngine::postProcessing(mean) = clamp(pow(1-exp(-0.5c), 1/2.2), 0, 1) (OfflineEngine.cpp:39-52):
+ * the contents of OfflineEngine::pixels (glm::vec3[W*H]). Host pointer. */
+int ne_b200_read_tonemapped(ne_b200_ctx* ctx, float* rgb);
+
+/* The single call a renderer front end makes per frame: camera from host, render all spp, resolve, copy the
+ * tone-mapped frame (and optionally the linear one, may be NULL) to host memory. Synchronous. */
+int ne_b200_render_frame(ne_b200_ctx* ctx, const ne_b200_camera* camera, int width, int height, int spp, int bounces,
+                         uint64_t seed, uint32_t flags, float* pixels_tonemapped, float* pixels_linear);
+
+/* Work counters of everything rendered since the last ne_b200_counters_reset (device counters; they are what
+ * bench.py's roofline uses). Byte sizes of the records are exported so the check is reproducible. */
+typedef struct ne_b200_counters {
+	uint64_t paths;               /* camera paths started */
+	uint64_t extend_rays;         /* Scene::intersectScene equivalents with tMin=1e-11 (Li) */
+	uint64_t shadow_rays;         /* intersectScene equivalents from visibilityTr / intersectTr (tMin=1e-3) */
+	uint64_t delta_steps;         /* GridMedia::sample tracking iterations (density lookups) */
+	uint64_t ratio_steps;         /* GridMedia::Tr tracking iterations (density lookups) */
+	uint64_t brick_visits;        /* macro-DDA brick entries */
+	uint64_t bvh_nodes;           /* BVH node visits */
+	uint64_t tri_tests;           /* ray/triangle tests */
+	uint64_t prim_tests;          /* analytic primitive / instance tests */
+	uint64_t scatter_events;      /* real collisions */
+	uint64_t surface_events;      /* surface shading events */
+	uint64_t wavefront_iterations;
+	uint64_t kernel_launches;     /* CUDA kernels launched by the library */
+	double ms_render;             /* device time (CUDA events) of ne_b200_render calls */
+	double ms_volume_kernel;      /* device time of the volume tracking kernel(s) */
+	double ms_extend_kernel;
+	double ms_shade_kernel;
+	double ms_upload;             /* host wall time of the last ne_b200_scene_upload */
+	uint32_t bytes_per_tracking_step;  /* 32 B cell + 4 B brick-table entry + 4 B majorant */
+	uint32_t bytes_per_bvh_node;
+	uint32_t bytes_per_triangle;
+	uint32_t bytes_per_path_record;
+} ne_b200_counters;
+int ne_b200_get_counters(ne_b200_ctx* ctx, ne_b200_counters* out);
+int ne_b200_counters_reset(ne_b200_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Test hooks: single device functions on arrays of inputs, optionally driven by an explicit uniform TAPE
+ * (the sequence narvalengine::random() would return) so results can be compared with the reference
+ * draw for draw. All pointers are HOST pointers; each call launches kernels on the context's GPU.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct ne_b200_hit {      /* RayIntersection, src/primitives/Ray.h:8-15 */
+	float hit_point[3], normal[3], uv[2];
+	float t_near, t_far;
+	int32_t hit;                  /* bool result of Scene::intersectScene */
+	int32_t instance;             /* index in fold order: instancedModels..., then lights... ; -1 = none */
+	int32_t is_light;
+	int32_t primitive;            /* triangle index inside a mesh (as given in `indices`), else 0 */
+} ne_b200_hit;
+
+/* Scene::intersectScene(ray, hit, t_min, t_max), src/core/Scene.cpp:30-56 */
+int ne_b200_test_intersect(ne_b200_ctx* ctx, int n, const float* origins, const float* directions,
+                           float t_min, float t_max, ne_b200_hit* out);
+
+/* Camera::getRayPassingThrough(x,y) with 2 tape uniforms per ray (theta, r), src/core/Camera.cpp:140-144 */
+int ne_b200_test_camera_rays(ne_b200_ctx* ctx, int n, const float* xy, const float* tape, float* origins, float* directions);
+
+/* BSDF::eval / BSDF::pdf / (with tape) BSDF::sample at a hit on `instance` (fold order) with the given uv and
+ * normal, src/core/BSDF.h:100-142. eval: 3 floats, pdf: 1 float, sampled: 3 floats per item (tape: 2 uniforms each). */
+int ne_b200_test_bsdf(ne_b200_ctx* ctx, int n, int instance, const float* incoming, const float* scattered,
+                      const float* normals, const float* uvs, const float* tape, float* eval, float* pdf, float* sampled);
+
+/* GridMedia::Tr(ray, isect) and GridMedia::sample(ray, scattered, isect) on `instance` with a tape of
+ * `tape_stride` uniforms per item; *_used returns uniforms consumed. src/materials/GridMedia.cpp:45-100.
+ * Always global-majorant tracking (tape-exact). */
+int ne_b200_test_grid_tr(ne_b200_ctx* ctx, int n, int instance, const float* origins, const float* directions,
+                         const float* t_near, const float* t_far, const float* tape, int tape_stride,
+                         float* tr, int32_t* used);
+int ne_b200_test_grid_sample(ne_b200_ctx* ctx, int n, int instance, const float* origins, const float* directions,
+                             const float* t_near, const float* t_far, const float* tape, int tape_stride,
+                             float* transmittance, float* scattered_o, float* scattered_d, int32_t* used);
+
+/* VolumetricPathIntegrator::Li(ray, scene) for n rays, each with its own tape (tape_stride uniforms), one GPU
+ * thread per ray, reference draw order. src/integrators/VolumetricPathIntegrator.cpp:176-301.
+ * This is Seam 1 (Integrator::Li). radiance: 3 floats per ray; used: uniforms consumed (or -1 if the tape ran out). */
+int ne_b200_test_li_tape(ne_b200_ctx* ctx, int n, const float* origins, const float* directions, int bounces,
+                         const float* tape, int tape_stride, float* radiance, int32_t* used);
+
+/* Same with Philox (seed, path index i, sample 0): the megakernel estimator used for wavefront A/B checks. */
+int ne_b200_test_li_philox(ne_b200_ctx* ctx, int n, const float* origins, const float* directions, int bounces,
+                           uint64_t seed, uint32_t flags, float* radiance);
+
+/* uniformSampleOneLight(incoming, isect, scene) (VolumetricPathIntegrator.cpp:159-174, incl. estimateDirect
+ * :74-157) at explicit hits: incoming ray dir, hit record (point, normal, uv, instance). Tape-driven. */
+int ne_b200_test_sample_one_light(ne_b200_ctx* ctx, int n, const float* incoming_dirs, const ne_b200_hit* hits,
+                                  const float* tape, int tape_stride, float* radiance, int32_t* used);
+
+/* Trilinear density GridMedia::interpolatedDensity at OCS points of `instance` (GridMedia.cpp:25-43) and the
+ * grid's invMaxDensity (GridMedia.cpp:12). */
+int ne_b200_test_density(ne_b200_ctx* ctx, int n, int instance, const float* ocs_points, float* density, float* inv_max_density);
+
+/* Philox4x32-10 uniforms: out[i] = u(seed, pixel, sample, dimension i), for KATs of the generator. */
+int ne_b200_test_philox(ne_b200_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NE_B200_H */
