@@ -1,0 +1,49 @@
+// ne_ctx.h — the context object behind ne_b200_ctx and the launch entry points shared by ne_api.cu (C ABI, scene
+// upload, test hooks, megakernel) and ne_wavefront.cu (production wavefront renderer).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ne_b200.h"
+#include "ne_scene.cuh"
+
+namespace ne {
+void set_error(const std::string& s);
+}
+
+#define NE_CUDA_OK(expr)                                                                                      \
+	do {                                                                                                      \
+		cudaError_t e_ = (expr);                                                                              \
+		if (e_ != cudaSuccess) {                                                                              \
+			ne::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                               \
+			return NE_B200_ERR_CUDA;                                                                          \
+		}                                                                                                     \
+	} while (0)
+
+struct ne_wavefront_state;
+
+struct ne_b200_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::vector<void*> sceneAllocs;  // device allocations owned by the uploaded scene
+	ne::DScene scene{};
+	bool haveScene = false;
+	ne::DCamera cam{};
+	bool haveCamera = false;
+	float* accum = nullptr;  // W*H*3 fp32 radiance sums
+	int W = 0, H = 0;
+	int samples = 0;
+	ne::DCounters* dCounters = nullptr;
+	unsigned long long kernelLaunches = 0, wavefrontIterations = 0;
+	double msRender = 0, msVolume = 0, msExtend = 0, msShade = 0, msUpload = 0;
+	cudaEvent_t evA = nullptr, evB = nullptr;
+	ne_wavefront_state* wf = nullptr;
+};
+
+namespace ne {
+// ne_wavefront.cu
+int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags);
+void wavefront_free(ne_b200_ctx* ctx);
+}  // namespace ne

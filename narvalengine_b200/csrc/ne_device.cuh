@@ -1,0 +1,885 @@
+// ne_device.cuh — device functions of the hot path. Each function names the reference code whose behaviour it
+// reproduces (paths relative to /root/reference/src). The estimator is reproduced WITH its quirks (SURVEY.md
+// Appendix A, Q1..Q30) because image parity is judged against the reference's own CPU render.
+//
+// Everything is templated on the uniform source R (TapeRng: reference draw order for tape-exact tests;
+// PhiloxRng: production) and on two compile-time switches:
+//   FAITHFUL  consume uniforms / do work whose result the reference discards (visibilityTr's ratio tracking
+//             behind `return 0`, intersectTr in medium-free scenes) so a tape stays aligned draw for draw.
+//   BRICKMAJ  track with per-brick majorants over a brick DDA instead of the reference's single global majorant
+//             (same expectation, far fewer null collisions; SURVEY.md A.5 last bullet).
+#pragma once
+#include "ne_math.cuh"
+#include "ne_rng.cuh"
+#include "ne_scene.cuh"
+
+namespace ne {
+
+struct Stats {
+	uint32_t extend_rays, shadow_rays, delta_steps, ratio_steps, brick_visits, bvh_nodes, tri_tests, prim_tests, scatter_events,
+		surface_events;
+	NE_D void clear() {
+		extend_rays = shadow_rays = delta_steps = ratio_steps = brick_visits = bvh_nodes = tri_tests = prim_tests = scatter_events =
+			surface_events = 0;
+	}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Textures: Texture::sample / sampleAtIndex / wrapTextureCoordinates, materials/Texture.cpp:37-129;
+// Material::sampleMaterial, materials/Material.h:62-69
+// ---------------------------------------------------------------------------------------------------------------
+NE_D V4 tex_at(const DTexture& t, uint32_t index) {
+	V4 r = {0, 0, 0, 0};
+	if (t.format == TEX_RGBA8) {
+		uchar4 c = reinterpret_cast<const uchar4*>(t.texels)[index];
+		r.x = c.x / 255.0f; r.y = c.y / 255.0f; r.z = c.z / 255.0f; r.w = c.w / 255.0f;
+		return r;
+	}
+	const float* p = reinterpret_cast<const float*>(t.texels);
+	switch (t.format) {
+	case TEX_R32F: r.x = __ldg(p + index); break;
+	case TEX_RG32F: r.x = __ldg(p + 2 * index); r.y = __ldg(p + 2 * index + 1); break;
+	case TEX_RGB32F: r.x = __ldg(p + 3 * index); r.y = __ldg(p + 3 * index + 1); r.z = __ldg(p + 3 * index + 2); break;
+	default: r.x = __ldg(p + 4 * index); r.y = __ldg(p + 4 * index + 1); r.z = __ldg(p + 4 * index + 2); r.w = __ldg(p + 4 * index + 3); break;
+	}
+	return r;
+}
+NE_D float tex_wrap(float u, int mode) {
+	if (mode == 1) return gclamp(fabsf(u - float(int(u))), 0.0f, 1.0f);  // "mirror"
+	return gclamp(u, 0.0f, 1.0f);
+}
+NE_D V4 tex_sample(const DTexture& t, float u, float v) {
+	u = tex_wrap(u, t.wrap_u);
+	v = tex_wrap(v, t.wrap_v);
+	int x = int(u * t.w), y = int(v * t.h);
+	if (x > 0 && x == t.w) x--;
+	if (y > 0 && y == t.h) y--;
+	return tex_at(t, uint32_t(t.w * y + x));
+}
+NE_D V4 material_sample(const DScene& s, int tex, float u, float v) {
+	if (tex < 0) { V4 r = {0, 0, 0, 1}; return r; }
+	return tex_sample(s.tex[tex], u, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Primitives
+// ---------------------------------------------------------------------------------------------------------------
+// AABB::intersect, primitives/AABB.cpp:48-79 (centre/half-size slab; true even when the box is behind the ray;
+// miss -> tNear=+inf, tFar=-inf).
+NE_D bool aabb_intersect(V3 bmin, V3 bmax, Ray r, float& tNear, float& tFar, V3& normal, V3& hitPoint) {
+	V3 s((r.d.x < 0.0f) ? 1.0f : -1.0f, (r.d.y < 0.0f) ? 1.0f : -1.0f, (r.d.z < 0.0f) ? 1.0f : -1.0f);
+	V3 invD = 1.0f / r.d;
+	V3 size = bmax - bmin;
+	V3 half = size / 2.0f;
+	V3 center = bmax - size / 2.0f;
+	V3 t1 = (center - r.o + s * half) * invD;
+	V3 t2 = (center - r.o - s * half) * invD;
+	V3 tmn = gmin(t1, t2), tmx = gmax(t1, t2);
+	float tn = gmax(gmax(tmn.x, tmn.y), tmn.z);
+	float tf = gmin(gmin(tmx.x, tmx.y), tmx.z);
+	V3 sg(gsign(r.d.x), gsign(r.d.y), gsign(r.d.z));
+	normal = -sg * V3(gstep(t1.y, t1.x), gstep(t1.z, t1.y), gstep(t1.x, t1.z)) * V3(gstep(t1.z, t1.x), gstep(t1.x, t1.y), gstep(t1.y, t1.z));
+	tNear = tn;
+	tFar = tf;
+	hitPoint = r.at(tn);
+	if (tn > tf) {
+		tNear = INFINITY;
+		tFar = -INFINITY;
+		return false;
+	}
+	return true;
+}
+
+// Rectangle::barycentricCoordinates + samplePointOnTexture, primitives/Rectangle.cpp:90-157, for the unit square
+// SceneReader builds (SceneReader.cpp:407-468): vertices a,b,c,d = (-.5,-.5,0),(.5,-.5,0),(.5,.5,0),(-.5,.5,0),
+// uv (0,0),(1,0),(1,1),(0,1).
+NE_D void bary3(V3 p, V3 a, V3 b, V3 c, float& l0, float& l1, float& l2) {
+	V3 v0 = b - a, v1 = c - a, v2 = p - a;
+	float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+	float denom = d00 * d11 - d01 * d01;
+	l1 = (d11 * d20 - d01 * d21) / denom;
+	l2 = (d00 * d21 - d01 * d20) / denom;
+	l0 = 1.0f - l1 - l2;
+}
+NE_D void rect_uv(V3 p, float& u, float& v) {
+	const V3 a(-0.5f, -0.5f, 0), b(0.5f, -0.5f, 0), c(0.5f, 0.5f, 0), d(-0.5f, 0.5f, 0);
+	float x0, x1, x2, y0, y1, y2;
+	bary3(p, a, b, c, x0, x1, x2);
+	bary3(p, d, b, c, y0, y1, y2);
+	if (x0 < 0 || x1 < 0 || x2 < 0 || x0 > 1 || x1 > 1 || x2 > 1) {
+		// w*D + u*B + v*C with uv D=(0,1), B=(1,0), C=(1,1)
+		u = y0 * 0.0f + y1 * 1.0f + y2 * 1.0f;
+		v = y0 * 1.0f + y1 * 0.0f + y2 * 1.0f;
+	} else {
+		u = x0 * 0.0f + x1 * 1.0f + x2 * 1.0f;
+		v = x0 * 0.0f + x1 * 0.0f + x2 * 1.0f;
+	}
+}
+// Rectangle::intersect, primitives/Rectangle.cpp:50-76 (plane z=0, normal (0,0,-1), corners (-.5,-.5,0),(.5,.5,0)).
+NE_D bool rect_intersect(Ray r, Hit& hit) {
+	const V3 normal(0.0f, 0.0f, -1.0f);
+	const V3 planeVertex(0.5f, 0.5f, 0.0f);
+	float denom = dot(normal, r.d);
+	if (double(fabsf(denom)) < NE_EPSILON) return false;
+	float num = dot(normal, planeVertex - r.o);
+	float t = num / denom;
+	if (t < 0) return false;
+	V3 p = r.at(t);
+	// containsPoint with size (1,1,0): only x and y are tested
+	if (p.x < -0.5f || p.x > 0.5f) return false;
+	if (p.y < -0.5f || p.y > 0.5f) return false;
+	hit.tNear = t;
+	hit.tFar = t;
+	hit.n = normal;
+	hit.p = p;
+	hit.prim = 0;
+	rect_uv(p, hit.u, hit.v);
+	return true;
+}
+// Sphere::intersect, primitives/Sphere.cpp:21-44 (centre = origin of the OCS; true for ANY real roots).
+NE_D bool sphere_intersect(Ray r, float radius, Hit& hit) {
+	V3 center(0.0f, 0.0f, 0.0f);
+	V3 oc = r.o - center;
+	float a = dot(r.d, r.d);
+	float b = dot(oc, r.d);
+	float c = dot(oc, oc) - radius * radius;
+	float disc = b * b - a * c;
+	if (disc >= 0) {
+		float sq = sqrtf(disc);
+		float t1 = (-b - sq) / a, t2 = (-b + sq) / a;
+		hit.tNear = gmin(t1, t2);
+		hit.tFar = gmax(t1, t2);
+		hit.p = r.at(hit.tNear);
+		hit.n = normalize((hit.p - center) / radius);
+		hit.u = hit.v = 0;
+		hit.prim = 0;
+		return true;
+	}
+	return false;
+}
+
+// Triangle::intersect, primitives/Triangle.cpp:49-81 — the t/u/v part. Accepts t >= 0, u,v in [0,1], u+v <= 1.
+NE_D bool tri_intersect(V3 v0, V3 v1, V3 v2, Ray ray, float& tOut) {
+	V3 v1v0 = v1 - v0, v2v0 = v2 - v0, rov0 = ray.o - v0;
+	V3 n = cross(v1v0, v2v0);
+	V3 q = cross(rov0, ray.d);
+	float denom = 1.0f / dot(ray.d, n);
+	float u = dot(-q, v2v0) * denom;
+	float v = dot(q, v1v0) * denom;
+	float t = dot(-n, rov0) * denom;
+	if (isnan(t) || t < 0) return false;
+	if (u < 0.0f || u > 1.0f || v < 0.0f || (u + v) > 1.0f) return false;
+	tOut = t;
+	return true;
+}
+
+// convertNormalFromTextureMap, utils/Math.h:1209-1215
+NE_D V3 normal_from_map(V3 texNormal, V3 worldNormal) {
+	V3 nt = texNormal * 2.0f - 1.0f;
+	V3 t = cross(worldNormal, V3(0.0f, 1.0f, 0.0f));
+	V3 b = normalize(cross(worldNormal, t));
+	// mat3(t,b,n) * nt = t*nt.x + b*nt.y + n*nt.z
+	V3 r = t * nt.x + b * nt.y + worldNormal * nt.z;
+	return normalize(r);
+}
+
+// Closest triangle with t >= 0 (BVH::intersect semantics, primitives/BVH.cpp:108-194: no tMin/tMax inside, strict
+// `<` keeps the first of equal hits) over OUR binned-SAH 2-wide BVH. Node boxes are tested with a conservative
+// slab test; every triangle test uses the reference arithmetic above.
+NE_D bool bvh_closest(const DMesh& m, Ray r, float& tBest, int& slotBest, Stats& st) {
+	const V3 inv = 1.0f / r.d;
+	int stack[48];
+	int sp = 0;
+	int node = 0;
+	tBest = INFINITY;
+	slotBest = -1;
+	bool any = false;
+	while (true) {
+		if (node < 0) {
+			int enc = ~node;
+			int first = enc >> 3, cnt = enc & 7;
+			for (int i = 0; i < cnt; i++) {
+				const float4* tp = m.tri + 3 * size_t(first + i);
+				float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				float t;
+				st.tri_tests++;
+				if (tri_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), r, t)) {
+					any = true;
+					if (t < tBest) { tBest = t; slotBest = first + i; }
+				}
+			}
+			if (sp == 0) break;
+			node = stack[--sp];
+			continue;
+		}
+		st.bvh_nodes++;
+		const float4* np = reinterpret_cast<const float4*>(m.nodes + node);
+		float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+		// n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = child0 child1 - -
+		float ax = (n0.x - r.o.x) * inv.x, bx = (n0.w - r.o.x) * inv.x;
+		float ay = (n0.y - r.o.y) * inv.y, by = (n1.x - r.o.y) * inv.y;
+		float az = (n0.z - r.o.z) * inv.z, bz = (n1.y - r.o.z) * inv.z;
+		float tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+		float tf0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+		ax = (n1.z - r.o.x) * inv.x; bx = (n2.y - r.o.x) * inv.x;
+		ay = (n1.w - r.o.y) * inv.y; by = (n2.z - r.o.y) * inv.y;
+		az = (n2.x - r.o.z) * inv.z; bz = (n2.w - r.o.z) * inv.z;
+		float tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+		float tf1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+		bool h0 = tn0 <= tf0 && tn0 <= tBest;
+		bool h1 = tn1 <= tf1 && tn1 <= tBest;
+		int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+		if (h0 && h1) {
+			if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
+			if (sp < 48) stack[sp++] = c1;
+			node = c0;
+		} else if (h0) node = c0;
+		else if (h1) node = c1;
+		else {
+			if (sp == 0) break;
+			node = stack[--sp];
+		}
+	}
+	return any;
+}
+
+// Triangle::samplePointOnTexture, primitives/Triangle.cpp:121-147 with Q30: the three vertices/uvs are read
+// CONSECUTIVELY from the vertex buffer starting at the triangle's first vertex (indices i0, i0+1, i0+2).
+NE_D void tri_uv(const DMesh& m, int tri, V3 p, float& u, float& v) {
+	u = v = 0;
+	if (!m.uv) return;
+	int i0 = int(m.idx[3 * size_t(tri)]);
+	int i1 = min(i0 + 1, m.n_verts - 1), i2 = min(i0 + 2, m.n_verts - 1);
+	V3 a(m.pos[3 * i0], m.pos[3 * i0 + 1], m.pos[3 * i0 + 2]);
+	V3 b(m.pos[3 * i1], m.pos[3 * i1 + 1], m.pos[3 * i1 + 2]);
+	V3 c(m.pos[3 * i2], m.pos[3 * i2 + 1], m.pos[3 * i2 + 2]);
+	float l0, l1, l2;
+	bary3(p, a, b, c, l0, l1, l2);
+	u = l0 * m.uv[2 * i0] + l1 * m.uv[2 * i1] + l2 * m.uv[2 * i2];
+	v = l0 * m.uv[2 * i0 + 1] + l1 * m.uv[2 * i1 + 1] + l2 * m.uv[2 * i2 + 1];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// InstancedModel::intersect (primitives/InstancedModel.cpp:24-38) over Model::intersect (primitives/Model.cpp:372-447)
+// for the one-primitive models SceneReader builds. `in_lights`: the instance sits in Scene::lights, i.e. its
+// primitive is in Model::lights (tested by the lights loop :432-444: no "inside" case).
+// ---------------------------------------------------------------------------------------------------------------
+NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st) {
+	const DInstance& in = s.inst[i];
+	if (!in.collision) return false;
+	Ray ray = transform_ray(rayW, in.Mi);
+	bool did = false;
+	st.prim_tests++;
+	if (in.type == PRIM_MESH) {
+		const DMesh& m = s.mesh[in.mesh];
+		float tn, tf; V3 nn, hp;
+		if (!aabb_intersect(V3(m.bbmin[0], m.bbmin[1], m.bbmin[2]), V3(m.bbmax[0], m.bbmax[1], m.bbmax[2]), ray, tn, tf, nn, hp)) return false;
+		float t; int slot;
+		bool local = bvh_closest(m, ray, t, slot, st);
+		if (local && t > tMin && t < tMax) {
+			tMax = t;
+			const float4* tp = m.tri + 3 * size_t(slot);
+			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			V3 v0(a.x, a.y, a.z), v1(b.x, b.y, b.z), v2(c.x, c.y, c.z);
+			int tri = __float_as_int(a.w);
+			hit.tNear = hit.tFar = t;
+			hit.p = ray.at(t);
+			tri_uv(m, tri, hit.p, hit.u, hit.v);
+			V3 n = normalize(cross(v1 - v0, v2 - v0));
+			if (in.material >= 0 && s.mat[in.material].has_normal_flag) {
+				V4 tn4 = material_sample(s, s.mat[in.material].normal_tex, hit.u, hit.v);
+				n = normal_from_map(V3(tn4.x, tn4.y, tn4.z), n);
+			}
+			hit.n = n;
+			hit.prim = tri;
+			did = true;
+		}
+	} else if (in.type == PRIM_VOLUME && !in_lights) {
+		// GridMedia special case, Model.cpp:394-413: ignores tMin/tMax (Q4)
+		float tn, tf; V3 nn, hp;
+		aabb_intersect(V3(-0.5f, -0.5f, -0.5f), V3(0.5f, 0.5f, 0.5f), ray, tn, tf, nn, hp);
+		float a = gmax(0.0f, tn), b = tf;
+		if (a <= b && !isinf(b) && !isinf(a)) {
+			hit.tNear = a;
+			hit.tFar = b;
+			hit.p = ray.at(a);
+			hit.n = -ray.d;
+			hit.u = hit.v = 0;
+			hit.prim = 0;
+			tMax = a;
+			did = true;
+		}
+	} else if (in.type == PRIM_RECTANGLE || in.type == PRIM_SPHERE) {
+		Hit tmp;
+		bool local = in.type == PRIM_RECTANGLE ? rect_intersect(ray, tmp) : sphere_intersect(ray, in.radius, tmp);
+		if (local && !in_lights && tmp.tNear != tmp.tFar && tmp.tNear < 0 && tmp.tFar > 0) {
+			// "inside" case, Model.cpp:418-424 (Q14): hit at t=0, normal left as computed at the negative root
+			tmp.tNear = 0;
+			tmp.p = ray.o;
+			tMax = 0;
+			hit = tmp;
+			did = true;
+		}
+		if (local && tmp.tNear > tMin && tmp.tNear < tMax) {
+			tMax = tmp.tNear;
+			hit = tmp;
+			did = true;
+		}
+	}
+	// PRIM_POINT: Point::intersect never hits (primitives/Point.cpp:10-12)
+	if (did) {
+		hit.p = xform_point(in.M, hit.p);
+		hit.n = normalize(xform_dir(in.M, hit.n));
+		hit.inst = i;
+	}
+	return did;
+}
+
+// Scene::intersectScene, core/Scene.cpp:30-56: sequential fold, instancedModels then lights, tMax shrinks on
+// every accepted hit (volumes may raise it again, Q4).
+NE_D bool intersect_scene(const DScene& s, Ray ray, Hit& hit, float tMin, float tMax, Stats& st) {
+	bool did = false;
+	hit.inst = -1;
+	for (int i = 0; i < s.n_inst; i++) {
+		bool th = instance_intersect(s, i, ray, hit, tMin, tMax, i >= s.n_models, st);
+		did = did || th;
+	}
+	return did;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BSDFs: BSDF wrapper core/BSDF.h:100-142; GlossyBSDF core/GlossyBSDF.cpp:10-48; GGX core/Microfacet.cpp:5-65;
+// Schlick core/BSDF.h:150-157; VolumeBSDF core/VolumeBSDF.cpp:13-23; phase functions materials/Medium.h:43-129
+// ---------------------------------------------------------------------------------------------------------------
+NE_D float ggx_D(float alpha, V3 h) {
+	float a2 = alpha * alpha;
+	float NdotH = h.z;
+	float NdotH2 = NdotH * NdotH;
+	float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+	double dd = NE_PI * double(denom) * double(denom);
+	denom = float((NE_EPSILON < dd) ? dd : NE_EPSILON);
+	return a2 / denom;
+}
+NE_D float ggx_g1(float alpha, float NdotV) {
+	float k = alpha / 2.0f;
+	double dd = double(NdotV) * (1.0 - double(k)) + double(k);
+	float denom = float((NE_EPSILON < dd) ? dd : NE_EPSILON);
+	return NdotV / denom;
+}
+NE_D float ggx_G(float alpha, V3 wo, V3 wi) {
+	V3 n = normalize(wo + wi);
+	float NdotV = gmax(dot(n, wo), 0.0f), NdotL = gmax(dot(n, wi), 0.0f);
+	return ggx_g1(alpha, NdotV) * ggx_g1(alpha, NdotL);
+}
+NE_D float ggx_pdf(float alpha, V3 wi, V3 h) {
+	float NdotH = h.z;
+	float VdotH = dot(wi, h);
+	float D = ggx_D(alpha, h) * NdotH;
+	return D / (4 * VdotH);
+}
+NE_D float fresnel_schlick(float c) { return 0.04f + (1.0f - 0.04f) * powf(1.0f - c, 5.0f); }
+
+template <class R>
+NE_D V3 ggx_sample_microfacet(float alpha, R& rng) {
+	float ry = rng.next(), rx = rng.next();  // glm::vec2(random(), random()): arguments evaluated right to left
+	float a2 = alpha * alpha;
+	float theta = acosf(gmin(1.0f, sqrtf((1.0f - rx) / gmax(float(NE_EPSILON), (rx * (a2 - 1.0f) + 1.0f)))));
+	float phi = float(NE_TWO_PI * double(ry));
+	return V3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+}
+
+NE_D float hg_eval(float g, V3 in, V3 out) {
+	float c = dot(normalize(in), normalize(out));
+	float denom = 1.0f + g * g - 2.0f * g * c;
+	return NE_INV4PI * (1.0f - g * g) / (denom * sqrtf(denom));
+}
+NE_D float phase_eval(const DMaterial& m, V3 in, V3 out) {
+	if (m.phase == 1) return hg_eval(m.g, in, out);
+	return float(1.0 / NE_FOUR_PI);
+}
+template <class R>
+NE_D V3 phase_sample(const DMaterial& m, R& rng) {
+	if (m.phase == 1) {
+		float u1 = rng.next(), u0 = rng.next();
+		float g = m.g, cosT;
+		if (fabsf(g) < 1e-3f)
+			cosT = 1.0f - 2.0f * u0;
+		else {
+			float sqr = (1.0f - g * g) / (1.0f + g - 2.0f * g * u0);
+			sqr = sqr * sqr;
+			cosT = -1.0f / (2.0f * g) * (1.0f + g * g - sqr);
+		}
+		float sinT = sqrtf(1.0f - cosT * cosT);
+		float phi = float(2.0 * NE_PI * double(u1));
+		return V3(cosf(phi) * sinT, sinf(phi) * sinT, cosT);
+	}
+	float e2 = rng.next(), e1 = rng.next();
+	return sample_unit_sphere(e1, e2);
+}
+
+template <class R>
+NE_D V3 bsdf_sample(const DScene& s, const DMaterial& m, V3 incoming, V3 normal, const Hit& ri, R& rng) {
+	V3 ss, ts;
+	onb(normal, ss, ts);
+	V3 wo = to_lcs(-normalize(incoming), normal, ss, ts);
+	V3 sc;
+	if (m.transmissive)
+		sc = phase_sample(m, rng);
+	else {
+		float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
+		float alpha = rough * rough;
+		V3 h = ggx_sample_microfacet(alpha, rng);
+		sc = reflect(normalize(wo), normalize(h));  // Q17
+	}
+	return to_world(sc, normal, ss, ts);
+}
+NE_D float bsdf_pdf(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered, V3 normal, const Hit& ri) {
+	if (!m.transmissive && (!(dot(-incoming, normal) > 0) || !(dot(scattered, normal) > 0))) return 0;
+	V3 ss, ts;
+	onb(normal, ss, ts);
+	V3 wo = to_lcs(-normalize(incoming), normal, ss, ts), wi = to_lcs(scattered, normal, ss, ts);
+	if (m.transmissive) return phase_eval(m, wo, wi);
+	V3 h = normalize(wo + wi);
+	float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
+	return ggx_pdf(rough * rough, wi, h);
+}
+NE_D V3 bsdf_eval(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered, const Hit& ri) {
+	if (!m.transmissive && (!(dot(-incoming, ri.n) > 0) || !(dot(scattered, ri.n) > 0))) return V3(0.0f);
+	V3 ss, ts;
+	onb(ri.n, ss, ts);
+	V3 wo = to_lcs(-normalize(incoming), ri.n, ss, ts), wi = to_lcs(scattered, ri.n, ss, ts);
+	if (m.transmissive) return V3(phase_eval(m, wo, wi));
+	float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
+	float alpha = rough * rough;
+	V3 H = normalize(wo + wi);
+	float HdotV = dot(wo, H);
+	float NdotV = wo.z, NdotL = wi.z;
+	float D = ggx_D(alpha, H);
+	float G = ggx_G(alpha, wo, wi);
+	float F = fresnel_schlick(HdotV);
+	float num = D * G * F;
+	float den = 4.0f * gmax(NdotV, 0.0f) * gmax(NdotL, 0.0f);
+	float spec = num / gmax(den, float(NE_EPSILON));
+	float kD = 1.0f - F;
+	float metallic = material_sample(s, m.metallic_tex, ri.u, ri.v).x;
+	V4 al = material_sample(s, m.albedo_tex, ri.u, ri.v);
+	kD *= float(1.0 - double(metallic));
+	const float pi = float(NE_PI);
+	return V3(((al.x / pi) * kD + spec) * NdotL, ((al.y / pi) * kD + spec) * NdotL, ((al.z / pi) * kD + spec) * NdotL);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GridMedia: density / interpolatedDensity / fromOCStoGCS (materials/GridMedia.cpp:15-43, GridMedia.h:33-36) over
+// the brick-sparse grid; Tr (ratio tracking) :45-69; sample (delta tracking) :71-100.
+// ---------------------------------------------------------------------------------------------------------------
+NE_D float voxel(const DVolume& v, int x, int y, int z) {
+	if (x >= v.W || y >= v.H || z >= v.D) return 0;
+	int b = __ldg(v.table + ((z >> 3) * v.by + (y >> 3)) * v.bx + (x >> 3));
+	if (b < 0) return 0;
+	return __ldg(v.pool + size_t(b) * BRICK_VOX + ((z & 7) << 6) + ((y & 7) << 3) + (x & 7));
+}
+NE_D float interpolated_density(const DVolume& v, V3 g) {
+	g = gmin(gmax(V3(0.0f), g), V3(float(v.W), float(v.H), float(v.D)));
+	int ix = int(floorf(g.x)), iy = int(floorf(g.y)), iz = int(floorf(g.z));
+	V3 d = g - V3(float(ix), float(iy), float(iz));
+	float v000, v100, v010, v110, v001, v101, v011, v111;
+	if ((ix & 7) != 7 && (iy & 7) != 7 && (iz & 7) != 7 && ix + 1 < v.W && iy + 1 < v.H && iz + 1 < v.D) {
+		// all eight voxels live in one brick: one table lookup, four 8-byte row segments
+		int b = __ldg(v.table + ((iz >> 3) * v.by + (iy >> 3)) * v.bx + (ix >> 3));
+		if (b < 0) return 0.0f * (1.0f - d.z) + 0.0f * d.z;
+		const float* p = v.pool + size_t(b) * BRICK_VOX + ((iz & 7) << 6) + ((iy & 7) << 3) + (ix & 7);
+		v000 = __ldg(p); v100 = __ldg(p + 1);
+		v010 = __ldg(p + 8); v110 = __ldg(p + 9);
+		v001 = __ldg(p + 64); v101 = __ldg(p + 65);
+		v011 = __ldg(p + 72); v111 = __ldg(p + 73);
+	} else {
+		v000 = voxel(v, ix, iy, iz); v100 = voxel(v, ix + 1, iy, iz);
+		v010 = voxel(v, ix, iy + 1, iz); v110 = voxel(v, ix + 1, iy + 1, iz);
+		v001 = voxel(v, ix, iy, iz + 1); v101 = voxel(v, ix + 1, iy, iz + 1);
+		v011 = voxel(v, ix, iy + 1, iz + 1); v111 = voxel(v, ix + 1, iy + 1, iz + 1);
+	}
+	float d00 = gmix(v000, v100, d.x), d10 = gmix(v010, v110, d.x), d01 = gmix(v001, v101, d.x), d11 = gmix(v011, v111, d.x);
+	float d0 = gmix(d00, d10, d.y), d1 = gmix(d01, d11, d.y);
+	return gmix(d0, d1, d.z);
+}
+NE_D V3 ocs_to_gcs(const DVolume& v, V3 p) { return (p + V3(0.5f)) * V3(float(v.W), float(v.H), float(v.D)); }
+NE_D float density_at(const DVolume& v, const Ray& rayO, float t) { return interpolated_density(v, ocs_to_gcs(v, rayO.at(t))); }
+
+// Brick DDA over the ray segment [0, tFar] of an OCS ray (origin already moved to the segment start).
+struct BrickDDA {
+	int bx, by, bz;       // current brick
+	int sx, sy, sz;       // step direction
+	float nx, ny, nz;     // ray parameter of the next boundary crossing per axis
+	float dx, dy, dz;     // parameter distance between crossings per axis
+	NE_D void init(const DVolume& v, const Ray& r) {
+		V3 g = ocs_to_gcs(v, r.o);
+		V3 res(float(v.W), float(v.H), float(v.D));
+		V3 gd = r.d * res;  // d(grid coord)/dt
+		float fx = g.x * 0.125f, fy = g.y * 0.125f, fz = g.z * 0.125f;
+		bx = min(max(int(floorf(fx)), 0), v.bx - 1);
+		by = min(max(int(floorf(fy)), 0), v.by - 1);
+		bz = min(max(int(floorf(fz)), 0), v.bz - 1);
+		sx = gd.x > 0 ? 1 : -1; sy = gd.y > 0 ? 1 : -1; sz = gd.z > 0 ? 1 : -1;
+		dx = gd.x != 0 ? 8.0f / fabsf(gd.x) : INFINITY;
+		dy = gd.y != 0 ? 8.0f / fabsf(gd.y) : INFINITY;
+		dz = gd.z != 0 ? 8.0f / fabsf(gd.z) : INFINITY;
+		nx = gd.x != 0 ? (float((gd.x > 0 ? bx + 1 : bx) * 8) - g.x) / gd.x : INFINITY;
+		ny = gd.y != 0 ? (float((gd.y > 0 ? by + 1 : by) * 8) - g.y) / gd.y : INFINITY;
+		nz = gd.z != 0 ? (float((gd.z > 0 ? bz + 1 : bz) * 8) - g.z) / gd.z : INFINITY;
+	}
+	NE_D float exit_t() const { return fminf(nx, fminf(ny, nz)); }
+	// advance to the next brick; false when the walk leaves the table
+	NE_D bool step(const DVolume& v) {
+		if (nx <= ny && nx <= nz) { bx += sx; nx += dx; return bx >= 0 && bx < v.bx; }
+		if (ny <= nz) { by += sy; ny += dy; return by >= 0 && by < v.by; }
+		bz += sz; nz += dz; return bz >= 0 && bz < v.bz;
+	}
+	NE_D float majorant(const DVolume& v) const { return __ldg(v.bmaj + (bz * v.by + by) * v.bx + bx); }
+};
+
+// GridMedia::Tr. rayW: WCS ray; tNear/tFar from the hit record. Returns the scalar transmittance.
+template <class R, bool BRICKMAJ>
+NE_D float grid_tr(const DInstance& in, const DMaterial& m, const DVolume& v, Ray rayW, float tNear, float tFar, R& rng, Stats& st) {
+	Ray ray = transform_ray(rayW, in.Mi);
+	ray.o = ray.at(tNear);
+	tFar = tFar - tNear;
+	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+	float sig = avg(ext * m.density_mult);
+	float Tr = 1, t = 0;
+	if (!BRICKMAJ) {
+		while (true) {
+			t -= logf(1 - rng.next()) * v.inv_max_density / sig;
+			if (t >= tFar) break;
+			st.ratio_steps++;
+			float density = density_at(v, ray, t);
+			Tr *= 1 - fmaxf(0.0f, density * v.inv_max_density);
+			const float rrThreshold = .1f;
+			if (Tr < rrThreshold) {
+				float q = fmaxf(0.05f, 1.0f - Tr);
+				if (rng.next() < q) return 0.0f;
+				Tr /= 1 - q;
+			}
+		}
+		return Tr;
+	}
+	BrickDDA dda;
+	dda.init(v, ray);
+	while (true) {
+		st.brick_visits++;
+		float tExit = fminf(dda.exit_t(), tFar);
+		float maj = dda.majorant(v);
+		if (maj > 0) {
+			float invMaj = 1.0f / maj;
+			float step = invMaj / sig;
+			while (true) {
+				t -= logf(1 - rng.next()) * step;
+				if (t >= tExit) break;
+				st.ratio_steps++;
+				float density = density_at(v, ray, t);
+				Tr *= 1 - fmaxf(0.0f, density * invMaj);
+				if (Tr < .1f) {
+					float q = fmaxf(0.05f, 1.0f - Tr);
+					if (rng.next() < q) return 0.0f;
+					Tr /= 1 - q;
+				}
+			}
+		}
+		t = tExit;
+		if (tExit >= tFar) break;
+		if (!dda.step(v)) break;
+	}
+	return Tr;
+}
+
+// GridMedia::sample. In Li `incoming` already has its origin at the segment start and tNear = 0.
+// Returns the value the reference returns: sigma_s/sigma_t on a collision, exactly (1,1,1) on escape (Q1, Q1b).
+template <class R, bool BRICKMAJ>
+NE_D V3 grid_sample(const DScene& s, const DInstance& in, const DMaterial& m, const DVolume& v, Ray incomingW, float tNear, float tFar,
+                    const Hit& isect, Ray& scattered, R& rng, Stats& st) {
+	scattered = incomingW;
+	Ray ray = transform_ray(incomingW, in.Mi);
+	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
+	float sig = avg(ext * m.density_mult);
+	float t = tNear;  // GridMedia.cpp:79; Li always passes 0 (the brick walk below relies on that)
+	bool collided = false;
+	if (!BRICKMAJ) {
+		while (true) {
+			float r = rng.next();
+			float sampledDist = logf(1 - r) * v.inv_max_density / sig;
+			t -= sampledDist;
+			if (t >= tFar) break;
+			st.delta_steps++;
+			float density = density_at(v, ray, t);
+			float ra = rng.next();
+			if (density * v.inv_max_density > ra) { collided = true; break; }
+		}
+	} else {
+		BrickDDA dda;
+		dda.init(v, ray);
+		while (true) {
+			st.brick_visits++;
+			float tExit = fminf(dda.exit_t(), tFar);
+			float maj = dda.majorant(v);
+			if (maj > 0) {
+				float invMaj = 1.0f / maj;
+				float step = invMaj / sig;
+				while (true) {
+					t -= logf(1 - rng.next()) * step;
+					if (t >= tExit) break;
+					st.delta_steps++;
+					float density = density_at(v, ray, t);
+					if (density * invMaj > rng.next()) { collided = true; break; }
+				}
+				if (collided) break;
+			}
+			t = tExit;
+			if (tExit >= tFar) break;
+			if (!dda.step(v)) break;
+		}
+	}
+	if (!collided) return V3(1.0f);
+	st.scatter_events++;
+	Ray so;
+	so.o = ray.at(t);
+	so.d = bsdf_sample(s, m, ray.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // Q19: about +Y of the OCS, ignores the incoming direction
+	scattered = transform_ray(so, in.M);                                 // direction keeps the instance scale
+	return sc / ext;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Emitter primitives: samplePointOnSurface / pdf of Rectangle (Rectangle.cpp:78-88,159-171), Sphere
+// (Sphere.cpp:46-52,58-68), Point (Point.cpp:14-26). `prim` = the primitive Light::primitive points at (Q7),
+// `li` = the chosen light instance (its transform and scale are used).
+// ---------------------------------------------------------------------------------------------------------------
+template <class R>
+NE_D V3 light_sample_point(const DInstance& prim, const DInstance& li, const Hit& isect, R& rng) {
+	if (prim.type == PRIM_RECTANGLE) {
+		float e2 = rng.next(), e1 = rng.next(), e0 = rng.next();  // vec3(random(),random(),random()) right to left
+		V3 p(-0.5f + 1.0f * e0, -0.5f + 1.0f * e1, 0.0f + 0.0f * e2);
+		return xform_point(li.M, p);
+	}
+	if (prim.type == PRIM_SPHERE) {
+		V3 c = xform_point(li.M, V3(0.0f, 0.0f, 0.0f));
+		V3 n = normalize(isect.p - c);
+		return c + n * prim.radius;
+	}
+	return xform_point(li.M, V3(prim.point[0], prim.point[1], prim.point[2]));
+}
+template <class R>
+NE_D float light_pdf(const DInstance& prim, const DInstance& li, const Hit& isect, R& rng) {
+	if (prim.type == PRIM_RECTANGLE) {
+		V3 sizeW = V3(li.scale[0], li.scale[1], li.scale[2]) * V3(1.0f, 1.0f, 0.0f);
+		float area = 1;
+		if (sizeW.x != 0) area = area * sizeW.x;
+		if (sizeW.y != 0) area = area * sizeW.y;
+		if (sizeW.z != 0) area = area * sizeW.z;
+		return area_to_solid_angle(1.0f / area, isect.n, isect.p, light_sample_point(prim, li, isect, rng));  // Q10, Q11
+	}
+	if (prim.type == PRIM_SPHERE) {
+		float pdfArea = float(double(1.0f / 4.0f) * NE_PI * double(prim.radius) * double(prim.radius));  // Q13
+		return area_to_solid_angle(pdfArea, isect.n, isect.p, light_sample_point(prim, li, isect, rng));
+	}
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// VolumetricPathIntegrator (integrators/VolumetricPathIntegrator.cpp)
+// ---------------------------------------------------------------------------------------------------------------
+#define NE_MAX_TR_SEGMENTS 64  // guard: the reference's intersectTr can loop forever (DESIGN.md "Deviations")
+
+// visibilityTr :34-72 — 1 if nothing or an emitter is hit first, else 0 (Q8, Q9).
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D float visibility_tr(const DScene& s, V3 p, V3 lightPoint, R& rng, Stats& st) {
+	Ray ray;
+	ray.o = p;
+	ray.d = lightPoint - p;
+	Hit h;
+	st.shadow_rays++;
+	bool hitSurface = intersect_scene(s, ray, h, float(NE_EPSILON3), INFINITY, st);
+	if (!hitSurface) return 1.0f;
+	int mi = s.inst[h.inst].material;
+	if (mi < 0) return 0.0f;
+	const DMaterial& m = s.mat[mi];
+	if (m.has_light) return 1.0f;
+	if (FAITHFUL && m.has_medium && m.volume >= 0)
+		(void)grid_tr<R, BRICKMAJ>(s.inst[h.inst], m, s.vol[m.volume], ray, h.tNear, h.tFar, rng, st);  // computed, then discarded by `return 0`
+	return 0.0f;
+}
+
+// intersectTr :10-32 — marches THROUGH non-medium surfaces until a medium (true, Tr) or nothing (false) (Q12).
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D bool intersect_tr(const DScene& s, Ray ray, float& Tr, R& rng, Stats& st) {
+	Tr = 1.0f;
+	if (!FAITHFUL && !s.has_medium) return false;  // can only return true through a medium
+	for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
+		Hit h;
+		st.shadow_rays++;
+		bool hitSurface = intersect_scene(s, ray, h, float(NE_EPSILON3), INFINITY, st);
+		if (!hitSurface) return false;
+		int mi = s.inst[h.inst].material;
+		if (mi >= 0 && s.mat[mi].has_medium && s.mat[mi].volume >= 0) {
+			Tr *= grid_tr<R, BRICKMAJ>(s.inst[h.inst], s.mat[mi], s.vol[s.mat[mi].volume], ray, h.tNear, h.tFar, rng, st);
+			return true;
+		}
+		ray.o = h.p;
+	}
+	return false;
+}
+
+// estimateDirect :74-157. `lightIdx` = fold index of the chosen light instance.
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D V3 estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int lightIdx, R& rng, Stats& st) {
+	V3 Ld(0.0f);
+	const DInstance& li = s.inst[lightIdx];
+	const DMaterial& lm = s.mat[li.material];
+	const DInstance& lprim = s.inst[lm.light_owner];
+	const DMaterial& m = s.mat[s.inst[isect.inst].material];
+	V3 Lrad(lm.li[0], lm.li[1], lm.li[2]);
+
+	// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
+	V3 A = light_sample_point(lprim, li, isect, rng);
+	Ray wo;
+	wo.o = isect.p;
+	wo.d = normalize(A - wo.o);
+	float lightPdf = light_pdf(lprim, li, isect, rng);
+	V3 Li = Lrad;
+	V3 f(0.0f);
+	float scatteringPdf = 0;
+	bool isSurface = !m.has_medium;
+
+	if (lightPdf > 0 && !is_black(Li)) {
+		if (isSurface) {
+			f = bsdf_eval(s, m, incoming.d, wo.d, isect) * fabsf(dot(wo.d, isect.n));
+			scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
+		} else {
+			f = bsdf_eval(s, m, incoming.d, wo.d, isect);
+			scatteringPdf = f.x;
+		}
+		if (!is_black(f)) {
+			V3 C = light_sample_point(lprim, li, isect, rng);
+			Li = Li * visibility_tr<R, FAITHFUL, BRICKMAJ>(s, isect.p, C, rng, st);
+			if (!is_black(Li)) {
+				float weight = power_heuristic(lightPdf, scatteringPdf);
+				Ld = Ld + f * Li * weight / lightPdf;
+			}
+		}
+	}
+
+	if (isSurface) {
+		wo.d = bsdf_sample(s, m, incoming.d, isect.n, isect, rng);
+		f = bsdf_eval(s, m, incoming.d, wo.d, isect);
+		f = f * fabsf(dot(wo.d, isect.n));
+		scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
+	} else {
+		f = bsdf_eval(s, m, incoming.d, wo.d, isect);  // Q18: f for the light-half direction ...
+		wo.d = bsdf_sample(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
+		scatteringPdf = f.x;
+	}
+
+	if (!is_black(f) && scatteringPdf > 0) {
+		lightPdf = light_pdf(lprim, li, isect, rng);
+		if (lightPdf == 0) return Ld;
+		float weight = power_heuristic(scatteringPdf, lightPdf);
+		Ray ray;
+		ray.o = isect.p;
+		ray.d = wo.d;
+		float Tr;
+		bool found = intersect_tr<R, FAITHFUL, BRICKMAJ>(s, ray, Tr, rng, st);
+		V3 Li2 = found ? Lrad : V3(0.0f);
+		if (!is_black(Li2)) Ld = Ld + f * Li2 * V3(Tr) * weight / scatteringPdf;
+	}
+	return Ld;
+}
+
+// uniformSampleOneLight :159-174
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng, Stats& st) {
+	float r = rng.next();
+	if (s.n_lights == 0) return V3(0.0f);  // the reference throws std::out_of_range here
+	int i = int(float(s.n_lights) * r);
+	float lightPdf = 1.0f / float(s.n_lights);
+	(void)rng.next();  // Model::getRandomLightPrimitive (Model.cpp:478-485), result used for the null check
+	(void)rng.next();  // second getRandomLightPrimitive call
+	return estimate_direct<R, FAITHFUL, BRICKMAJ>(s, incoming, isect, s.n_models + i, rng, st) / lightPdf;
+}
+
+// Li :176-301
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D V3 li_path(const DScene& s, Ray incoming, int bounces, R& rng, Stats& st) {
+	V3 L(0.0f), T(1.0f);
+	Hit isect;
+	int guard = 0;
+	for (int b = 0; b < bounces; b++) {
+		st.extend_rays++;
+		bool did = intersect_scene(s, incoming, isect, float(NE_EPSILON12), INFINITY, st);
+		if (is_black(T)) break;
+		int mi = did ? s.inst[isect.inst].material : -1;
+		if (did && mi >= 0 && s.mat[mi].has_bsdf && s.mat[mi].transmissive) {
+			const DMaterial& m = s.mat[mi];
+			const DInstance& in = s.inst[isect.inst];
+			incoming.o = incoming.at(isect.tNear);
+			isect.tFar = isect.tFar - isect.tNear;
+			isect.tNear = 0;
+			Ray scattered;
+			V3 a = grid_sample<R, BRICKMAJ>(s, in, m, s.vol[m.volume], incoming, 0.0f, isect.tFar, isect, scattered, rng, st);
+			if (all_one(a)) {  // Q1: escape detected by value, does not consume a bounce
+				incoming.o = incoming.at(isect.tFar + 0.01f);
+				b--;
+				if (++guard > 4096) break;  // the reference has no bound here (DESIGN.md "Deviations")
+				continue;
+			}
+			T = T * a;
+			V3 phaseFr = bsdf_eval(s, m, incoming.d, scattered.d, isect);
+			float phasePdf = bsdf_pdf(s, m, incoming.d, scattered.d, isect.n, isect);
+			if (is_black(phaseFr) || phasePdf == 0.f) break;
+			V3 lightSample = sample_one_light<R, FAITHFUL, BRICKMAJ>(s, scattered, isect, rng, st);  // Q2
+			T = T * (phaseFr / phasePdf);
+			L = L + T * lightSample;
+			incoming = scattered;
+		} else {
+			if (b == 0) {
+				if (did && mi >= 0 && s.mat[mi].has_light) {
+					const DMaterial& m = s.mat[mi];
+					L = L + T * V3(m.li[0], m.li[1], m.li[2]);
+				}
+				// else: sum of Light::Le over all lights = 0 for DiffuseLight (lights/Light.h:20-22)
+			}
+			if (!did || mi < 0 || !s.mat[mi].has_bsdf) break;
+			const DMaterial& m = s.mat[mi];
+			st.surface_events++;
+			L = L + T * sample_one_light<R, FAITHFUL, BRICKMAJ>(s, incoming, isect, rng, st);
+			Ray scattered;
+			scattered.o = isect.p;
+			scattered.d = bsdf_sample(s, m, incoming.d, isect.n, isect, rng);
+			float bsdfPdf = bsdf_pdf(s, m, incoming.d, scattered.d, isect.n, isect);
+			V3 fr = bsdf_eval(s, m, incoming.d, scattered.d, isect);
+			if (is_black(fr) || bsdfPdf == 0.f) break;
+			T = T * (fr * fabsf(dot(incoming.d, isect.n)) / bsdfPdf);  // Q5
+			incoming = scattered;
+		}
+	}
+	return L;
+}
+
+// Camera::getRayPassingThrough, core/Camera.cpp:140-144 + randomInUnitDisk, utils/Math.h:502-507
+template <class R>
+NE_D Ray camera_ray(const DCamera& c, float x, float y, R& rng) {
+	float theta = float(2.0 * NE_PI * double(rng.next()));
+	float r = sqrtf(rng.next());
+	V3 rd = c.lens_radius * (r * V3(cosf(theta), sinf(theta), 0.0f));
+	V3 offset = c.side * rd.x + c.up * rd.y;
+	Ray ray;
+	ray.o = c.position + offset;
+	ray.d = -normalize(c.lower_left + x * c.horizontal + y * c.vertical - c.position - offset);
+	return ray;
+}
+
+// OfflineEngine::postProcessing, core/OfflineEngine.cpp:39-52 (exposure 0.5, gamma 2.2, clamp)
+NE_D float tonemap1(float c) {
+	float m = 1.0f - expf(-c * 0.5f);
+	m = powf(m, 1.0f / 2.2f);
+	return gclamp(m, 0.0f, 1.0f);
+}
+
+}  // namespace ne

@@ -1,0 +1,62 @@
+// ne_rng.cuh — uniform sources for the estimator.
+//   TapeRng    replays an explicit uniform tape in the reference's draw order: what
+//              narvalengine::random() (src/utils/Math.h:59-66) returned after mt.seed(k). Test hooks only.
+//   PhiloxRng  Philox4x32-10 (Salmon et al., SC'11), counter-based: key = 64-bit seed, counter =
+//              (pixel, sample, dimension/4, 0). Any (pixel, sample) stream is reproducible on any GPU in any order.
+#pragma once
+#include "ne_math.cuh"
+
+namespace ne {
+
+struct TapeRng {
+	const float* tape;
+	int n, pos;
+	bool overflow;
+	NE_D void init(const float* t, int len) { tape = t; n = len; pos = 0; overflow = false; }
+	NE_D float next() {
+		if (pos >= n) { overflow = true; return 0.5f; }
+		return tape[pos++];
+	}
+};
+
+NE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+	const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+	for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+		uint32_t hi0 = __umulhi(M0, c0), hi1 = __umulhi(M1, c2);
+#else
+		uint32_t hi0 = uint32_t((uint64_t(M0) * c0) >> 32), hi1 = uint32_t((uint64_t(M1) * c2) >> 32);
+#endif
+		uint32_t lo0 = M0 * c0, lo1 = M1 * c2;
+		uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+		c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+		k0 += W0; k1 += W1;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+NE_HD float u32_to_unit(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f); }  // [0, 1 - 2^-24]
+
+struct PhiloxRng {
+	uint32_t k0, k1, pixel, sample, dim;
+	uint32_t b0, b1, b2, b3;
+	NE_D void init(uint64_t seed, uint32_t px, uint32_t smp, uint32_t dimension = 0) {
+		k0 = uint32_t(seed); k1 = uint32_t(seed >> 32); pixel = px; sample = smp; dim = dimension;
+		if (dim & 3) refill();
+	}
+	NE_D void refill() {
+		uint32_t o[4];
+		philox4x32_10(pixel, sample, dim >> 2, 0u, k0, k1, o);
+		b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+	}
+	NE_D float next() {
+		uint32_t l = dim & 3;
+		if (l == 0) refill();
+		dim++;
+		uint32_t x = l == 0 ? b0 : (l == 1 ? b1 : (l == 2 ? b2 : b3));
+		return u32_to_unit(x);
+	}
+};
+
+}  // namespace ne

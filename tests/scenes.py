@@ -51,3 +51,172 @@ def s2_volume(transform_fn=None, leaves=False):
     b.add_volume("cloud", (0, 1, 0), (0, 0, 0), (2, 2, 2))
     b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
     return b
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Synthetic data of the shapes BASELINE.json names
+# ---------------------------------------------------------------------------------------------------------------
+def fbm_noise(res, seed=1337, base=4, octaves=5):
+    """Deterministic value-noise fBm in [0,1], array indexed [z,y,x]. (BASELINE config 2 says "fastnoise-generated";
+    FastNoise lives in the reference's includes/ and is unused by its hot path, so the density field is generated
+    here with the same character: 5 octaves, base frequency 4 cells across the volume.)"""
+    from scipy.ndimage import zoom
+    W, H, D = res
+    rng = np.random.default_rng(seed)
+    out = np.zeros((D, H, W), np.float32)
+    amp, tot, f = 1.0, 0.0, base
+    for _ in range(octaves):
+        lat = rng.uniform(0, 1, (f + 1, f + 1, f + 1)).astype(np.float32)
+        up = zoom(lat, (D / (f + 1), H / (f + 1), W / (f + 1)), order=1, mode="nearest", grid_mode=True)
+        out += amp * up[:D, :H, :W]
+        tot += amp
+        amp *= 0.5
+        f *= 2
+    return out / tot
+
+
+def cloud_density(res, seed=1337, threshold=0.45):
+    """fBm remapped to a sparse density in [0,1] with a radial falloff (config 2 shape: dense core, empty rim)."""
+    W, H, D = res
+    n = fbm_noise(res, seed)
+    z, y, x = np.meshgrid(np.linspace(-.5, .5, D), np.linspace(-.5, .5, H), np.linspace(-.5, .5, W), indexing="ij")
+    r = np.sqrt(x * x + y * y + z * z)
+    t = np.clip((0.5 - r) / 0.15, 0, 1)
+    fall = t * t * (3 - 2 * t)
+    g = np.maximum(0, n - threshold) / (1 - threshold) * fall
+    g = g / max(g.max(), 1e-9)
+    return g.astype(np.float32)
+
+
+def dense_to_leaves(grid):
+    """Split a [z,y,x] grid into the 8^3 leaves an OpenVDB leaf iterator would yield (inactive = all-zero omitted)."""
+    D, H, W = grid.shape
+    pd, ph, pw = (-D) % 8, (-H) % 8, (-W) % 8
+    g = np.pad(grid, ((0, pd), (0, ph), (0, pw)))
+    bz, by, bx = g.shape[0] // 8, g.shape[1] // 8, g.shape[2] // 8
+    blocks = g.reshape(bz, 8, by, 8, bx, 8).transpose(0, 2, 4, 1, 3, 5).reshape(-1, 8, 8, 8)
+    iz, iy, ix = np.meshgrid(np.arange(bz), np.arange(by), np.arange(bx), indexing="ij")
+    origins = np.stack([ix.ravel() * 8, iy.ravel() * 8, iz.ravel() * 8], 1).astype(np.int32)
+    act = blocks.reshape(len(blocks), -1).any(axis=1)
+    return origins[act], np.ascontiguousarray(blocks[act])
+
+
+def s2_volume(transform_fn=None, leaves=False, phase="hg", g=0.0):  # noqa: F811  (extends the definition above)
+    b = SceneBuilder(transform_fn)
+    if leaves:
+        v = np.zeros((1, 8, 8, 8), np.float32)
+        v[0, :4, :4, :4] = s2_grid()
+        vol = b.add_volume_leaves((4, 4, 4), [[0, 0, 0]], v)
+    else:
+        vol = b.add_volume_dense(s2_grid())
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 3.0, vol, phase, g)
+    b.add_emitter("light", (400, 400, 400))
+    b.add_volume("cloud", (0, 1, 0), (0, 0, 0), (2, 2, 2))
+    b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
+    return b
+
+
+def noise_volume_scene(res=(64, 64, 64), leaves=False, density=100.0, light="point", scale=(2.4, 2.4, 2.4), pos=(0, 1, 0),
+                       li=(100, 100, 70), transform_fn=None, grid=None, g=0.0):
+    """Config-2 shape (resources/scenes/volumes.json): one heterogeneous grid volume + one emitter."""
+    b = SceneBuilder(transform_fn)
+    grid = cloud_density(res) if grid is None else grid
+    if leaves:
+        o, v = dense_to_leaves(grid)
+        vol = b.add_volume_leaves(res, o, v)
+    else:
+        vol = b.add_volume_dense(grid)
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), density, vol, "hg", g)
+    b.add_emitter("light", li)
+    b.add_volume("cloud", pos, (0, 0, 0), scale)
+    if light == "point":
+        b.add_point("light", (0, 6, 0))
+    else:
+        b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1.5, 1.5, 1))
+    return b
+
+
+def displaced_grid(n, size=4.0, amp=0.35, seed=11):
+    """n x n quads (2 n^2 triangles) displaced by fBm: the config-4 mesh shape at any size."""
+    from scipy.ndimage import zoom
+    rng = np.random.default_rng(seed)
+    h = np.zeros((n + 1, n + 1), np.float32)
+    a, f = 1.0, 4
+    while f <= max(4, n):
+        lat = rng.uniform(-1, 1, (f + 1, f + 1)).astype(np.float32)
+        h += a * zoom(lat, ((n + 1) / (f + 1),) * 2, order=1, mode="nearest", grid_mode=True)[:n + 1, :n + 1]
+        a *= 0.5
+        f *= 2
+        if a < 0.02:
+            break
+    xs = np.linspace(-size / 2, size / 2, n + 1, dtype=np.float32)
+    X, Z = np.meshgrid(xs, xs, indexing="xy")
+    pos = np.stack([X, amp * h, Z], -1).reshape(-1, 3).astype(np.float32)
+    uv = np.stack([(X / size + .5), (Z / size + .5)], -1).reshape(-1, 2).astype(np.float32)
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    v00 = (j * (n + 1) + i).ravel()
+    v10, v01, v11 = v00 + 1, v00 + n + 1, v00 + n + 2
+    # wound so that the geometric normal cross(v1-v0, v2-v0) points up (+y)
+    idx = np.stack([np.stack([v00, v01, v10], 1), np.stack([v10, v01, v11], 1)], 1).reshape(-1, 3).astype(np.uint32)
+    return pos, idx, uv
+
+
+def mesh_scene(n=64, transform_fn=None, roughness=0.6, li=(60, 60, 60)):
+    """Config-4 shape: a displaced-grid OBJ-style mesh with one GGX material and two rectangle area lights."""
+    b = SceneBuilder(transform_fn)
+    b.add_microfacet("mesh", (.7, .6, .5), roughness, 0.0)
+    b.add_emitter("light", li)
+    pos, idx, uv = displaced_grid(n)
+    b.add_mesh("mesh", pos, idx, uv, pos=(0, 0, 0))
+    b.add_rectangle("light", (-1, 3.5, 0), (-90, 0, 0), (1.5, 1.5, 1))
+    b.add_rectangle("light", (1.5, 3.0, 1), (-70, 0, 20), (1, 1, 1))
+    return b
+
+
+MESH_CAMERA = CameraParams((0, 3.2, -4.2), (0, 0, 0), 45.0)
+
+
+def mixed_scene(sort_and_group=True, transform_fn=None, res=(32, 24, 40), mesh_n=24):
+    """Config-5 shape: mesh + rectangles + sphere light + sparse cloud volume (the volume deliberately FIRST in JSON
+    order so sort_and_group changes the fold)."""
+    b = SceneBuilder(transform_fn, sort_and_group=sort_and_group)
+    o, v = dense_to_leaves(cloud_density(res, seed=7))
+    vol = b.add_volume_leaves(res, o, v)
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 25.0, vol, "hg", 0.0)
+    b.add_microfacet("floor", (.8, .8, .8), 0.95, 0.0)
+    b.add_microfacet("mesh", (.7, .5, .3), 0.8, 0.1)
+    b.add_emitter("light", (300, 300, 260))
+    b.add_emitter("bulb", (800, 700, 500))
+    b.add_volume("cloud", (0, 1.6, 0.5), (0, 20, 0), (2.2, 1.4, 1.8))
+    b.add_rectangle("floor", (0, 0, 0), (90, 0, 0), (8, 8, 1))
+    b.add_rectangle("floor", (0, 2, 3), (0, 0, 0), (8, 6, 1))
+    pos, idx, uv = displaced_grid(mesh_n, size=3.0, amp=0.25)
+    b.add_mesh("mesh", pos, idx, uv, pos=(0, 0.3, 0))
+    b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
+    b.add_sphere("bulb", (2.3, 2.5, 0), 0.05)
+    return b
+
+
+MIXED_CAMERA = CameraParams((0, 2, -5), (0, 1.2, 0), 45.0)
+
+
+def textured_scene(transform_fn=None):
+    """A floor with an RGBA8 image albedo (mirror wrap, nearest texel) like cornellbox.json's checkboard.png."""
+    b = SceneBuilder(transform_fn)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    b.add_microfacet("tex", None, 0.7, 0.1, albedo_image=img)
+    b.add_emitter("light", (50, 50, 50))
+    b.add_rectangle("tex", (0, 0, 0), (90, 0, 0), (4, 4, 1))
+    b.add_rectangle("light", (0, 3, 0), (-90, 0, 0), (1, 1, 1))
+    return b
+
+
+def cornell_c1(transform_fn=None):
+    """BASELINE config 1: Cornell-box-style scene (cornellbox.json walls, GGX) + area emitter + a sphere. The sphere is
+    an EMITTER (as in resources/scenes/playground.json): the reference never terminates on a GGX sphere
+    (DESIGN.md "Deviations": intersectTr loops forever on the 'inside' self-hit, Model.cpp:418-424)."""
+    b = s1_cornell(transform_fn, with_sphere=False)
+    b.add_emitter("bulb", (200, 160, 120))
+    b.add_sphere("bulb", (.9, .8, .3), 0.15)
+    return b
