@@ -8,7 +8,7 @@
 #include <memory>
 
 #include "ne_ctx.h"
-#include "ne_device.cuh"
+#include "ne_integrator.cuh"
 #include "ne_host.h"
 
 using namespace ne;
@@ -259,7 +259,9 @@ __global__ void k_test_one_light(DScene s, int n, const float* dirs, const ne_b2
 	rng.init(tape + size_t(stride) * i, stride);
 	Stats st;
 	st.clear();
-	V3 v = sample_one_light<TapeRng, true, false>(s, in, h, rng, st);
+	ImmediateSink<TapeRng, true, false> sink;
+	sink.L = V3(0.0f);
+	V3 v = sample_one_light(s, in, h, rng, sink, 1u, st);
 	L[3 * i] = v.x; L[3 * i + 1] = v.y; L[3 * i + 2] = v.z;
 	if (used) used[i] = rng.overflow ? -1 : rng.pos;
 }

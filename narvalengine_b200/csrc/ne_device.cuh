@@ -145,8 +145,9 @@ NE_D bool sphere_intersect(Ray r, float radius, Hit& hit) {
 	float c = dot(oc, oc) - radius * radius;
 	float disc = b * b - a * c;
 	if (disc >= 0) {
-		float sq = sqrtf(disc);
-		float t1 = (-b - sq) / a, t2 = (-b + sq) / a;
+		// `sqrt(discriminant)` resolves to ::sqrt(double) in the reference build: roots are formed in double, then narrowed
+		double sq = sqrt(double(disc)), nb = double(-b), ad = double(a);
+		float t1 = float((nb - sq) / ad), t2 = float((nb + sq) / ad);
 		hit.tNear = gmin(t1, t2);
 		hit.tFar = gmax(t1, t2);
 		hit.p = r.at(hit.tNear);
@@ -187,7 +188,10 @@ NE_D V3 normal_from_map(V3 texNormal, V3 worldNormal) {
 // `<` keeps the first of equal hits) over OUR binned-SAH 2-wide BVH. Node boxes are tested with a conservative
 // slab test; every triangle test uses the reference arithmetic above.
 NE_D bool bvh_closest(const DMesh& m, Ray r, float& tBest, int& slotBest, Stats& st) {
-	const V3 inv = 1.0f / r.d;
+	// A zero direction component would give 0*inf = NaN for rays lying exactly in a box face; a huge finite reciprocal
+	// keeps the slab test inclusive there (the reference's one-triangle unit test hits at a vertex, tests.cpp:300-347).
+	const V3 inv(1.0f / (fabsf(r.d.x) > 1e-20f ? r.d.x : copysignf(1e-20f, r.d.x)), 1.0f / (fabsf(r.d.y) > 1e-20f ? r.d.y : copysignf(1e-20f, r.d.y)),
+	             1.0f / (fabsf(r.d.z) > 1e-20f ? r.d.z : copysignf(1e-20f, r.d.z)));
 	int stack[48];
 	int sp = 0;
 	int node = 0;
@@ -385,7 +389,11 @@ NE_D V3 ggx_sample_microfacet(float alpha, R& rng) {
 	float a2 = alpha * alpha;
 	float theta = acosf(gmin(1.0f, sqrtf((1.0f - rx) / gmax(float(NE_EPSILON), (rx * (a2 - 1.0f) + 1.0f)))));
 	float phi = float(NE_TWO_PI * double(ry));
-	return V3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+	// unqualified sin/cos resolve to the double overloads in the reference build; products are formed in double
+	double st, ct, sp, cp;
+	sincos(double(theta), &st, &ct);
+	sincos(double(phi), &sp, &cp);
+	return V3(float(st * cp), float(st * sp), float(ct));
 }
 
 NE_D float hg_eval(float g, V3 in, V3 out) {
@@ -683,191 +691,14 @@ NE_D float light_pdf(const DInstance& prim, const DInstance& li, const Hit& isec
 	return 1;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// VolumetricPathIntegrator (integrators/VolumetricPathIntegrator.cpp)
-// ---------------------------------------------------------------------------------------------------------------
-#define NE_MAX_TR_SEGMENTS 64  // guard: the reference's intersectTr can loop forever (DESIGN.md "Deviations")
-
-// visibilityTr :34-72 — 1 if nothing or an emitter is hit first, else 0 (Q8, Q9).
-template <class R, bool FAITHFUL, bool BRICKMAJ>
-NE_D float visibility_tr(const DScene& s, V3 p, V3 lightPoint, R& rng, Stats& st) {
-	Ray ray;
-	ray.o = p;
-	ray.d = lightPoint - p;
-	Hit h;
-	st.shadow_rays++;
-	bool hitSurface = intersect_scene(s, ray, h, float(NE_EPSILON3), INFINITY, st);
-	if (!hitSurface) return 1.0f;
-	int mi = s.inst[h.inst].material;
-	if (mi < 0) return 0.0f;
-	const DMaterial& m = s.mat[mi];
-	if (m.has_light) return 1.0f;
-	if (FAITHFUL && m.has_medium && m.volume >= 0)
-		(void)grid_tr<R, BRICKMAJ>(s.inst[h.inst], m, s.vol[m.volume], ray, h.tNear, h.tFar, rng, st);  // computed, then discarded by `return 0`
-	return 0.0f;
-}
-
-// intersectTr :10-32 — marches THROUGH non-medium surfaces until a medium (true, Tr) or nothing (false) (Q12).
-template <class R, bool FAITHFUL, bool BRICKMAJ>
-NE_D bool intersect_tr(const DScene& s, Ray ray, float& Tr, R& rng, Stats& st) {
-	Tr = 1.0f;
-	if (!FAITHFUL && !s.has_medium) return false;  // can only return true through a medium
-	for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
-		Hit h;
-		st.shadow_rays++;
-		bool hitSurface = intersect_scene(s, ray, h, float(NE_EPSILON3), INFINITY, st);
-		if (!hitSurface) return false;
-		int mi = s.inst[h.inst].material;
-		if (mi >= 0 && s.mat[mi].has_medium && s.mat[mi].volume >= 0) {
-			Tr *= grid_tr<R, BRICKMAJ>(s.inst[h.inst], s.mat[mi], s.vol[s.mat[mi].volume], ray, h.tNear, h.tFar, rng, st);
-			return true;
-		}
-		ray.o = h.p;
-	}
-	return false;
-}
-
-// estimateDirect :74-157. `lightIdx` = fold index of the chosen light instance.
-template <class R, bool FAITHFUL, bool BRICKMAJ>
-NE_D V3 estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int lightIdx, R& rng, Stats& st) {
-	V3 Ld(0.0f);
-	const DInstance& li = s.inst[lightIdx];
-	const DMaterial& lm = s.mat[li.material];
-	const DInstance& lprim = s.inst[lm.light_owner];
-	const DMaterial& m = s.mat[s.inst[isect.inst].material];
-	V3 Lrad(lm.li[0], lm.li[1], lm.li[2]);
-
-	// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
-	V3 A = light_sample_point(lprim, li, isect, rng);
-	Ray wo;
-	wo.o = isect.p;
-	wo.d = normalize(A - wo.o);
-	float lightPdf = light_pdf(lprim, li, isect, rng);
-	V3 Li = Lrad;
-	V3 f(0.0f);
-	float scatteringPdf = 0;
-	bool isSurface = !m.has_medium;
-
-	if (lightPdf > 0 && !is_black(Li)) {
-		if (isSurface) {
-			f = bsdf_eval(s, m, incoming.d, wo.d, isect) * fabsf(dot(wo.d, isect.n));
-			scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
-		} else {
-			f = bsdf_eval(s, m, incoming.d, wo.d, isect);
-			scatteringPdf = f.x;
-		}
-		if (!is_black(f)) {
-			V3 C = light_sample_point(lprim, li, isect, rng);
-			Li = Li * visibility_tr<R, FAITHFUL, BRICKMAJ>(s, isect.p, C, rng, st);
-			if (!is_black(Li)) {
-				float weight = power_heuristic(lightPdf, scatteringPdf);
-				Ld = Ld + f * Li * weight / lightPdf;
-			}
-		}
-	}
-
-	if (isSurface) {
-		wo.d = bsdf_sample(s, m, incoming.d, isect.n, isect, rng);
-		f = bsdf_eval(s, m, incoming.d, wo.d, isect);
-		f = f * fabsf(dot(wo.d, isect.n));
-		scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
-	} else {
-		f = bsdf_eval(s, m, incoming.d, wo.d, isect);  // Q18: f for the light-half direction ...
-		wo.d = bsdf_sample(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
-		scatteringPdf = f.x;
-	}
-
-	if (!is_black(f) && scatteringPdf > 0) {
-		lightPdf = light_pdf(lprim, li, isect, rng);
-		if (lightPdf == 0) return Ld;
-		float weight = power_heuristic(scatteringPdf, lightPdf);
-		Ray ray;
-		ray.o = isect.p;
-		ray.d = wo.d;
-		float Tr;
-		bool found = intersect_tr<R, FAITHFUL, BRICKMAJ>(s, ray, Tr, rng, st);
-		V3 Li2 = found ? Lrad : V3(0.0f);
-		if (!is_black(Li2)) Ld = Ld + f * Li2 * V3(Tr) * weight / scatteringPdf;
-	}
-	return Ld;
-}
-
-// uniformSampleOneLight :159-174
-template <class R, bool FAITHFUL, bool BRICKMAJ>
-NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng, Stats& st) {
-	float r = rng.next();
-	if (s.n_lights == 0) return V3(0.0f);  // the reference throws std::out_of_range here
-	int i = int(float(s.n_lights) * r);
-	float lightPdf = 1.0f / float(s.n_lights);
-	(void)rng.next();  // Model::getRandomLightPrimitive (Model.cpp:478-485), result used for the null check
-	(void)rng.next();  // second getRandomLightPrimitive call
-	return estimate_direct<R, FAITHFUL, BRICKMAJ>(s, incoming, isect, s.n_models + i, rng, st) / lightPdf;
-}
-
-// Li :176-301
-template <class R, bool FAITHFUL, bool BRICKMAJ>
-NE_D V3 li_path(const DScene& s, Ray incoming, int bounces, R& rng, Stats& st) {
-	V3 L(0.0f), T(1.0f);
-	Hit isect;
-	int guard = 0;
-	for (int b = 0; b < bounces; b++) {
-		st.extend_rays++;
-		bool did = intersect_scene(s, incoming, isect, float(NE_EPSILON12), INFINITY, st);
-		if (is_black(T)) break;
-		int mi = did ? s.inst[isect.inst].material : -1;
-		if (did && mi >= 0 && s.mat[mi].has_bsdf && s.mat[mi].transmissive) {
-			const DMaterial& m = s.mat[mi];
-			const DInstance& in = s.inst[isect.inst];
-			incoming.o = incoming.at(isect.tNear);
-			isect.tFar = isect.tFar - isect.tNear;
-			isect.tNear = 0;
-			Ray scattered;
-			V3 a = grid_sample<R, BRICKMAJ>(s, in, m, s.vol[m.volume], incoming, 0.0f, isect.tFar, isect, scattered, rng, st);
-			if (all_one(a)) {  // Q1: escape detected by value, does not consume a bounce
-				incoming.o = incoming.at(isect.tFar + 0.01f);
-				b--;
-				if (++guard > 4096) break;  // the reference has no bound here (DESIGN.md "Deviations")
-				continue;
-			}
-			T = T * a;
-			V3 phaseFr = bsdf_eval(s, m, incoming.d, scattered.d, isect);
-			float phasePdf = bsdf_pdf(s, m, incoming.d, scattered.d, isect.n, isect);
-			if (is_black(phaseFr) || phasePdf == 0.f) break;
-			V3 lightSample = sample_one_light<R, FAITHFUL, BRICKMAJ>(s, scattered, isect, rng, st);  // Q2
-			T = T * (phaseFr / phasePdf);
-			L = L + T * lightSample;
-			incoming = scattered;
-		} else {
-			if (b == 0) {
-				if (did && mi >= 0 && s.mat[mi].has_light) {
-					const DMaterial& m = s.mat[mi];
-					L = L + T * V3(m.li[0], m.li[1], m.li[2]);
-				}
-				// else: sum of Light::Le over all lights = 0 for DiffuseLight (lights/Light.h:20-22)
-			}
-			if (!did || mi < 0 || !s.mat[mi].has_bsdf) break;
-			const DMaterial& m = s.mat[mi];
-			st.surface_events++;
-			L = L + T * sample_one_light<R, FAITHFUL, BRICKMAJ>(s, incoming, isect, rng, st);
-			Ray scattered;
-			scattered.o = isect.p;
-			scattered.d = bsdf_sample(s, m, incoming.d, isect.n, isect, rng);
-			float bsdfPdf = bsdf_pdf(s, m, incoming.d, scattered.d, isect.n, isect);
-			V3 fr = bsdf_eval(s, m, incoming.d, scattered.d, isect);
-			if (is_black(fr) || bsdfPdf == 0.f) break;
-			T = T * (fr * fabsf(dot(incoming.d, isect.n)) / bsdfPdf);  // Q5
-			incoming = scattered;
-		}
-	}
-	return L;
-}
-
 // Camera::getRayPassingThrough, core/Camera.cpp:140-144 + randomInUnitDisk, utils/Math.h:502-507
 template <class R>
 NE_D Ray camera_ray(const DCamera& c, float x, float y, R& rng) {
 	float theta = float(2.0 * NE_PI * double(rng.next()));
 	float r = sqrtf(rng.next());
-	V3 rd = c.lens_radius * (r * V3(cosf(theta), sinf(theta), 0.0f));
+	double sn, cs;
+	sincos(double(theta), &sn, &cs);  // ::cos/::sin(double) in the reference build
+	V3 rd = c.lens_radius * (r * V3(float(cs), float(sn), 0.0f));
 	V3 offset = c.side * rd.x + c.up * rd.y;
 	Ray ray;
 	ray.o = c.position + offset;

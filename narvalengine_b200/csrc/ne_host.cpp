@@ -142,7 +142,7 @@ void host_camera_make(const float from[3], const float at[3], const float upv[3]
 	V3 lookFrom(from[0], from[1], from[2]), lookAt(at[0], at[1], at[2]), up(upv[0], upv[1], upv[2]);
 	float lensRadius = aperture / 2.0f;
 	const float rad = static_cast<float>(0.01745329251994329576923690768489);
-	float halfHeight = std::tan((vfov * rad) / 2.0f);
+	float halfHeight = float(::tan(double((vfov * rad) / 2.0f)));  // ::tan(double) in the reference build
 	float halfWidth = aspect * halfHeight;
 	V3 position = lookFrom;
 	V3 front = normalize(lookFrom - lookAt);

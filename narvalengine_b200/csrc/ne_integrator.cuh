@@ -1,0 +1,254 @@
+// ne_integrator.cuh — VolumetricPathIntegrator (integrators/VolumetricPathIntegrator.cpp) restated as STAGES so the
+// same code drives both executions:
+//   * one thread per path, start to finish (li_path: test hooks, megakernel A/B check) with an ImmediateSink that
+//     resolves every next-event query in place, and
+//   * the wavefront renderer (ne_wavefront.cu), whose QueueSink turns the two next-event queries of estimateDirect
+//     into shadow / transmittance requests that separate kernels resolve and splat.
+// Stage map:  classify_hit = Li :187-193 + :244-260 (emission, termination)
+//             shade_volume = Li :194-240          shade_surface = Li :262-283
+//             estimate_direct = :74-157           sample_one_light = :159-174
+//             visibility_tr = :34-72              intersect_tr = :10-32
+#pragma once
+#include "ne_device.cuh"
+
+namespace ne {
+
+#define NE_MAX_TR_SEGMENTS 64   // guard: the reference's intersectTr can loop forever (DESIGN.md "Deviations")
+#define NE_MAX_NULL_SEGMENTS 4096  // guard on Q1 escape/re-enter iterations (the reference has no bound)
+
+// visibilityTr :34-72 — 1 if nothing or an emitter is hit first, else 0 (Q8, Q9).
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D float visibility_tr(const DScene& s, V3 p, V3 lightPoint, R& rng, Stats& st) {
+	Ray ray;
+	ray.o = p;
+	ray.d = lightPoint - p;
+	Hit h;
+	st.shadow_rays++;
+	bool hitSurface = intersect_scene(s, ray, h, float(NE_EPSILON3), INFINITY, st);
+	if (!hitSurface) return 1.0f;
+	int mi = s.inst[h.inst].material;
+	if (mi < 0) return 0.0f;
+	const DMaterial& m = s.mat[mi];
+	if (m.has_light) return 1.0f;
+	if (FAITHFUL && m.has_medium && m.volume >= 0)
+		(void)grid_tr<R, BRICKMAJ>(s.inst[h.inst], m, s.vol[m.volume], ray, h.tNear, h.tFar, rng, st);  // computed, then discarded by `return 0`
+	return 0.0f;
+}
+
+// intersectTr :10-32 — marches THROUGH non-medium surfaces until a medium (true, Tr) or nothing (false) (Q12).
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D bool intersect_tr(const DScene& s, Ray ray, float& Tr, R& rng, Stats& st) {
+	Tr = 1.0f;
+	if (!FAITHFUL && !s.has_medium) return false;  // can only return true through a medium
+	for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
+		Hit h;
+		st.shadow_rays++;
+		bool hitSurface = intersect_scene(s, ray, h, float(NE_EPSILON3), INFINITY, st);
+		if (!hitSurface) return false;
+		int mi = s.inst[h.inst].material;
+		if (mi >= 0 && s.mat[mi].has_medium && s.mat[mi].volume >= 0) {
+			Tr *= grid_tr<R, BRICKMAJ>(s.inst[h.inst], s.mat[mi], s.vol[s.mat[mi].volume], ray, h.tNear, h.tFar, rng, st);
+			return true;
+		}
+		ray.o = h.p;
+	}
+	return false;
+}
+
+// Resolves next-event queries in place and sums Ld in the reference's order.
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+struct ImmediateSink {
+	V3 L;           // radiance of the path so far
+	V3 Ld;          // estimateDirect accumulator
+	V3 scale;       // unused here: the throughput a queueing sink folds into its requests
+	float sel_pdf;  // unused here: light-selection pdf
+	NE_D void begin() { Ld = V3(0.0f); }
+	NE_D void emit(V3 v) { L = L + v; }
+	// light half :100-112: Li *= visibilityTr(p, C); Ld += f * Li * weight / lightPdf
+	NE_D void light_term(const DScene& s, V3 p, V3 C, V3 f, V3 Li, float weight, float pdf, R& rng, Stats& st) {
+		Li = Li * visibility_tr<R, FAITHFUL, BRICKMAJ>(s, p, C, rng, st);
+		if (!is_black(Li)) Ld = Ld + f * Li * weight / pdf;
+	}
+	// BSDF half :132-153: Ld += f * Li * Tr * weight / scatteringPdf when intersectTr finds a medium
+	NE_D void bsdf_term(const DScene& s, Ray ray, V3 f, V3 Li, float weight, float pdf, R& rng, uint32_t stream, Stats& st) {
+		float Tr;
+		Fork<R> fork(rng, stream);
+		bool found = intersect_tr<R, FAITHFUL, BRICKMAJ>(s, ray, Tr, fork.get(), st);
+		V3 Li2 = found ? Li : V3(0.0f);
+		if (!is_black(Li2)) Ld = Ld + f * Li2 * V3(Tr) * weight / pdf;
+	}
+	// uniformSampleOneLight's return value (Ld / lightSelectionPdf), added by the caller as L += T * value
+	NE_D V3 end(float selPdf) { return Ld / selPdf; }
+};
+
+// estimateDirect :74-157. `lightIdx` = fold index of the chosen light instance; `stream` names the side stream of
+// the BSDF-half transmittance walk.
+template <class R, class SINK>
+NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int lightIdx, R& rng, SINK& sink, uint32_t stream, Stats& st) {
+	const DInstance& li = s.inst[lightIdx];
+	const DMaterial& lm = s.mat[li.material];
+	const DInstance& lprim = s.inst[lm.light_owner];
+	const DMaterial& m = s.mat[s.inst[isect.inst].material];
+	V3 Lrad(lm.li[0], lm.li[1], lm.li[2]);
+
+	// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
+	V3 A = light_sample_point(lprim, li, isect, rng);
+	Ray wo;
+	wo.o = isect.p;
+	wo.d = normalize(A - wo.o);
+	float lightPdf = light_pdf(lprim, li, isect, rng);
+	V3 Li = Lrad;
+	V3 f(0.0f);
+	float scatteringPdf = 0;
+	bool isSurface = !m.has_medium;
+
+	if (lightPdf > 0 && !is_black(Li)) {
+		if (isSurface) {
+			f = bsdf_eval(s, m, incoming.d, wo.d, isect) * fabsf(dot(wo.d, isect.n));
+			scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
+		} else {
+			f = bsdf_eval(s, m, incoming.d, wo.d, isect);
+			scatteringPdf = f.x;
+		}
+		if (!is_black(f)) {
+			V3 C = light_sample_point(lprim, li, isect, rng);
+			sink.light_term(s, isect.p, C, f, Li, power_heuristic(lightPdf, scatteringPdf), lightPdf, rng, st);
+		}
+	}
+
+	if (isSurface) {
+		wo.d = bsdf_sample(s, m, incoming.d, isect.n, isect, rng);
+		f = bsdf_eval(s, m, incoming.d, wo.d, isect);
+		f = f * fabsf(dot(wo.d, isect.n));
+		scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
+	} else {
+		f = bsdf_eval(s, m, incoming.d, wo.d, isect);                            // Q18: f for the light-half direction ...
+		wo.d = bsdf_sample(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
+		scatteringPdf = f.x;
+	}
+
+	if (!is_black(f) && scatteringPdf > 0) {
+		lightPdf = light_pdf(lprim, li, isect, rng);
+		if (lightPdf == 0) return;
+		float weight = power_heuristic(scatteringPdf, lightPdf);
+		Ray ray;
+		ray.o = isect.p;
+		ray.d = wo.d;
+		sink.bsdf_term(s, ray, f, Lrad, weight, scatteringPdf, rng, stream, st);
+	}
+}
+
+// uniformSampleOneLight :159-174. Returns what the caller must add as L += T * value (zero for queueing sinks,
+// which splat T * value later themselves).
+template <class R, class SINK>
+NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng, SINK& sink, uint32_t stream, Stats& st) {
+	float r = rng.next();
+	if (s.n_lights == 0) return V3(0.0f);  // the reference throws std::out_of_range here
+	int i = int(float(s.n_lights) * r);
+	float lightPdf = 1.0f / float(s.n_lights);
+	(void)rng.next();  // Model::getRandomLightPrimitive (Model.cpp:478-485), result used for the null check
+	(void)rng.next();  // second getRandomLightPrimitive call
+	sink.begin();
+	sink.sel_pdf = lightPdf;
+	estimate_direct(s, incoming, isect, s.n_models + i, rng, sink, stream, st);
+	return sink.end(lightPdf);
+}
+
+struct PathState {
+	Ray ray;
+	V3 T;
+	int bounce;
+	int guard;      // Q1 escape/re-enter count
+	uint32_t nee;   // number of uniformSampleOneLight calls so far (names the side streams)
+};
+enum { HIT_TERMINATE = 0, HIT_VOLUME = 1, HIT_SURFACE = 2 };
+enum { PATH_DONE = 0, PATH_NEXT_BOUNCE = 1, PATH_SAME_BOUNCE = 2 };
+
+// Li :187-193 and :244-260 — what happens right after intersectScene: throughput check, volume / surface split,
+// emission for camera rays (Q3), termination on miss / no BSDF.
+template <class SINK>
+NE_D int classify_hit(const DScene& s, bool did, const Hit& isect, const PathState& ps, SINK& sink) {
+	if (is_black(ps.T)) return HIT_TERMINATE;
+	int mi = did ? s.inst[isect.inst].material : -1;
+	if (did && mi >= 0 && s.mat[mi].has_bsdf && s.mat[mi].transmissive) return HIT_VOLUME;
+	if (ps.bounce == 0 && did && mi >= 0 && s.mat[mi].has_light) {
+		const DMaterial& m = s.mat[mi];
+		sink.emit(ps.T * V3(m.li[0], m.li[1], m.li[2]));
+	}
+	// else at bounce 0: sum of Light::Le over all lights = 0 for DiffuseLight (lights/Light.h:20-22)
+	if (!did || mi < 0 || !s.mat[mi].has_bsdf) return HIT_TERMINATE;
+	return HIT_SURFACE;
+}
+
+// Li :194-240 — the volume branch.
+template <class R, bool BRICKMAJ, class SINK>
+NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& sink, Stats& st) {
+	const DInstance& in = s.inst[isect.inst];
+	const DMaterial& m = s.mat[in.material];
+	ps.ray.o = ps.ray.at(isect.tNear);
+	isect.tFar = isect.tFar - isect.tNear;
+	isect.tNear = 0;
+	Ray scattered;
+	V3 a = grid_sample<R, BRICKMAJ>(s, in, m, s.vol[m.volume], ps.ray, 0.0f, isect.tFar, isect, scattered, rng, st);
+	if (all_one(a)) {  // Q1: escape detected by value, does not consume a bounce
+		ps.ray.o = ps.ray.at(isect.tFar + 0.01f);
+		if (++ps.guard > NE_MAX_NULL_SEGMENTS) return PATH_DONE;
+		return PATH_SAME_BOUNCE;
+	}
+	ps.T = ps.T * a;
+	V3 phaseFr = bsdf_eval(s, m, ps.ray.d, scattered.d, isect);
+	float phasePdf = bsdf_pdf(s, m, ps.ray.d, scattered.d, isect.n, isect);
+	if (is_black(phaseFr) || phasePdf == 0.f) return PATH_DONE;
+	V3 Tnew = ps.T * (phaseFr / phasePdf);
+	sink.scale = Tnew;  // L += T * lightSample happens AFTER the throughput update (:228-232)
+	V3 lightSample = sample_one_light(s, scattered, isect, rng, sink, 1u + ps.nee++, st);  // Q2
+	ps.T = Tnew;
+	sink.emit(ps.T * lightSample);
+	ps.ray = scattered;
+	return PATH_NEXT_BOUNCE;
+}
+
+// Li :262-283 — the surface branch.
+template <class R, class SINK>
+NE_D int shade_surface(const DScene& s, PathState& ps, const Hit& isect, R& rng, SINK& sink, Stats& st) {
+	const DMaterial& m = s.mat[s.inst[isect.inst].material];
+	st.surface_events++;
+	sink.scale = ps.T;
+	V3 ls = sample_one_light(s, ps.ray, isect, rng, sink, 1u + ps.nee++, st);
+	sink.emit(ps.T * ls);
+	Ray scattered;
+	scattered.o = isect.p;
+	scattered.d = bsdf_sample(s, m, ps.ray.d, isect.n, isect, rng);
+	float bsdfPdf = bsdf_pdf(s, m, ps.ray.d, scattered.d, isect.n, isect);
+	V3 fr = bsdf_eval(s, m, ps.ray.d, scattered.d, isect);
+	if (is_black(fr) || bsdfPdf == 0.f) return PATH_DONE;
+	ps.T = ps.T * (fr * fabsf(dot(ps.ray.d, isect.n)) / bsdfPdf);  // Q5
+	ps.ray = scattered;
+	return PATH_NEXT_BOUNCE;
+}
+
+// Li :176-301, one thread start to finish.
+template <class R, bool FAITHFUL, bool BRICKMAJ>
+NE_D V3 li_path(const DScene& s, Ray incoming, int bounces, R& rng, Stats& st) {
+	ImmediateSink<R, FAITHFUL, BRICKMAJ> sink;
+	sink.L = V3(0.0f);
+	PathState ps;
+	ps.ray = incoming;
+	ps.T = V3(1.0f);
+	ps.bounce = 0;
+	ps.guard = 0;
+	ps.nee = 0;
+	Hit isect;
+	while (ps.bounce < bounces) {
+		st.extend_rays++;
+		bool did = intersect_scene(s, ps.ray, isect, float(NE_EPSILON12), INFINITY, st);
+		int kind = classify_hit(s, did, isect, ps, sink);
+		if (kind == HIT_TERMINATE) break;
+		int next = kind == HIT_VOLUME ? shade_volume<R, BRICKMAJ>(s, ps, isect, rng, sink, st) : shade_surface<R>(s, ps, isect, rng, sink, st);
+		if (next == PATH_DONE) break;
+		if (next == PATH_NEXT_BOUNCE) ps.bounce++;
+	}
+	return sink.L;
+}
+
+}  // namespace ne

@@ -129,8 +129,13 @@ NE_HD float area_to_solid_angle(float pdfArea, V3 normal, V3 p1, V3 p2) {
 // sampleUnitSphere(e1, e2), src/utils/Math.h:442-457
 NE_HD V3 sample_unit_sphere(float e1, float e2) {
 	float theta = float(NE_TWO_PI * double(e1));
-	float phi = acosf(1.0f - 2.0f * e2);
-	return V3(sinf(phi) * cosf(theta), sinf(phi) * sinf(theta), cosf(phi));
+	// acos/sin/cos resolve to the double overloads in the reference build (Math.h is compiled without <math.h>'s
+	// float overloads in scope); phi is narrowed to float in between
+	float phi = float(acos(double(1.0f - 2.0f * e2)));
+	double sp, cp, st, ct;
+	sincos(double(phi), &sp, &cp);
+	sincos(double(theta), &st, &ct);
+	return V3(float(sp * ct), float(sp * st), float(cp));
 }
 
 }  // namespace ne

@@ -2,7 +2,7 @@
 //   TapeRng    replays an explicit uniform tape in the reference's draw order: what
 //              narvalengine::random() (src/utils/Math.h:59-66) returned after mt.seed(k). Test hooks only.
 //   PhiloxRng  Philox4x32-10 (Salmon et al., SC'11), counter-based: key = 64-bit seed, counter =
-//              (pixel, sample, dimension/4, 0). Any (pixel, sample) stream is reproducible on any GPU in any order.
+//              (pixel, sample, dimension/4, stream). Any (pixel, sample) stream is reproducible on any GPU in any order.
 #pragma once
 #include "ne_math.cuh"
 
@@ -39,15 +39,15 @@ NE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 NE_HD float u32_to_unit(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f); }  // [0, 1 - 2^-24]
 
 struct PhiloxRng {
-	uint32_t k0, k1, pixel, sample, dim;
+	uint32_t k0, k1, pixel, sample, dim, stream;
 	uint32_t b0, b1, b2, b3;
-	NE_D void init(uint64_t seed, uint32_t px, uint32_t smp, uint32_t dimension = 0) {
-		k0 = uint32_t(seed); k1 = uint32_t(seed >> 32); pixel = px; sample = smp; dim = dimension;
+	NE_D void init(uint64_t seed, uint32_t px, uint32_t smp, uint32_t dimension = 0, uint32_t strm = 0) {
+		k0 = uint32_t(seed); k1 = uint32_t(seed >> 32); pixel = px; sample = smp; dim = dimension; stream = strm;
 		if (dim & 3) refill();
 	}
 	NE_D void refill() {
 		uint32_t o[4];
-		philox4x32_10(pixel, sample, dim >> 2, 0u, k0, k1, o);
+		philox4x32_10(pixel, sample, dim >> 2, stream, k0, k1, o);
 		b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
 	}
 	NE_D float next() {
@@ -57,6 +57,25 @@ struct PhiloxRng {
 		uint32_t x = l == 0 ? b0 : (l == 1 ? b1 : (l == 2 ? b2 : b3));
 		return u32_to_unit(x);
 	}
+};
+
+// A side stream for work that is evaluated out of line (the transmittance walk of a next-event request runs in
+// its own wavefront kernel): Philox forks to counter word 3 = `stream`, dimension 0; a tape just continues.
+template <class R>
+struct Fork {
+	R& r;
+	NE_D Fork(R& base, uint32_t) : r(base) {}
+	NE_D R& get() { return r; }
+};
+template <>
+struct Fork<PhiloxRng> {
+	PhiloxRng f;
+	NE_D Fork(PhiloxRng& base, uint32_t stream) {
+		f = base;
+		f.stream = stream;
+		f.dim = 0;
+	}
+	NE_D PhiloxRng& get() { return f; }
 };
 
 }  // namespace ne

@@ -1,0 +1,37 @@
+"""Generates the committed golden fixtures from the ORACLE (the reference's own code, oracle/_ref). Run where
+/root/reference exists:  python tests/golden/make_golden.py [images]
+  image_<case>.npz : two independent converged oracle renders (different mt seeds per thread) of the test_gpu_render
+                     cases at equal spp -> parity target + oracle-vs-oracle noise floor.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import scenes  # noqa: E402
+from refclient import RefOracle  # noqa: E402
+
+SIZES = {"cornell": (24, 16, 16384), "volume": (24, 16, 8192), "mixed": (16, 12, 32768), "mesh": (24, 16, 8192)}
+
+
+def main():
+    from test_gpu_render import CASES
+    o = RefOracle()
+    nthreads = os.cpu_count() or 1
+    for name, (mk, cam) in CASES.items():
+        W, H, spp = SIZES[name]
+        sc = o.scene(mk(o.transform_fn()) if name in ("cornell", "mixed") and False else mk())
+        t = time.time()
+        a, _ = sc.render(cam, W, H, spp, 6, seed=1, threads=nthreads)
+        b, _ = sc.render(cam, W, H, spp, 6, seed=2, threads=nthreads)
+        np.savez_compressed(os.path.join(HERE, f"image_{name}.npz"), linear=a, linear_b=b, W=W, H=H, spp=spp)
+        from imgmetrics import rel_mse
+        print(name, W, H, spp, f"{time.time() - t:.1f}s mean {a.mean():.5f} floor {rel_mse(b, a):.3e}")
+
+
+if __name__ == "__main__":
+    main()

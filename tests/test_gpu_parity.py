@@ -29,7 +29,8 @@ def ctx():
 
 def close(a, b, rtol=RTOL, atol=1e-6):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.abs(a - b) <= atol + rtol * np.abs(b)
+    with np.errstate(invalid="ignore"):
+        return (np.abs(a - b) <= atol + rtol * np.abs(b)) | (np.isnan(a) & np.isnan(b)) | (a == b)
 
 
 def assert_close(a, b, rtol=RTOL, atol=1e-6, frac=1.0, what=""):
