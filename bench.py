@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — Mpaths/s of the path-tracing hot path on BASELINE.json's headline configuration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one heterogeneous 256^3 density volume (synthetic fBm cloud),
+sigma_s 1.1, sigma_a 0.01, HG g=0, density multiplier 100, scale 5 at the origin, point emitter, camera (0,0,-12) ->
+origin, vfov 45, 1920x1080, 64 spp, 6 bounces. One STEP = one whole frame (132.7 M camera paths) through the wavefront
+renderer. With N GPUs every rank holds a scene replica and renders 64 samples/pixel of its own sample-index range
+(weak scaling); the per-GPU fp32 accumulation buffers are summed onto rank 0 with one NCCL reduce inside the step.
+
+Printed JSON (rank 0, one line): see README / the driver contract. `value` = device-timed render (scene resident in
+HBM); `e2e` = the same frame through ne_b200_scene_upload + ne_b200_render_frame with HOST buffers (scene H2D, frame
+D2H inside the timed region); `roofline` = the volume-tracking kernels (delta tracking `k_wf_shade<volume>` + ratio
+tracking `k_wf_tr`), algorithmic bytes = 40 B per tracking step over their CUDA-event time;
+`cpu_baseline` = the reference's own integrator (oracle/_ref, thread-local RNG build) on this box's host cores over a
+bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+W, H, SPP, BOUNCES = 1920, 1080, 64, 6
+GRID = 256
+METRIC = "Mpaths/s (1080p, 64 spp, heterogeneous 256^3 volume + point light)"
+WORKLOAD = "C2: heterogeneous 256^3 density volume, delta tracking + point light, 1920x1080, 64 spp, 6 bounces"
+
+
+def build_scene(grid_res=GRID):
+    import scenes
+    t = time.time()
+    cache = os.path.join(ROOT, "build", f"bench_cloud_{grid_res}.npy")
+    if os.path.exists(cache):
+        grid = np.load(cache)
+    else:
+        grid = scenes.cloud_density((grid_res,) * 3, seed=1337)
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            np.save(cache, grid)
+        except OSError:
+            pass
+    b = scenes.noise_volume_scene(res=(grid_res,) * 3, density=100.0, light="point", scale=(5, 5, 5), pos=(0, 0, 0), li=(100, 100, 70),
+                                  grid=grid)
+    cam = scenes.CameraParams((0, 0, -12), (0, 0, 0), 45.0)
+    return b, cam, grid, time.time() - t
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def cpu_reference_run(builder, cam, budget_s, threads=None):
+    """The reference's own integrator on the host cores over a bounded, frame-covering sample of the workload:
+    every `row_step`-th row of the 1080p frame at `spp` samples. Returns (Mpaths/s, description, cores)."""
+    from refclient import RefOracle
+    oracle = RefOracle()
+    threads = threads or os.cpu_count() or 1
+    sc = oracle.scene(builder)
+    # pilot to size the sample: every 90th row (12 rows) x 1 spp
+    _, secs = sc.render(cam, W, H, 1, BOUNCES, seed=3, threads=threads, row_step=90)
+    rate = (len(range(0, H, 90)) * W) / max(secs, 1e-6)
+    target_paths = rate * budget_s
+    row_step = 18
+    rows = len(range(0, H, row_step))
+    spp = int(max(1, min(SPP, round(target_paths / (rows * W)))))
+    _, secs = sc.render(cam, W, H, spp, BOUNCES, seed=4, threads=threads, row_step=row_step)
+    paths = rows * W * spp
+    sc.close()
+    return paths / secs / 1e6, f"every {row_step}th row of the 1920x1080 frame ({rows} rows) x {spp} spp = {paths} paths in {secs:.1f} s", threads
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    b, cam, _, _ = build_scene()
+    vals, sample, cores = [], "", 0
+    for i in range(args.warmup + args.steps):
+        v, sample, cores = cpu_reference_run(b, cam, budget_s=args.ref_seconds)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per reference step / cpu_baseline sample")
+    ap.add_argument("--spp", type=int, default=SPP, help="debug only: a value other than 64 is not the headline configuration")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from narvalengine_b200.engine import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; narvalengine_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    spp = args.spp
+    b, cam_params, grid, t_scene = build_scene()
+    ctx = Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload(b)
+    cam = cam_params.make(W / H, ctx.lib)
+    ctx.set_camera(cam)
+    ctx.render(W, H, 0, 0, BOUNCES)  # allocate the accumulation buffer
+    ptr, nfloat, _ = ctx.accum_buffer()
+
+    class _Alias:  # the library's accumulation buffer as a torch tensor (for the NCCL reduce)
+        __cuda_array_interface__ = {"shape": (nfloat,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    accum = torch.as_tensor(_Alias(), device=f"cuda:{local_rank}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step(i):
+        """One frame: this rank's 64 samples per pixel (sample indices rank*spp ...), then the cross-GPU sum."""
+        ctx.clear()
+        ctx.render(W, H, rank * spp, (rank + 1) * spp, BOUNCES, seed=1 + i)
+        if world > 1:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                ctx.set_samples_accumulated(world * spp)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    ctx.counters_reset()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)  # L2 flush between timed iterations (outside the timed bracket)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step(args.warmup + i)
+        e1.record(stream)
+        sync_all()
+        ms.append(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    c = ctx.counters()
+    total_ms = float(sum(ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    paths_per_step = W * H * spp * world
+    value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- roofline of the volume-tracking kernels (this rank), live CUDA-event time inside the library
+    steps_tracked = int(c.delta_steps + c.ratio_steps)
+    alg_bytes = steps_tracked * int(c.bytes_per_tracking_step)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (c.ms_volume_kernel * 1e-3) / 1e9 if c.ms_volume_kernel > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+    launches_volume = max(1, int(c.wavefront_iterations) * 2)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_wf_shade<volume> (delta tracking) + k_wf_tr (ratio tracking)", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes / launches_volume, "tracking_steps_per_frame": steps_tracked / args.steps,
+                "kernel_ms_per_frame": c.ms_volume_kernel / args.steps,
+                "share_of_step": c.ms_volume_kernel / (c.ms_volume_kernel + c.ms_extend_kernel + c.ms_shade_kernel + 1e-9),
+                "Mrays_per_s": (c.extend_rays + c.shadow_rays) / (total_ms * 1e-3) / 1e6 * world}
+    gpu_launches = int(c.kernel_launches)
+
+    # ---- e2e: the reference-facing calls with HOST buffers (scene H2D + frame D2H inside the timed region)
+    e2e = None
+    if rank == 0 or world > 1:
+        tm = np.empty((H, W, 3), np.float32)
+        desc = b.desc()
+        h2d = int(grid.nbytes + 4096)
+        d2h = int(tm.nbytes)
+        ts = []
+        for i in range(2 + args.steps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            ctx.upload(desc)
+            if world == 1:
+                ctx.render_frame(cam, W, H, spp, BOUNCES, 100 + i, 0, tm, None)
+            else:
+                step(1000 + i)
+                if rank == 0:
+                    ctx.read_tonemapped(W, H, tm)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ts.append(time.perf_counter() - t0)
+        ts = ts[2:]
+        e2e_t = float(np.mean(ts))
+        if world > 1:
+            t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_t = float(t.item())
+        e2e = {"value": paths_per_step / e2e_t / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_t * 1e3, "includes": "ne_b200_scene_upload (brick build + H2D) + ne_b200_render_frame (render, resolve, D2H)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sample, cores = cpu_reference_run(b, cam_params, budget_s=args.ref_seconds)
+        cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample,
+               "note": "reference TUs compiled unmodified except a thread_local patch of the global mt19937 (oracle/Makefile)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [DEBUG spp={spp}]", "resolution": [W, H], "spp_per_gpu": spp,
+                           "bounces": BOUNCES, "grid": [GRID] * 3, "partition": f"sample-index x{world} + NCCL reduce" if world > 1 else "single GPU",
+                           "l2": "flushed between timed steps (256 MiB write)", "majorant": "per-brick (8^3) DDA", "pool_slots": 1 << 21},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+                "counters": {k: int(getattr(c, k)) for k in ("paths", "extend_rays", "shadow_rays", "delta_steps", "ratio_steps", "brick_visits",
+                                                              "scatter_events", "wavefront_iterations")},
+                "kernel_ms": {"volume": c.ms_volume_kernel, "extend_shadow": c.ms_extend_kernel, "surface": c.ms_shade_kernel, "render": c.ms_render}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

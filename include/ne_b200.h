@@ -176,6 +176,12 @@ int ne_b200_device_count(void);                 /* number of CUDA devices visibl
 int ne_b200_create(int cuda_device, ne_b200_ctx** out);
 void ne_b200_destroy(ne_b200_ctx* ctx);
 
+/* Run the context's kernels and copies on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream) instead of the private stream made by ne_b200_create, so that a host that already owns a
+ * stream (an NCCL communicator, a GL interop queue, a profiler's event pair) orders against the render without
+ * extra synchronisation. The stream must outlive the context or be replaced before it is destroyed. */
+int ne_b200_set_stream(ne_b200_ctx* ctx, void* cuda_stream);
+
 /* Flatten + copy the scene into HBM: SoA primitive/instance tables in reference fold order, SoA triangles +
  * binned-SAH BVH, brick-sparse density grids with per-brick majorants, emitter table. Replaces the Scene*
  * handed to OfflineEngine's ctor. May be called again to replace the scene. */

@@ -87,6 +87,7 @@ SYMBOLS = {
     "ne_b200_device_count": (C.c_int, []),
     "ne_b200_create": (C.c_int, [C.c_int, C.POINTER(_ctx)]),
     "ne_b200_destroy": (None, [_ctx]),
+    "ne_b200_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "ne_b200_scene_upload": (C.c_int, [_ctx, C.POINTER(SceneDesc)]),
     "ne_b200_camera_set": (C.c_int, [_ctx, C.POINTER(Camera)]),
     "ne_b200_render": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64, u32]),

@@ -351,7 +351,8 @@ int ne_b200_create(int cuda_device, ne_b200_ctx** out) {
 	NE_CUDA_OK(cudaSetDevice(cuda_device));
 	std::unique_ptr<ne_b200_ctx> ctx(new ne_b200_ctx());
 	ctx->device = cuda_device;
-	NE_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	NE_CUDA_OK(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
+	ctx->stream = ctx->ownStream;
 	NE_CUDA_OK(cudaEventCreate(&ctx->evA));
 	NE_CUDA_OK(cudaEventCreate(&ctx->evB));
 	NE_CUDA_OK(cudaMalloc(&ctx->dCounters, sizeof(DCounters)));
@@ -370,8 +371,16 @@ void ne_b200_destroy(ne_b200_ctx* ctx) {
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->evA) cudaEventDestroy(ctx->evA);
 	if (ctx->evB) cudaEventDestroy(ctx->evB);
-	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
+}
+
+int ne_b200_set_stream(ne_b200_ctx* ctx, void* cuda_stream) {
+	int rc = check_ctx(ctx, false);
+	if (rc) return rc;
+	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return NE_B200_OK;
 }
 
 int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {

@@ -26,7 +26,8 @@ struct ne_wavefront_state;
 
 struct ne_b200_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;     // the stream everything runs on
+	cudaStream_t ownStream = nullptr;  // created by ne_b200_create, destroyed with the context
 	std::vector<void*> sceneAllocs;  // device allocations owned by the uploaded scene
 	ne::DScene scene{};
 	bool haveScene = false;

@@ -52,6 +52,10 @@ class Context:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (an int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self.lib, self.lib.ne_b200_set_stream(self.h, C.c_void_p(cuda_stream)), "ne_b200_set_stream")
+
     # ---- scene / camera / render
     def upload(self, builder_or_desc):
         desc = builder_or_desc.desc() if hasattr(builder_or_desc, "desc") else builder_or_desc

@@ -616,9 +616,10 @@ void neref_sample_one_light(void* h, int n, const float* incomingDirs, const ne_
 // and sample loops (OfflineEngine.cpp:61-71) over the WHOLE image (the shipped 40x10 tiling drops edge pixels,
 // Q28). Rows are interleaved over `nthreads` std::threads. With the thread_local RNG build every thread seeds
 // its own engine; with the as-shipped build all threads share (and race on) the single global engine.
+// Only rows rowBegin, rowBegin+rowStep, ... < rowEnd are rendered (a bounded, frame-covering sample for timing).
 // linear / tonemapped: W*H*3 floats, may be NULL. Returns wall seconds of the render loop.
 double neref_render(void* h, const float* lookFrom, const float* lookAt, const float* up, float vfov, float aperture, float focus,
-                    int W, int H, int spp, int bounces, uint32_t seed, int nthreads, int rowBegin, int rowEnd, float* linear, float* tonemapped) {
+                    int W, int H, int spp, int bounces, uint32_t seed, int nthreads, int rowBegin, int rowEnd, int rowStep, float* linear, float* tonemapped) {
 	RefScene* rs = (RefScene*)h;
 	rs->scene->settings.bounces = bounces;
 	rs->scene->settings.spp = spp;
@@ -629,6 +630,7 @@ double neref_render(void* h, const float* lookFrom, const float* lookAt, const f
 	if (nthreads < 1) nthreads = 1;
 	if (rowEnd <= 0 || rowEnd > H) rowEnd = H;
 	if (rowBegin < 0) rowBegin = 0;
+	if (rowStep < 1) rowStep = 1;
 	auto t0 = std::chrono::steady_clock::now();
 	auto worker = [&](int tid) {
 #ifdef NE_ORACLE_TLS_RNG
@@ -637,7 +639,7 @@ double neref_render(void* h, const float* lookFrom, const float* lookAt, const f
 		if (tid == 0) narvalengine::mt.seed(seed);
 #endif
 		Integrator* integ = eng.pathIntegrator->clone();
-		for (int y = rowBegin + tid; y < rowEnd; y += nthreads)
+		for (int y = rowBegin + tid * rowStep; y < rowEnd; y += nthreads * rowStep)
 			for (int x = 0; x < W; x++) {
 				glm::vec3 color(0, 0, 0);
 				for (int s = 0; s < spp; s++) {

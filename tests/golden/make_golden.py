@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import scenes  # noqa: E402
 from refclient import RefOracle  # noqa: E402
 
-SIZES = {"cornell": (24, 16, 16384), "volume": (24, 16, 8192), "mixed": (16, 12, 32768), "mesh": (24, 16, 8192)}
+SIZES = {"cornell": (24, 16, 65536), "volume": (24, 16, 65536), "mixed": (16, 12, 131072), "mesh": (24, 16, 32768)}
 
 
 def main():

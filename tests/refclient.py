@@ -194,13 +194,13 @@ class RefScene:
         self.lib.neref_sample_one_light(self.h, n, _p(dd), hits, _p(sd, pu32), _p(L), _p(used, pi32))
         return L, used
 
-    def render(self, cp, W, H, spp, bounces, seed=1, threads=1, rows=None, tonemapped=False):
+    def render(self, cp, W, H, spp, bounces, seed=1, threads=1, rows=None, tonemapped=False, row_step=1):
         lin = np.zeros((H, W, 3), np.float32)
         tm = np.zeros((H, W, 3), np.float32) if tonemapped else None
         r0, r1 = rows if rows else (0, H)
         secs = self.lib.neref_render(self.h, _p(f32a(cp.look_from)), _p(f32a(cp.look_at)), _p(f32a(cp.up)),
                                      f32(cp.vfov), f32(cp.aperture), f32(cp.focus), W, H, spp, bounces,
-                                     C.c_uint32(seed), threads, r0, r1, _p(lin), _p(tm) if tonemapped else None)
+                                     C.c_uint32(seed), threads, r0, r1, row_step, _p(lin), _p(tm) if tonemapped else None)
         return (lin, tm, secs) if tonemapped else (lin, secs)
 
     def render_tile(self, cp, W, H, spp, bounces, seed, tile):

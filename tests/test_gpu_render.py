@@ -106,8 +106,12 @@ def test_offline_engine_tile_protocol(ctx):
     oracle = RefOracle()
     eng = B200OfflineEngine(scenes.CORNELL_CAMERA, SceneSettings((80, 40), 4, 6), scenes.cornell_c1())
     assert eng.numberOfTiles == (40, 10) and eng.tileSize == (2, 4)
-    eng.renderTile(0)
-    assert eng.pixels[:4, :2].any() and not eng.pixels[4:, :].any()
+    tile = 5 * 40 + 20  # a tile in the middle of the frame: rows 20..23, columns 40..41
+    eng.renderTile(tile)
+    assert eng.pixels[20:24, 40:42].any()
+    mask = np.ones(eng.pixels.shape[:2], bool)
+    mask[20:24, 40:42] = False
+    assert not eng.pixels[mask].any()
     eng.render()
     assert eng.pixels.min() >= 0 and eng.pixels.max() <= 1
     np.testing.assert_allclose(eng.pixels, oracle.tonemap(eng.linear).reshape(eng.pixels.shape), rtol=1e-5, atol=1e-6)
