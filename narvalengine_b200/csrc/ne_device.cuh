@@ -545,115 +545,10 @@ struct BrickDDA {
 	NE_D float majorant(const DVolume& v) const { return __ldg(v.bmaj + (bz * v.by + by) * v.bx + bx); }
 };
 
-// GridMedia::Tr. rayW: WCS ray; tNear/tFar from the hit record. Returns the scalar transmittance.
-template <class R, bool BRICKMAJ>
-NE_D float grid_tr(const DInstance& in, const DMaterial& m, const DVolume& v, Ray rayW, float tNear, float tFar, R& rng, Stats& st) {
-	Ray ray = transform_ray(rayW, in.Mi);
-	ray.o = ray.at(tNear);
-	tFar = tFar - tNear;
-	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
-	float sig = avg(ext * m.density_mult);
-	float Tr = 1, t = 0;
-	if (!BRICKMAJ) {
-		while (true) {
-			t -= logf(1 - rng.next()) * v.inv_max_density / sig;
-			if (t >= tFar) break;
-			st.ratio_steps++;
-			float density = density_at(v, ray, t);
-			Tr *= 1 - fmaxf(0.0f, density * v.inv_max_density);
-			const float rrThreshold = .1f;
-			if (Tr < rrThreshold) {
-				float q = fmaxf(0.05f, 1.0f - Tr);
-				if (rng.next() < q) return 0.0f;
-				Tr /= 1 - q;
-			}
-		}
-		return Tr;
-	}
-	BrickDDA dda;
-	dda.init(v, ray);
-	while (true) {
-		st.brick_visits++;
-		float tExit = fminf(dda.exit_t(), tFar);
-		float maj = dda.majorant(v);
-		if (maj > 0) {
-			float invMaj = 1.0f / maj;
-			float step = invMaj / sig;
-			while (true) {
-				t -= logf(1 - rng.next()) * step;
-				if (t >= tExit) break;
-				st.ratio_steps++;
-				float density = density_at(v, ray, t);
-				Tr *= 1 - fmaxf(0.0f, density * invMaj);
-				if (Tr < .1f) {
-					float q = fmaxf(0.05f, 1.0f - Tr);
-					if (rng.next() < q) return 0.0f;
-					Tr /= 1 - q;
-				}
-			}
-		}
-		t = tExit;
-		if (tExit >= tFar) break;
-		if (!dda.step(v)) break;
-	}
-	return Tr;
-}
+}  // namespace ne
+#include "ne_tracking.cuh"  // Tracker, ratio_walk, delta_walk, grid_tr, grid_scatter, grid_sample
+namespace ne {
 
-// GridMedia::sample. In Li `incoming` already has its origin at the segment start and tNear = 0.
-// Returns the value the reference returns: sigma_s/sigma_t on a collision, exactly (1,1,1) on escape (Q1, Q1b).
-template <class R, bool BRICKMAJ>
-NE_D V3 grid_sample(const DScene& s, const DInstance& in, const DMaterial& m, const DVolume& v, Ray incomingW, float tNear, float tFar,
-                    const Hit& isect, Ray& scattered, R& rng, Stats& st) {
-	scattered = incomingW;
-	Ray ray = transform_ray(incomingW, in.Mi);
-	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
-	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
-	float sig = avg(ext * m.density_mult);
-	float t = tNear;  // GridMedia.cpp:79; Li always passes 0 (the brick walk below relies on that)
-	bool collided = false;
-	if (!BRICKMAJ) {
-		while (true) {
-			float r = rng.next();
-			float sampledDist = logf(1 - r) * v.inv_max_density / sig;
-			t -= sampledDist;
-			if (t >= tFar) break;
-			st.delta_steps++;
-			float density = density_at(v, ray, t);
-			float ra = rng.next();
-			if (density * v.inv_max_density > ra) { collided = true; break; }
-		}
-	} else {
-		BrickDDA dda;
-		dda.init(v, ray);
-		while (true) {
-			st.brick_visits++;
-			float tExit = fminf(dda.exit_t(), tFar);
-			float maj = dda.majorant(v);
-			if (maj > 0) {
-				float invMaj = 1.0f / maj;
-				float step = invMaj / sig;
-				while (true) {
-					t -= logf(1 - rng.next()) * step;
-					if (t >= tExit) break;
-					st.delta_steps++;
-					float density = density_at(v, ray, t);
-					if (density * invMaj > rng.next()) { collided = true; break; }
-				}
-				if (collided) break;
-			}
-			t = tExit;
-			if (tExit >= tFar) break;
-			if (!dda.step(v)) break;
-		}
-	}
-	if (!collided) return V3(1.0f);
-	st.scatter_events++;
-	Ray so;
-	so.o = ray.at(t);
-	so.d = bsdf_sample(s, m, ray.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // Q19: about +Y of the OCS, ignores the incoming direction
-	scattered = transform_ray(so, in.M);                                 // direction keeps the instance scale
-	return sc / ext;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Emitter primitives: samplePointOnSurface / pdf of Rectangle (Rectangle.cpp:78-88,159-171), Sphere

@@ -180,21 +180,29 @@ NE_D int classify_hit(const DScene& s, bool did, const Hit& isect, const PathSta
 	return HIT_SURFACE;
 }
 
-// Li :194-240 — the volume branch.
-template <class R, bool BRICKMAJ, class SINK>
-NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& sink, Stats& st) {
-	const DInstance& in = s.inst[isect.inst];
-	const DMaterial& m = s.mat[in.material];
+// Li :194-240 — the volume branch, in three pieces so the wavefront can run the tracking loop in its own kernel.
+// (1) :198-201 move the origin to the volume's boundary (idempotent once tNear is 0).
+NE_D void volume_enter(PathState& ps, Hit& isect) {
 	ps.ray.o = ps.ray.at(isect.tNear);
 	isect.tFar = isect.tFar - isect.tNear;
 	isect.tNear = 0;
-	Ray scattered;
-	V3 a = grid_sample<R, BRICKMAJ>(s, in, m, s.vol[m.volume], ps.ray, 0.0f, isect.tFar, isect, scattered, rng, st);
-	if (all_one(a)) {  // Q1: escape detected by value, does not consume a bounce
-		ps.ray.o = ps.ray.at(isect.tFar + 0.01f);
-		if (++ps.guard > NE_MAX_NULL_SEGMENTS) return PATH_DONE;
-		return PATH_SAME_BOUNCE;
-	}
+}
+// (2a) :209-213 escape (Q1: detected by value in the reference; does not consume a bounce).
+NE_D int volume_escape(PathState& ps, const Hit& isect) {
+	ps.ray.o = ps.ray.at(isect.tFar + 0.01f);
+	if (++ps.guard > NE_MAX_NULL_SEGMENTS) return PATH_DONE;
+	return PATH_SAME_BOUNCE;
+}
+// (2b) :215-236 real collision at parameter t of the OCS ray `rayO`.
+template <class R, class SINK>
+NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const Ray& rayO, float t, R& rng, SINK& sink, Stats& st) {
+	const DInstance& in = s.inst[isect.inst];
+	const DMaterial& m = s.mat[in.material];
+	Ray scattered = grid_scatter(s, in, m, rayO, t, isect, rng, st);
+	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
+	V3 a = sc / ext;
+	if (all_one(a)) return volume_escape(ps, isect);  // Q1b: albedo exactly 1 is mistaken for an escape
 	ps.T = ps.T * a;
 	V3 phaseFr = bsdf_eval(s, m, ps.ray.d, scattered.d, isect);
 	float phasePdf = bsdf_pdf(s, m, ps.ray.d, scattered.d, isect.n, isect);
@@ -206,6 +214,19 @@ NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& 
 	sink.emit(ps.T * lightSample);
 	ps.ray = scattered;
 	return PATH_NEXT_BOUNCE;
+}
+// The whole volume branch in one go (one thread per path).
+template <class R, bool BRICKMAJ, class SINK>
+NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& sink, Stats& st) {
+	const DInstance& in = s.inst[isect.inst];
+	const DMaterial& m = s.mat[in.material];
+	const DVolume& v = s.vol[m.volume];
+	volume_enter(ps, isect);
+	Ray rayO = transform_ray(ps.ray, in.Mi);
+	Tracker<BRICKMAJ> trk;
+	trk.init(v, m, rayO, 0.0f, isect.tFar, st);
+	if (delta_walk<R, BRICKMAJ>(v, trk, rng, st, NE_NO_BUDGET) != TRACK_CANDIDATE) return volume_escape(ps, isect);
+	return volume_scatter(s, ps, isect, rayO, trk.t, rng, sink, st);
 }
 
 // Li :262-283 — the surface branch.

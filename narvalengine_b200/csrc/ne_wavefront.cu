@@ -1,17 +1,21 @@
 // ne_wavefront.cu — the production renderer: OfflineEngine::renderTile's pixel x sample loops
 // (core/OfflineEngine.cpp:61-71) over the whole frame as a WAVEFRONT of SoA path records.
 //
-//   pool      N path slots (SoA float4 arrays, 56 B of state each) that are refilled with new camera samples as
+//   pool      N path slots (SoA float4 arrays, 64 B of state each) that are refilled with new camera samples as
 //             paths terminate, so the wavefront stays full until the work runs out
-//   queues    arrays of slot indices: extend -> {volume, surface} -> next extend; free slots; all pushes are
-//             warp-aggregated (one atomicAdd per warp per queue)
+//   queues    arrays of slot indices: extend -> {volume, surface}; volume -> {scatter, volume (walk not finished),
+//             next extend}; free slots. All pushes are warp-aggregated (one atomicAdd per warp per queue)
 //   kernels   plan (1 thread: queue bookkeeping) · generate (camera rays) · extend (Scene::intersectScene fold, BVH)
-//             · volume (delta tracking + phase + next-event setup) · surface (GGX shading + next-event setup)
-//             · shadow (visibilityTr requests) · tr (intersectTr + ratio tracking requests)
+//             · track (delta tracking, bounded events per pass) · scatter (phase function + next-event setup)
+//             · surface (GGX shading + next-event setup) · shadow (visibilityTr requests)
+//             · tr (intersectTr requests: walk to the first medium + ratio tracking, bounded events per pass)
 //   output    fp32 atomicAdd splats into the context's linear accumulation buffer
 //
-// Every kernel is a grid-stride loop over a device-side count with a fixed grid of (SM count x resident blocks), so
-// no host round trip is needed to size launches; the host only polls a mapped "done" word.
+// The two tracking kernels stop a walk after `budget` events (brick moves + density look-ups), move the origin to the
+// point reached and queue the remainder for the next pass: exponential free flights are memoryless, so the estimate is
+// unchanged, and a warp is never held hostage by its longest walk. Every kernel is a grid-stride loop over a
+// device-side count with a fixed grid of (SM count x resident blocks): no host round trip sizes a launch; the host
+// only polls a mapped "done" word every few iterations.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -24,23 +28,24 @@ using namespace ne;
 namespace {
 
 struct WfCounts {
-	uint32_t extend, next, vol, surf, freeN, shadow, tr, gen;
+	uint32_t extend, next, vol, volNext, scat, surf, freeN, shadow, tr, trNext, gen, done;
 	unsigned long long workNext, workTotal;
-	uint32_t done, pad;
 };
 
 struct WfBuf {
-	// path record: A=(o.xyz,d.x) B=(d.yz,T.xy) C=(T.z,pixel,sample,dim) D=(bounce|guard<<8, nee)
+	// path record: A=(o.xyz,d.x) B=(d.yz,T.xy) C=(T.z,pixel,sample,dim) D=(bounce|guard<<8, nee, collision t, -)
 	float4 *pA, *pB, *pC;
-	uint2* pD;
+	uint4* pD;
 	// hit record: A=(p.xyz,tNear) B=(n.xyz,tFar) C=(u,v,inst,prim)
 	float4 *hA, *hB, *hC;
 	// shadow request: A=(o.xyz,C.x) B=(C.yz,w.xy) C=(w.z,pixel)
 	float4 *sA, *sB;
 	float2* sC;
-	// transmittance request: A=(o.xyz,d.x) B=(d.yz,w.xy) C=(w.z,pixel,sample,stream)
-	float4 *tA, *tB, *tC;
-	uint32_t *qExtend, *qNext, *qVol, *qSurf, *qFree;
+	// transmittance request (current / next pass): A=(o.xyz,d.x) B=(d.yz,w.xy) C=(w.z,pixel,sample,stream)
+	// D=(Tr so far, remaining tFar, medium instance or -1 = not found yet, dim)
+	float4 *tA, *tB, *tC, *tD;
+	float4 *uA, *uB, *uC, *uD;
+	uint32_t *qExtend, *qNext, *qVol, *qVolNext, *qScat, *qSurf, *qFree;
 	WfCounts* c;
 };
 
@@ -48,7 +53,7 @@ struct WfParams {
 	DScene s;
 	DCamera cam;
 	float* accum;
-	int W, H, sppBegin, bounces;
+	int W, H, sppBegin, bounces, budget;
 	uint64_t seed;
 	DCounters* counters;
 };
@@ -63,26 +68,25 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter) {
 	return base + __popc(m & ((1u << lane) - 1));
 }
 
-__device__ __forceinline__ void flush_stats_wf(const Stats& st, DCounters* c, unsigned paths) {
+__device__ __forceinline__ void flush_stats_wf(const Stats& st, DCounters* c) {
 	unsigned m = __activemask();
 	unsigned lane = threadIdx.x & 31;
 	unsigned leader = __ffs(m) - 1;
-#define NE_FLUSH(field, val)                                                   \
+#define NE_FLUSH(field)                                                        \
 	{                                                                          \
-		unsigned v = __reduce_add_sync(m, (unsigned)(val));                    \
+		unsigned v = __reduce_add_sync(m, (unsigned)(st.field));               \
 		if (lane == leader && v) atomicAdd(&c->field, (unsigned long long)v);  \
 	}
-	NE_FLUSH(paths, paths)
-	NE_FLUSH(extend_rays, st.extend_rays)
-	NE_FLUSH(shadow_rays, st.shadow_rays)
-	NE_FLUSH(delta_steps, st.delta_steps)
-	NE_FLUSH(ratio_steps, st.ratio_steps)
-	NE_FLUSH(brick_visits, st.brick_visits)
-	NE_FLUSH(bvh_nodes, st.bvh_nodes)
-	NE_FLUSH(tri_tests, st.tri_tests)
-	NE_FLUSH(prim_tests, st.prim_tests)
-	NE_FLUSH(scatter_events, st.scatter_events)
-	NE_FLUSH(surface_events, st.surface_events)
+	NE_FLUSH(extend_rays)
+	NE_FLUSH(shadow_rays)
+	NE_FLUSH(delta_steps)
+	NE_FLUSH(ratio_steps)
+	NE_FLUSH(brick_visits)
+	NE_FLUSH(bvh_nodes)
+	NE_FLUSH(tri_tests)
+	NE_FLUSH(prim_tests)
+	NE_FLUSH(scatter_events)
+	NE_FLUSH(surface_events)
 #undef NE_FLUSH
 }
 
@@ -95,10 +99,11 @@ __device__ __forceinline__ void splat(float* accum, uint32_t pixel, V3 v) {
 struct PathRec {
 	PathState ps;
 	uint32_t pixel, sample, dim;
+	float tHit;  // collision parameter handed from track to scatter
 };
 __device__ __forceinline__ PathRec load_path(const WfBuf& b, uint32_t slot) {
 	float4 A = b.pA[slot], B = b.pB[slot], C = b.pC[slot];
-	uint2 D = b.pD[slot];
+	uint4 D = b.pD[slot];
 	PathRec r;
 	r.ps.ray.o = V3(A.x, A.y, A.z);
 	r.ps.ray.d = V3(A.w, B.x, B.y);
@@ -109,13 +114,14 @@ __device__ __forceinline__ PathRec load_path(const WfBuf& b, uint32_t slot) {
 	r.ps.bounce = int(D.x & 0xff);
 	r.ps.guard = int(D.x >> 8);
 	r.ps.nee = D.y;
+	r.tHit = __uint_as_float(D.z);
 	return r;
 }
 __device__ __forceinline__ void store_path(const WfBuf& b, uint32_t slot, const PathRec& r) {
 	b.pA[slot] = make_float4(r.ps.ray.o.x, r.ps.ray.o.y, r.ps.ray.o.z, r.ps.ray.d.x);
 	b.pB[slot] = make_float4(r.ps.ray.d.y, r.ps.ray.d.z, r.ps.T.x, r.ps.T.y);
 	b.pC[slot] = make_float4(r.ps.T.z, __uint_as_float(r.pixel), __uint_as_float(r.sample), __uint_as_float(r.dim));
-	b.pD[slot] = make_uint2(uint32_t(r.ps.bounce) | (uint32_t(r.ps.guard) << 8), r.ps.nee);
+	b.pD[slot] = make_uint4(uint32_t(r.ps.bounce) | (uint32_t(r.ps.guard) << 8), r.ps.nee, __float_as_uint(r.tHit), 0u);
 }
 __device__ __forceinline__ Hit load_hit(const WfBuf& b, uint32_t slot) {
 	float4 A = b.hA[slot], B = b.hB[slot], C = b.hC[slot];
@@ -163,6 +169,7 @@ struct QueueSink {
 		b->tA[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
 		b->tB[i] = make_float4(ray.d.y, ray.d.z, w.x, w.y);
 		b->tC[i] = make_float4(w.z, __uint_as_float(pixel), __uint_as_float(sample), __uint_as_float(stream));
+		b->tD[i] = make_float4(1.0f, 0.0f, __int_as_float(-1), __uint_as_float(0u));
 	}
 };
 
@@ -181,18 +188,22 @@ __global__ void k_wf_init(WfBuf b, uint32_t nSlots, unsigned long long workTotal
 	}
 }
 
-// One thread: retire the finished iteration (next -> extend, clear stage queues) and plan the refill.
-// `flip` tells which of the two extend buffers is current; the host alternates it.
+// One thread: retire the finished iteration (next -> extend, unfinished walks -> vol / tr, clear stage queues) and
+// plan the refill. The host alternates which buffer of each ping-pong pair is "current".
 __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 	WfCounts& c = *b.c;
 	c.extend = c.next;
 	c.next = 0;
-	c.vol = c.surf = c.shadow = c.tr = 0;
+	c.vol = c.volNext;
+	c.volNext = 0;
+	c.tr = c.trNext;
+	c.trNext = 0;
+	c.scat = c.surf = c.shadow = 0;
 	unsigned long long remaining = c.workTotal - c.workNext;
 	uint32_t gen = uint32_t(remaining < c.freeN ? remaining : c.freeN);
 	c.gen = gen;
 	c.freeN -= gen;
-	c.done = (c.extend == 0 && gen == 0) ? 1u : 0u;
+	c.done = (c.extend == 0 && gen == 0 && c.vol == 0 && c.tr == 0) ? 1u : 0u;
 	if (hostDone) *hostDone = c.done;
 }
 
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(WfBuf b, WfParams P) {
 		r.pixel = pixel;
 		r.sample = sample;
 		r.dim = rng.dim;
+		r.tHit = 0;
 		store_path(b, slot, r);
 		b.qExtend[extendBase + i] = slot;
 	}
@@ -258,17 +270,65 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 			else b.qSurf[warp_push(&b.c->surf)] = slot;
 		}
 	}
-	flush_stats_wf(st, P.counters, 0);
+	flush_stats_wf(st, P.counters);
 }
 
-template <bool BRICKMAJ, bool VOLUME>
-__global__ void __launch_bounds__(256) k_wf_shade(WfBuf b, WfParams P) {
-	const uint32_t n = VOLUME ? b.c->vol : b.c->surf;
-	const uint32_t* q = VOLUME ? b.qVol : b.qSurf;
+// Delta tracking (GridMedia::sample's loop) for every path of the volume queue, at most P.budget events per pass.
+template <bool BRICKMAJ>
+__global__ void __launch_bounds__(256) k_wf_track(WfBuf b, WfParams P) {
+	const uint32_t n = b.c->vol;
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		uint32_t slot = q[i];
+		uint32_t slot = b.qVol[i];
+		PathRec r = load_path(b, slot);
+		float4 hA = b.hA[slot], hB = b.hB[slot], hC = b.hC[slot];
+		Hit h;
+		h.tNear = hA.w;
+		h.tFar = hB.w;
+		h.inst = __float_as_int(hC.z);
+		volume_enter(r.ps, h);
+		const DInstance& in = P.s.inst[h.inst];
+		const DMaterial& m = P.s.mat[in.material];
+		const DVolume& v = P.s.vol[m.volume];
+		PhiloxRng rng;
+		rng.init(P.seed, r.pixel, r.sample, r.dim);
+		Ray rayO = transform_ray(r.ps.ray, in.Mi);
+		Tracker<BRICKMAJ> trk;
+		trk.init(v, m, rayO, 0.0f, h.tFar, st);
+		int e = delta_walk<PhiloxRng, BRICKMAJ>(v, trk, rng, st, P.budget);
+		r.dim = rng.dim;
+		if (e == TRACK_CANDIDATE) {
+			r.tHit = trk.t;
+			store_path(b, slot, r);
+			b.hA[slot].w = 0.0f;
+			b.hB[slot].w = h.tFar;
+			b.qScat[warp_push(&b.c->scat)] = slot;
+		} else if (e == TRACK_BUDGET) {
+			r.ps.ray.o = r.ps.ray.at(trk.t);
+			store_path(b, slot, r);
+			b.hA[slot].w = 0.0f;
+			b.hB[slot].w = h.tFar - trk.t;
+			b.qVolNext[warp_push(&b.c->volNext)] = slot;
+		} else {
+			if (volume_escape(r.ps, h) == PATH_DONE) {
+				b.qFree[warp_push(&b.c->freeN)] = slot;
+			} else {
+				store_path(b, slot, r);
+				b.qNext[warp_push(&b.c->next)] = slot;
+			}
+		}
+	}
+	flush_stats_wf(st, P.counters);
+}
+
+// Real collisions: phase function, next-event setup, continuation (Li :215-236).
+__global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
+	const uint32_t n = b.c->scat;
+	Stats st;
+	st.clear();
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint32_t slot = b.qScat[i];
 		PathRec r = load_path(b, slot);
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
@@ -278,7 +338,8 @@ __global__ void __launch_bounds__(256) k_wf_shade(WfBuf b, WfParams P) {
 		sink.accum = P.accum;
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
-		int next = VOLUME ? shade_volume<PhiloxRng, BRICKMAJ>(P.s, r.ps, h, rng, sink, st) : shade_surface<PhiloxRng>(P.s, r.ps, h, rng, sink, st);
+		Ray rayO = transform_ray(r.ps.ray, P.s.inst[h.inst].Mi);
+		int next = volume_scatter(P.s, r.ps, h, rayO, r.tHit, rng, sink, st);
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
 		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
@@ -288,7 +349,36 @@ __global__ void __launch_bounds__(256) k_wf_shade(WfBuf b, WfParams P) {
 			b.qNext[warp_push(&b.c->next)] = slot;
 		}
 	}
-	flush_stats_wf(st, P.counters, 0);
+	flush_stats_wf(st, P.counters);
+}
+
+// Surface hits: GGX shading, next-event setup, continuation (Li :262-283).
+__global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
+	const uint32_t n = b.c->surf;
+	Stats st;
+	st.clear();
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint32_t slot = b.qSurf[i];
+		PathRec r = load_path(b, slot);
+		Hit h = load_hit(b, slot);
+		PhiloxRng rng;
+		rng.init(P.seed, r.pixel, r.sample, r.dim);
+		QueueSink sink;
+		sink.b = &b;
+		sink.accum = P.accum;
+		sink.pixel = r.pixel;
+		sink.sample = r.sample;
+		int next = shade_surface<PhiloxRng>(P.s, r.ps, h, rng, sink, st);
+		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
+		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
+			b.qFree[warp_push(&b.c->freeN)] = slot;
+		} else {
+			r.dim = rng.dim;
+			store_path(b, slot, r);
+			b.qNext[warp_push(&b.c->next)] = slot;
+		}
+	}
+	flush_stats_wf(st, P.counters);
 }
 
 // visibilityTr requests: splat the weight when nothing or an emitter is hit first.
@@ -303,27 +393,63 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 		float vis = visibility_tr<PhiloxRng, false, true>(P.s, V3(A.x, A.y, A.z), V3(A.w, B.x, B.y), dummy, st);
 		if (vis != 0) splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * vis);
 	}
-	flush_stats_wf(st, P.counters, 0);
+	flush_stats_wf(st, P.counters);
 }
 
-// intersectTr requests: walk through surfaces to the first medium, ratio-track through it, splat weight * Tr.
+// intersectTr requests: walk through surfaces to the first medium (first pass), ratio-track through it (at most
+// P.budget events per pass), splat weight * Tr.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(256) k_wf_tr(WfBuf b, WfParams P) {
 	const uint32_t n = b.c->tr;
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 A = b.tA[i], B = b.tB[i], C = b.tC[i];
+		float4 A = b.tA[i], B = b.tB[i], C = b.tC[i], D = b.tD[i];
 		Ray ray;
 		ray.o = V3(A.x, A.y, A.z);
 		ray.d = V3(A.w, B.x, B.y);
+		float Tr = D.x, tRemain = D.y;
+		int inst = __float_as_int(D.z);
 		PhiloxRng rng;
-		rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), 0u, __float_as_uint(C.w));
-		float Tr;
-		bool found = intersect_tr<PhiloxRng, false, BRICKMAJ>(P.s, ray, Tr, rng, st);
-		if (found && Tr != 0) splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+		rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
+		float tStart = 0;
+		if (inst < 0) {
+			// intersectTr :13-31: through non-medium surfaces until a medium or nothing
+			for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
+				Hit h;
+				st.shadow_rays++;
+				if (!intersect_scene(P.s, ray, h, float(NE_EPSILON3), INFINITY, st)) break;
+				int mi = P.s.inst[h.inst].material;
+				if (mi >= 0 && P.s.mat[mi].has_medium && P.s.mat[mi].volume >= 0) {
+					inst = h.inst;
+					tStart = h.tNear;
+					tRemain = h.tFar - h.tNear;
+					break;
+				}
+				ray.o = h.p;
+			}
+			if (inst < 0) continue;  // nothing found: Li = 0
+		}
+		const DInstance& in = P.s.inst[inst];
+		const DMaterial& m = P.s.mat[in.material];
+		const DVolume& v = P.s.vol[m.volume];
+		Ray rayO = transform_ray(ray, in.Mi);
+		rayO.o = rayO.at(tStart);  // GridMedia::Tr :49
+		Tracker<BRICKMAJ> trk;
+		trk.init(v, m, rayO, 0.0f, tRemain, st);
+		int e = ratio_walk<PhiloxRng, BRICKMAJ>(v, trk, Tr, rng, st, P.budget);
+		if (e == TRACK_BUDGET) {
+			uint32_t j = warp_push(&b.c->trNext);
+			V3 o = ray.at(tStart + trk.t);
+			b.uA[j] = make_float4(o.x, o.y, o.z, ray.d.x);
+			b.uB[j] = B;
+			b.uC[j] = C;
+			b.uD[j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
+		} else if (Tr != 0) {
+			splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+		}
 	}
-	flush_stats_wf(st, P.counters, 0);
+	flush_stats_wf(st, P.counters);
 }
 
 }  // namespace
@@ -366,7 +492,8 @@ static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
 	int rc;
 	WfBuf& b = w->b;
 #define A(field) if ((rc = wf_alloc(w, &b.field, nSlots))) return rc;
-	A(pA) A(pB) A(pC) A(pD) A(hA) A(hB) A(hC) A(sA) A(sB) A(sC) A(tA) A(tB) A(tC) A(qExtend) A(qNext) A(qVol) A(qSurf) A(qFree)
+	A(pA) A(pB) A(pC) A(pD) A(hA) A(hB) A(hC) A(sA) A(sB) A(sC) A(tA) A(tB) A(tC) A(tD) A(uA) A(uB) A(uC) A(uD)
+	A(qExtend) A(qNext) A(qVol) A(qVolNext) A(qScat) A(qSurf) A(qFree)
 #undef A
 	if ((rc = wf_alloc(w, &b.c, 1))) return rc;
 	NE_CUDA_OK(cudaHostAlloc(&w->hostDone, sizeof(uint32_t), cudaHostAllocMapped));
@@ -377,11 +504,15 @@ static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
 	return NE_B200_OK;
 }
 
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+	const char* e = getenv(name);
+	return e ? (uint32_t)strtoul(e, nullptr, 10) : dflt;
+}
+
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
 	const unsigned long long work = (unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin);
 	if (work == 0 || bounces == 0) return NE_B200_OK;
-	uint32_t pool = 1u << 21;
-	if (const char* e = getenv("NE_B200_POOL")) pool = std::max(1024u, (uint32_t)strtoul(e, nullptr, 10));
+	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 21));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
 	int rc = wavefront_ensure(ctx, nSlots);
 	if (rc) return rc;
@@ -395,13 +526,14 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	P.H = ctx->H;
 	P.sppBegin = sppBegin;
 	P.bounces = bounces;
+	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 48)));
 	P.seed = seed;
 	P.counters = ctx->dCounters;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
 	cudaStream_t st = ctx->stream;
 	const int G = w->gridBlocks, B = 256;
 
-	// event pool for per-stage device times (volume / extend / shade), resolved after the loop
+	// event pool for per-stage device times, resolved after every host poll
 	size_t evUsed = 0;
 	auto ev = [&]() -> cudaEvent_t {
 		if (evUsed == w->events.size()) {
@@ -426,17 +558,25 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 		// a few iterations per host poll; finished iterations cost only empty launches
 		for (int k = 0; k < 4; k++) {
 			WfBuf b = w->b;
-			if (iter & 1) std::swap(b.qExtend, b.qNext);
+			if (iter & 1) {
+				std::swap(b.qExtend, b.qNext);
+				std::swap(b.qVol, b.qVolNext);
+				std::swap(b.tA, b.uA);
+				std::swap(b.tB, b.uB);
+				std::swap(b.tC, b.uC);
+				std::swap(b.tD, b.uD);
+			}
 			k_wf_plan<<<1, 1, 0, st>>>(b, w->devDone);
 			k_wf_generate<<<G, B, 0, st>>>(b, P);
 			k_wf_commit<<<1, 1, 0, st>>>(b, ctx->dCounters);
 			cudaEvent_t e0 = timeStages ? ev() : nullptr;
 			k_wf_extend<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e1 = timeStages ? ev() : nullptr;
-			if (brick) k_wf_shade<true, true><<<G, B, 0, st>>>(b, P);
-			else k_wf_shade<false, true><<<G, B, 0, st>>>(b, P);
+			if (brick) k_wf_track<true><<<G, B, 0, st>>>(b, P);
+			else k_wf_track<false><<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e2 = timeStages ? ev() : nullptr;
-			k_wf_shade<true, false><<<G, B, 0, st>>>(b, P);
+			k_wf_scatter<<<G, B, 0, st>>>(b, P);
+			k_wf_surface<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e3 = timeStages ? ev() : nullptr;
 			k_wf_shadow<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e4 = timeStages ? ev() : nullptr;
@@ -444,13 +584,13 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 			else k_wf_tr<false><<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e5 = timeStages ? ev() : nullptr;
 			if (timeStages) {
-				spans.push_back({e0, e1, 0});
-				spans.push_back({e1, e2, 1});
-				spans.push_back({e2, e3, 2});
-				spans.push_back({e3, e4, 0});
-				spans.push_back({e4, e5, 1});
+				spans.push_back({e0, e1, 0});  // extend
+				spans.push_back({e1, e2, 1});  // delta tracking
+				spans.push_back({e2, e3, 2});  // scatter + surface shading
+				spans.push_back({e3, e4, 0});  // shadow rays
+				spans.push_back({e4, e5, 1});  // ratio tracking
 			}
-			ctx->kernelLaunches += 8;
+			ctx->kernelLaunches += 9;
 			iter++;
 		}
 		NE_CUDA_OK(cudaStreamSynchronize(st));

@@ -40,10 +40,12 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", list(CASES))
-def test_wavefront_equals_megakernel(ctx, name):
+def test_wavefront_equals_megakernel(ctx, name, monkeypatch):
     mk, cam = CASES[name]
     b = mk()
     W, H, spp = 96, 64, 8
+    # unbounded walks: a walk that is stopped and resumed (NE_B200_TRACK_BUDGET) restarts from a rounded origin
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
     a = render(ctx, b, cam, W, H, spp, flags=0)
     m = render(ctx, b, cam, W, H, spp, flags=abi.RENDER_MEGAKERNEL)
     assert np.isfinite(a).all() and np.isfinite(m).all()
@@ -70,6 +72,20 @@ def test_sample_ranges_are_additive(ctx):
     ctx.wait()
     one = ctx.read_linear(W, H)
     np.testing.assert_allclose(two, one, rtol=2e-4, atol=1e-5 * float(one.mean()))
+
+
+@pytest.mark.parametrize("name", ["volume", "mixed"])
+def test_bounded_walks_are_unbiased(ctx, name, monkeypatch):
+    """Stopping every tracking walk after a handful of events and resuming it in the next pass (memoryless restart)
+    must not change the estimate: compare a 3-event budget with unbounded walks at high spp."""
+    mk, cam = CASES[name]
+    b = mk()
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "3")
+    a = render(ctx, b, cam, 24, 16, 8192, seed=11)
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    u = render(ctx, b, cam, 24, 16, 8192, seed=12)
+    assert abs(luminance(a).mean() - luminance(u).mean()) / luminance(u).mean() < 0.01
+    assert rel_mse(a, u) < 5e-3
 
 
 def test_global_and_brick_majorants_agree_statistically(ctx):
