@@ -477,7 +477,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 		o.inv_max_density = 1.0f / hb.maxDensity;
 		if ((rc = push_alloc(ctx, hb.table.data(), hb.table.size(), &o.table))) return rc;
 		if ((rc = push_alloc(ctx, hb.pool.data(), hb.pool.size(), &o.pool))) return rc;
-		if ((rc = push_alloc(ctx, hb.bmaj.data(), hb.bmaj.size(), &o.bmaj))) return rc;
+		if ((rc = push_alloc(ctx, hb.binv.data(), hb.binv.size(), &o.binv))) return rc;
 	}
 
 	// ---- instances + meshes

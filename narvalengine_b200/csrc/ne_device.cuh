@@ -480,32 +480,19 @@ NE_D V3 bsdf_eval(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered
 // GridMedia: density / interpolatedDensity / fromOCStoGCS (materials/GridMedia.cpp:15-43, GridMedia.h:33-36) over
 // the brick-sparse grid; Tr (ratio tracking) :45-69; sample (delta tracking) :71-100.
 // ---------------------------------------------------------------------------------------------------------------
-NE_D float voxel(const DVolume& v, int x, int y, int z) {
-	if (x >= v.W || y >= v.H || z >= v.D) return 0;
-	int b = __ldg(v.table + ((z >> 3) * v.by + (y >> 3)) * v.bx + (x >> 3));
-	if (b < 0) return 0;
-	return __ldg(v.pool + size_t(b) * BRICK_VOX + ((z & 7) << 6) + ((y & 7) << 3) + (x & 7));
-}
 NE_D float interpolated_density(const DVolume& v, V3 g) {
 	g = gmin(gmax(V3(0.0f), g), V3(float(v.W), float(v.H), float(v.D)));
 	int ix = int(floorf(g.x)), iy = int(floorf(g.y)), iz = int(floorf(g.z));
+	if (ix >= v.W || iy >= v.H || iz >= v.D) return 0.0f;  // every corner is at or beyond the grid: density() = 0
+	int b = __ldg(v.table + ((iz >> 3) * v.by + (iy >> 3)) * v.bx + (ix >> 3));
+	if (b < 0) return 0.0f;
 	V3 d = g - V3(float(ix), float(iy), float(iz));
-	float v000, v100, v010, v110, v001, v101, v011, v111;
-	if ((ix & 7) != 7 && (iy & 7) != 7 && (iz & 7) != 7 && ix + 1 < v.W && iy + 1 < v.H && iz + 1 < v.D) {
-		// all eight voxels live in one brick: one table lookup, four 8-byte row segments
-		int b = __ldg(v.table + ((iz >> 3) * v.by + (iy >> 3)) * v.bx + (ix >> 3));
-		if (b < 0) return 0.0f * (1.0f - d.z) + 0.0f * d.z;
-		const float* p = v.pool + size_t(b) * BRICK_VOX + ((iz & 7) << 6) + ((iy & 7) << 3) + (ix & 7);
-		v000 = __ldg(p); v100 = __ldg(p + 1);
-		v010 = __ldg(p + 8); v110 = __ldg(p + 9);
-		v001 = __ldg(p + 64); v101 = __ldg(p + 65);
-		v011 = __ldg(p + 72); v111 = __ldg(p + 73);
-	} else {
-		v000 = voxel(v, ix, iy, iz); v100 = voxel(v, ix + 1, iy, iz);
-		v010 = voxel(v, ix, iy + 1, iz); v110 = voxel(v, ix + 1, iy + 1, iz);
-		v001 = voxel(v, ix, iy, iz + 1); v101 = voxel(v, ix + 1, iy, iz + 1);
-		v011 = voxel(v, ix, iy + 1, iz + 1); v111 = voxel(v, ix + 1, iy + 1, iz + 1);
-	}
+	// apron layout: all eight corners are in this brick's 9^3 record
+	const float* p = v.pool + size_t(b) * BRICK_VOX + ((iz & 7) * 9 + (iy & 7)) * 9 + (ix & 7);
+	float v000 = __ldg(p), v100 = __ldg(p + 1);
+	float v010 = __ldg(p + 9), v110 = __ldg(p + 10);
+	float v001 = __ldg(p + 81), v101 = __ldg(p + 82);
+	float v011 = __ldg(p + 90), v111 = __ldg(p + 91);
 	float d00 = gmix(v000, v100, d.x), d10 = gmix(v010, v110, d.x), d01 = gmix(v001, v101, d.x), d11 = gmix(v011, v111, d.x);
 	float d0 = gmix(d00, d10, d.y), d1 = gmix(d01, d11, d.y);
 	return gmix(d0, d1, d.z);
@@ -542,7 +529,7 @@ struct BrickDDA {
 		if (ny <= nz) { by += sy; ny += dy; return by >= 0 && by < v.by; }
 		bz += sz; nz += dz; return bz >= 0 && bz < v.bz;
 	}
-	NE_D float majorant(const DVolume& v) const { return __ldg(v.bmaj + (bz * v.by + by) * v.bx + bx); }
+	NE_D float inv_majorant(const DVolume& v) const { return __ldg(v.binv + (bz * v.by + by) * v.bx + bx); }  // 0 = empty
 };
 
 }  // namespace ne

@@ -373,11 +373,11 @@ void host_build_bricks(const ne_b200_volume& v, HostBricks& out) {
 		int32_t slots = 0;
 		for (size_t b = 0; b < nb; b++)
 			if (active[b]) out.table[b] = slots++;
-		out.pool.assign(size_t(slots) * BRICK_VOX, 0.0f);
+		out.pool.assign(size_t(slots) * CORE_VOX, 0.0f);
 		parallelFor(nb, [&](size_t b) {
 			if (out.table[b] < 0) return;
 			int bx = int(b % out.bx), by = int((b / out.bx) % out.by), bz = int(b / (size_t(out.bx) * out.by));
-			float* dst = &out.pool[size_t(out.table[b]) * BRICK_VOX];
+			float* dst = &out.pool[size_t(out.table[b]) * CORE_VOX];
 			for (int z = 0; z < 8 && bz * 8 + z < v.depth; z++)
 				for (int y = 0; y < 8 && by * 8 + y < v.height; y++) {
 					const float* row = v.dense + W * H * (bz * 8 + z) + W * (by * 8 + y);
@@ -395,13 +395,13 @@ void host_build_bricks(const ne_b200_volume& v, HostBricks& out) {
 			if (out.table[b] < 0) out.table[b] = slots++;
 			leafSlot[l] = out.table[b];
 		}
-		out.pool.assign(size_t(slots) * BRICK_VOX, 0.0f);
+		out.pool.assign(size_t(slots) * CORE_VOX, 0.0f);
 		// later leaves overwrite earlier ones at the same origin, like repeated copyToDense writes would
 		for (int l = 0; l < v.n_leaves; l++) {
 			if (leafSlot[l] < 0) continue;
 			const int32_t* o = v.leaf_origin + 3 * size_t(l);
-			const float* src = v.leaf_values + size_t(BRICK_VOX) * l;
-			float* dst = &out.pool[size_t(leafSlot[l]) * BRICK_VOX];
+			const float* src = v.leaf_values + size_t(CORE_VOX) * l;
+			float* dst = &out.pool[size_t(leafSlot[l]) * CORE_VOX];
 			for (int z = 0; z < 8; z++)
 				for (int y = 0; y < 8; y++)
 					for (int x = 0; x < 8; x++) {
@@ -420,7 +420,7 @@ void host_build_bricks(const ne_b200_volume& v, HostBricks& out) {
 		int32_t slot = out.table[b];
 		if (slot < 0) return;
 		int bx = int(b % out.bx), by = int((b / out.bx) % out.by), bz = int(b / (size_t(out.bx) * out.by));
-		const float* src = &out.pool[size_t(slot) * BRICK_VOX];
+		const float* src = &out.pool[size_t(slot) * CORE_VOX];
 		// range of local indices contributing to the neighbour at offset -1 / 0 / +1 along one axis
 		const int lo[3] = {0, 0, 7}, hi[3] = {0, 7, 7};
 		for (int oz = -1; oz <= 1; oz++)
@@ -443,6 +443,47 @@ void host_build_bricks(const ne_b200_volume& v, HostBricks& out) {
 	}
 	uint32_t gb = gmaxBits.load();
 	memcpy(&out.maxDensity, &gb, 4);
+	// 1/majorant (0 = nothing to collide with in this brick): the tracking loop never divides
+	out.binv.resize(nb);
+	for (size_t b = 0; b < nb; b++) out.binv[b] = out.bmaj[b] > 0 ? 1.0f / out.bmaj[b] : 0.0f;
+
+	// Apron layout: every stored brick holds the 9x9x9 voxels [8b, 8b+8]^3, so the eight corners of any cell of
+	// the brick come from ONE brick record (one table look-up, no neighbour fetches). A brick gets storage iff that
+	// 9^3 support holds a non-zero voxel. Voxels at or beyond the grid's size are 0 (GridMedia::density :17-18).
+	std::vector<int32_t> coreTable;
+	coreTable.swap(out.table);
+	std::vector<float> core;
+	core.swap(out.pool);
+	auto coreVoxel = [&](int x, int y, int z) -> float {
+		if (x >= out.W || y >= out.H || z >= out.D) return 0.0f;
+		int32_t s = coreTable[(size_t(z >> 3) * out.by + (y >> 3)) * out.bx + (x >> 3)];
+		return s < 0 ? 0.0f : core[size_t(s) * CORE_VOX + ((z & 7) << 6) + ((y & 7) << 3) + (x & 7)];
+	};
+	std::vector<uint8_t> need(nb, 0);
+	parallelFor(nb, [&](size_t b) {
+		int bx = int(b % out.bx), by = int((b / out.bx) % out.by), bz = int(b / (size_t(out.bx) * out.by));
+		if (coreTable[b] >= 0) { need[b] = 1; return; }
+		// an empty core still needs storage when a +x/+y/+z neighbour's first voxel layer is non-zero
+		for (int z = 0; z <= 8; z++)
+			for (int y = 0; y <= 8; y++)
+				for (int x = 0; x <= 8; x++) {
+					if (x < 8 && y < 8 && z < 8) continue;
+					if (coreVoxel(bx * 8 + x, by * 8 + y, bz * 8 + z) != 0.0f) { need[b] = 1; return; }
+				}
+	});
+	out.table.assign(nb, -1);
+	int32_t slots = 0;
+	for (size_t b = 0; b < nb; b++)
+		if (need[b]) out.table[b] = slots++;
+	out.pool.assign(size_t(slots) * BRICK_VOX, 0.0f);
+	parallelFor(nb, [&](size_t b) {
+		if (out.table[b] < 0) return;
+		int bx = int(b % out.bx), by = int((b / out.bx) % out.by), bz = int(b / (size_t(out.bx) * out.by));
+		float* dst = &out.pool[size_t(out.table[b]) * BRICK_VOX];
+		for (int z = 0; z <= 8; z++)
+			for (int y = 0; y <= 8; y++)
+				for (int x = 0; x <= 8; x++) dst[(z * 9 + y) * 9 + x] = coreVoxel(bx * 8 + x, by * 8 + y, bz * 8 + z);
+	});
 }
 
 }  // namespace ne

@@ -27,7 +27,8 @@ struct HostBricks {
 	int W, H, D, bx, by, bz;
 	std::vector<int32_t> table;
 	std::vector<float> pool;
-	std::vector<float> bmaj;
+	std::vector<float> bmaj;  // per-brick majorant density
+	std::vector<float> binv;  // its reciprocal (0 = empty)
 	float maxDensity;
 };
 // From a dense W*H*D grid or from OpenVDB-style 8^3 leaves (see ne_b200_volume).

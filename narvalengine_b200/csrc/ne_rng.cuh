@@ -17,6 +17,7 @@ struct TapeRng {
 		if (pos >= n) { overflow = true; return 0.5f; }
 		return tape[pos++];
 	}
+	NE_D void begin_event() {}
 };
 
 NE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
@@ -41,9 +42,18 @@ NE_HD float u32_to_unit(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f
 struct PhiloxRng {
 	uint32_t k0, k1, pixel, sample, dim, stream;
 	uint32_t b0, b1, b2, b3;
+	bool fresh;  // the block of the current (4-aligned) dimension is already in b0..b3
 	NE_D void init(uint64_t seed, uint32_t px, uint32_t smp, uint32_t dimension = 0, uint32_t strm = 0) {
 		k0 = uint32_t(seed); k1 = uint32_t(seed >> 32); pixel = px; sample = smp; dim = dimension; stream = strm;
+		fresh = false;
 		if (dim & 3) refill();
+	}
+	// Start a tracking event on a fresh block: all lanes of a warp generate their block HERE, together, instead of
+	// each lane refilling inside whichever next() happens to cross a multiple of four (a divergent ~70-instruction branch).
+	NE_D void begin_event() {
+		dim = (dim + 3u) & ~3u;
+		refill();
+		fresh = true;
 	}
 	NE_D void refill() {
 		uint32_t o[4];
@@ -52,7 +62,8 @@ struct PhiloxRng {
 	}
 	NE_D float next() {
 		uint32_t l = dim & 3;
-		if (l == 0) refill();
+		if (l == 0 && !fresh) refill();
+		fresh = false;
 		dim++;
 		uint32_t x = l == 0 ? b0 : (l == 1 ? b1 : (l == 2 ? b2 : b3));
 		return u32_to_unit(x);
@@ -74,6 +85,7 @@ struct Fork<PhiloxRng> {
 		f = base;
 		f.stream = stream;
 		f.dim = 0;
+		f.fresh = false;
 	}
 	NE_D PhiloxRng& get() { return f; }
 };

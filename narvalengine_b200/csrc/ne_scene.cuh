@@ -8,7 +8,7 @@ namespace ne {
 enum { PRIM_RECTANGLE = 0, PRIM_SPHERE = 1, PRIM_POINT = 2, PRIM_VOLUME = 3, PRIM_MESH = 4 };
 enum { MAT_MICROFACET = 0, MAT_EMITTER = 1, MAT_VOLUME = 2, MAT_DIRECTIONAL = 3, MAT_INFINITE = 4 };
 enum { TEX_R32F = 0, TEX_RG32F = 1, TEX_RGB32F = 2, TEX_RGBA32F = 3, TEX_RGBA8 = 4 };
-enum { BRICK = 8, BRICK_VOX = 512 };
+enum { BRICK = 8, CORE_VOX = 512, BRICK_VOX = 729 };  // bricks are stored with a +1 apron: 9x9x9 voxels
 
 struct DTexture {
 	int w, h, format, wrap_u, wrap_v;
@@ -16,14 +16,15 @@ struct DTexture {
 };
 
 // Brick-sparse density grid (GridMedia's Texture, src/materials/GridMedia.h). table[bz][by][bx] = brick slot or
-// -1 (all-zero brick); pool[slot*512 + 64*z + 8*y + x]; bmaj[bz][by][bx] = max voxel over the brick's 9^3
-// support (the trilinear stencil of a cell inside the brick reaches one voxel into the +x/+y/+z neighbours).
+// -1 (nothing but zeros within reach); pool[slot*729 + 81*z + 9*y + x] holds the 9^3 voxels [8b, 8b+8]^3 (apron
+// layout: the trilinear stencil of any cell of the brick is inside its own record); binv[bz][by][bx] = 1 / (max voxel
+// over [8b-1, 8b+8]^3), the reciprocal per-brick majorant, or 0 when that support is empty.
 struct DVolume {
 	int W, H, D;
 	int bx, by, bz;
 	const int* table;
 	const float* pool;
-	const float* bmaj;
+	const float* binv;
 	float max_density, inv_max_density;  // GridMedia::invMaxDensity, GridMedia.cpp:12
 };
 

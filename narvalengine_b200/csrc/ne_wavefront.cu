@@ -28,7 +28,7 @@ using namespace ne;
 namespace {
 
 struct WfCounts {
-	uint32_t extend, next, vol, volNext, scat, surf, freeN, shadow, tr, trNext, gen, done;
+	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, gen, done;
 	unsigned long long workNext, workTotal;
 };
 
@@ -199,6 +199,7 @@ __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 	c.tr = c.trNext;
 	c.trNext = 0;
 	c.scat = c.surf = c.shadow = 0;
+	c.volHead = c.trHead = 0;
 	unsigned long long remaining = c.workTotal - c.workNext;
 	uint32_t gen = uint32_t(remaining < c.freeN ? remaining : c.freeN);
 	c.gen = gen;
@@ -273,49 +274,85 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 	flush_stats_wf(st, P.counters);
 }
 
-// Delta tracking (GridMedia::sample's loop) for every path of the volume queue, at most P.budget events per pass.
+// Warp-level work fetch for the persistent tracking kernels: every idle lane takes the next index of the queue.
+// Returns the index (>= n when the queue is exhausted).
+__device__ __forceinline__ uint32_t warp_fetch(uint32_t* head, bool want) {
+	unsigned need = __ballot_sync(0xffffffffu, want);
+	unsigned lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == 0 && need) base = atomicAdd(head, (uint32_t)__popc(need));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	return base + __popc(need & ((1u << lane) - 1));
+}
+#define NE_REFILL_LANES 12  // refill a warp once this many lanes are idle (amortises the set-up code)
+
+// Delta tracking (GridMedia::sample's loop) for every path of the volume queue. PERSISTENT warps: a lane whose walk
+// ends (collision, escape, or P.budget events) writes its result and takes the next queued walk, so a warp is never
+// left with one lane grinding through a long walk while 31 idle.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(256) k_wf_track(WfBuf b, WfParams P) {
 	const uint32_t n = b.c->vol;
 	Stats st;
 	st.clear();
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		uint32_t slot = b.qVol[i];
-		PathRec r = load_path(b, slot);
-		float4 hA = b.hA[slot], hB = b.hB[slot], hC = b.hC[slot];
-		Hit h;
-		h.tNear = hA.w;
-		h.tFar = hB.w;
-		h.inst = __float_as_int(hC.z);
-		volume_enter(r.ps, h);
-		const DInstance& in = P.s.inst[h.inst];
-		const DMaterial& m = P.s.mat[in.material];
-		const DVolume& v = P.s.vol[m.volume];
-		PhiloxRng rng;
-		rng.init(P.seed, r.pixel, r.sample, r.dim);
-		Ray rayO = transform_ray(r.ps.ray, in.Mi);
-		Tracker<BRICKMAJ> trk;
-		trk.init(v, m, rayO, 0.0f, h.tFar, st);
-		int e = delta_walk<PhiloxRng, BRICKMAJ>(v, trk, rng, st, P.budget);
-		r.dim = rng.dim;
-		if (e == TRACK_CANDIDATE) {
-			r.tHit = trk.t;
-			store_path(b, slot, r);
-			b.hA[slot].w = 0.0f;
-			b.hB[slot].w = h.tFar;
-			b.qScat[warp_push(&b.c->scat)] = slot;
-		} else if (e == TRACK_BUDGET) {
-			r.ps.ray.o = r.ps.ray.at(trk.t);
-			store_path(b, slot, r);
-			b.hA[slot].w = 0.0f;
-			b.hB[slot].w = h.tFar - trk.t;
-			b.qVolNext[warp_push(&b.c->volNext)] = slot;
-		} else {
-			if (volume_escape(r.ps, h) == PATH_DONE) {
-				b.qFree[warp_push(&b.c->freeN)] = slot;
-			} else {
-				store_path(b, slot, r);
-				b.qNext[warp_push(&b.c->next)] = slot;
+	bool active = false, exhausted = false;
+	uint32_t slot = 0;
+	PathRec r;
+	Hit h;
+	PhiloxRng rng;
+	Tracker<BRICKMAJ> trk;
+	const DVolume* vol = nullptr;
+	int budget = 0;
+	while (true) {
+		unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if (!exhausted && (__popc(idle) >= NE_REFILL_LANES)) {
+			uint32_t i = warp_fetch(&b.c->volHead, !active);
+			if (!active && i < n) {
+				slot = b.qVol[i];
+				r = load_path(b, slot);
+				h.tNear = b.hA[slot].w;
+				h.tFar = b.hB[slot].w;
+				h.inst = __float_as_int(b.hC[slot].z);
+				volume_enter(r.ps, h);
+				const DInstance& in = P.s.inst[h.inst];
+				const DMaterial& m = P.s.mat[in.material];
+				vol = &P.s.vol[m.volume];
+				rng.init(P.seed, r.pixel, r.sample, r.dim);
+				trk.init(*vol, m, transform_ray(r.ps.ray, in.Mi), 0.0f, h.tFar, st);
+				budget = P.budget;
+				active = true;
+			}
+			if (__ballot_sync(0xffffffffu, !active && i >= n)) exhausted = true;
+		}
+		if (__ballot_sync(0xffffffffu, active) == 0) {
+			if (exhausted) break;
+			continue;
+		}
+#pragma unroll 1
+		for (int k = 0; k < 8; k++) {
+			if (active) {
+				int e = budget-- > 0 ? delta_event<PhiloxRng, BRICKMAJ>(*vol, trk, rng, st) : TRACK_BUDGET;
+				if (e != TRACK_MOVED) {
+					active = false;
+					r.dim = rng.dim;
+					if (e == TRACK_CANDIDATE) {
+						r.tHit = trk.t;
+						store_path(b, slot, r);
+						b.hA[slot].w = 0.0f;
+						b.hB[slot].w = h.tFar;
+						b.qScat[warp_push(&b.c->scat)] = slot;
+					} else if (e == TRACK_BUDGET) {
+						r.ps.ray.o = r.ps.ray.at(trk.t);
+						store_path(b, slot, r);
+						b.hA[slot].w = 0.0f;
+						b.hB[slot].w = h.tFar - trk.t;
+						b.qVolNext[warp_push(&b.c->volNext)] = slot;
+					} else if (volume_escape(r.ps, h) == PATH_DONE) {
+						b.qFree[warp_push(&b.c->freeN)] = slot;
+					} else {
+						store_path(b, slot, r);
+						b.qNext[warp_push(&b.c->next)] = slot;
+					}
+				}
 			}
 		}
 	}
@@ -397,56 +434,86 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 }
 
 // intersectTr requests: walk through surfaces to the first medium (first pass), ratio-track through it (at most
-// P.budget events per pass), splat weight * Tr.
+// P.budget events per pass), splat weight * Tr. Persistent warps like k_wf_track.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(256) k_wf_tr(WfBuf b, WfParams P) {
 	const uint32_t n = b.c->tr;
 	Stats st;
 	st.clear();
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 A = b.tA[i], B = b.tB[i], C = b.tC[i], D = b.tD[i];
-		Ray ray;
-		ray.o = V3(A.x, A.y, A.z);
-		ray.d = V3(A.w, B.x, B.y);
-		float Tr = D.x, tRemain = D.y;
-		int inst = __float_as_int(D.z);
-		PhiloxRng rng;
-		rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
-		float tStart = 0;
-		if (inst < 0) {
-			// intersectTr :13-31: through non-medium surfaces until a medium or nothing
-			for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
-				Hit h;
-				st.shadow_rays++;
-				if (!intersect_scene(P.s, ray, h, float(NE_EPSILON3), INFINITY, st)) break;
-				int mi = P.s.inst[h.inst].material;
-				if (mi >= 0 && P.s.mat[mi].has_medium && P.s.mat[mi].volume >= 0) {
-					inst = h.inst;
-					tStart = h.tNear;
-					tRemain = h.tFar - h.tNear;
-					break;
+	bool active = false, exhausted = false;
+	float4 B, C;
+	Ray ray;
+	float Tr = 1, tRemain = 0, tStart = 0;
+	int inst = -1;
+	PhiloxRng rng;
+	Tracker<BRICKMAJ> trk;
+	const DVolume* vol = nullptr;
+	int budget = 0;
+	while (true) {
+		unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if (!exhausted && (__popc(idle) >= NE_REFILL_LANES)) {
+			uint32_t i = warp_fetch(&b.c->trHead, !active);
+			if (!active && i < n) {
+				float4 A = b.tA[i], D = b.tD[i];
+				B = b.tB[i];
+				C = b.tC[i];
+				ray.o = V3(A.x, A.y, A.z);
+				ray.d = V3(A.w, B.x, B.y);
+				Tr = D.x;
+				tRemain = D.y;
+				inst = __float_as_int(D.z);
+				rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
+				tStart = 0;
+				if (inst < 0) {
+					// intersectTr :13-31: through non-medium surfaces until a medium or nothing
+					for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
+						Hit hh;
+						st.shadow_rays++;
+						if (!intersect_scene(P.s, ray, hh, float(NE_EPSILON3), INFINITY, st)) break;
+						int mi = P.s.inst[hh.inst].material;
+						if (mi >= 0 && P.s.mat[mi].has_medium && P.s.mat[mi].volume >= 0) {
+							inst = hh.inst;
+							tStart = hh.tNear;
+							tRemain = hh.tFar - hh.tNear;
+							break;
+						}
+						ray.o = hh.p;
+					}
 				}
-				ray.o = h.p;
+				if (inst >= 0) {  // else nothing found: Li = 0, the request is dropped
+					const DInstance& in = P.s.inst[inst];
+					const DMaterial& m = P.s.mat[in.material];
+					vol = &P.s.vol[m.volume];
+					Ray rayO = transform_ray(ray, in.Mi);
+					rayO.o = rayO.at(tStart);  // GridMedia::Tr :49
+					trk.init(*vol, m, rayO, 0.0f, tRemain, st);
+					budget = P.budget;
+					active = true;
+				}
 			}
-			if (inst < 0) continue;  // nothing found: Li = 0
+			if (__ballot_sync(0xffffffffu, !active && i >= n)) exhausted = true;
 		}
-		const DInstance& in = P.s.inst[inst];
-		const DMaterial& m = P.s.mat[in.material];
-		const DVolume& v = P.s.vol[m.volume];
-		Ray rayO = transform_ray(ray, in.Mi);
-		rayO.o = rayO.at(tStart);  // GridMedia::Tr :49
-		Tracker<BRICKMAJ> trk;
-		trk.init(v, m, rayO, 0.0f, tRemain, st);
-		int e = ratio_walk<PhiloxRng, BRICKMAJ>(v, trk, Tr, rng, st, P.budget);
-		if (e == TRACK_BUDGET) {
-			uint32_t j = warp_push(&b.c->trNext);
-			V3 o = ray.at(tStart + trk.t);
-			b.uA[j] = make_float4(o.x, o.y, o.z, ray.d.x);
-			b.uB[j] = B;
-			b.uC[j] = C;
-			b.uD[j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
-		} else if (Tr != 0) {
-			splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+		if (__ballot_sync(0xffffffffu, active) == 0) {
+			if (exhausted) break;
+			continue;
+		}
+#pragma unroll 1
+		for (int k = 0; k < 8; k++) {
+			if (active) {
+				int e = budget-- > 0 ? ratio_event<PhiloxRng, BRICKMAJ>(*vol, trk, Tr, rng, st) : TRACK_BUDGET;
+				if (e == TRACK_BUDGET) {
+					active = false;
+					uint32_t j = warp_push(&b.c->trNext);
+					V3 o = ray.at(tStart + trk.t);
+					b.uA[j] = make_float4(o.x, o.y, o.z, ray.d.x);
+					b.uB[j] = B;
+					b.uC[j] = C;
+					b.uD[j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
+				} else if (e == TRACK_END) {
+					active = false;
+					if (Tr != 0) splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+				}
+			}
 		}
 	}
 	flush_stats_wf(st, P.counters);
@@ -526,7 +593,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	P.H = ctx->H;
 	P.sppBegin = sppBegin;
 	P.bounces = bounces;
-	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 48)));
+	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
 	P.seed = seed;
 	P.counters = ctx->dCounters;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
