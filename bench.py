@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per reference step / cpu_baseline sample")
     ap.add_argument("--spp", type=int, default=SPP, help="debug only: a value other than 64 is not the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,21 +190,14 @@ def main():
     cam = cam_params.make(W / H, ctx.lib)
     ctx.set_camera(cam)
     ctx.render(W, H, 0, 0, BOUNCES)  # allocate the accumulation buffer
-    ptr, nfloat, _ = ctx.accum_buffer()
-
-    class _Alias:  # the library's accumulation buffer as a torch tensor (for the NCCL reduce)
-        __cuda_array_interface__ = {"shape": (nfloat,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-    accum = torch.as_tensor(_Alias(), device=f"cuda:{local_rank}")
+    from narvalengine_b200.multigpu import PartitionedFrame, alias_accum
+    frame = PartitionedFrame(ctx, alias_accum(ctx, local_rank), rank, world, dist if world > 1 else None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step(i):
-        """One frame: this rank's 64 samples per pixel (sample indices rank*spp ...), then the cross-GPU sum."""
-        ctx.clear()
-        ctx.render(W, H, rank * spp, (rank + 1) * spp, BOUNCES, seed=1 + i)
-        if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                ctx.set_samples_accumulated(world * spp)
+        """One frame: this rank's 64 samples per pixel of the world*64 the frame holds (weak scaling), then the one
+        exchange step of the path: the sum of the per-GPU accumulation buffers onto rank 0 (NCCL reduce)."""
+        frame.render(W, H, world * spp, BOUNCES, seed=1 + i)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -261,7 +255,7 @@ def main():
 
     # ---- e2e: the reference-facing calls with HOST buffers (scene H2D + frame D2H inside the timed region)
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         tm = np.empty((H, W, 3), np.float32)
         desc = b.desc()
         h2d = int(grid.nbytes + 4096)

@@ -164,6 +164,23 @@ int ne_b200_make_transform(const float position[3], const float rotation_deg[3],
 int ne_b200_camera_make(const float look_from[3], const float look_at[3], const float up[3], float vfov_deg,
                         float aspect, float aperture, float focus_distance, ne_b200_camera* out);
 
+/* Host-side scene builders, exposed so a front end (and the CPU test-suite) can inspect exactly what
+ * ne_b200_scene_upload will put in HBM. Pure host code. Two-call pattern: pass NULL output arrays to get the sizes.
+ *
+ * Brick-sparse grid built from a ne_b200_volume (replaces the dense Texture that ResourceManager::loadVolasTexture /
+ * loadVDBasTexture hand to GridMedia, ResourceManager.cpp:165-286): dims = {bx, by, bz, n_slots}; table[bz][by][bx] =
+ * slot or -1; inv_majorant[bz][by][bx] = 1 / max voxel over the brick's trilinear support [8b-1, 8b+8]^3 (0 = empty);
+ * pool = n_slots records of 9x9x9 voxels [8b, 8b+8]^3 (apron layout, x fastest); *max_density =
+ * GridMedia::calculateMaxDensity (GridMedia.h:16-21). */
+int ne_b200_host_build_bricks(const ne_b200_volume* volume, int32_t dims[4], int32_t* table, float* inv_majorant,
+                              float* pool, float* max_density);
+/* Binned-SAH 2-wide BVH over a triangle soup (replaces BVH::init, src/primitives/BVH.cpp:6-106): counts =
+ * {n_nodes, n_triangle_slots}; nodes = n_nodes records of 16 x 4 bytes {lo0[3], hi0[3], lo1[3], hi1[3], child0,
+ * child1, 0, 0} (child >= 0: node index; child < 0: leaf, ~child = (first_slot << 3) | count);
+ * triangles = n_triangle_slots records of 12 floats {v0.xyz, bits(original triangle index), v1.xyz, 0, v2.xyz, 0}. */
+int ne_b200_host_build_bvh(const float* positions, int32_t n_vertices, const uint32_t* indices, int32_t n_triangles,
+                           int32_t counts[2], void* nodes, float* triangles);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Context, scene, render (replaces OfflineEngine, src/core/OfflineEngine.cpp).
  * ---------------------------------------------------------------------------------------------------------- */

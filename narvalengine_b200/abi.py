@@ -83,6 +83,8 @@ _ctx = C.c_void_p
 SYMBOLS = {
     "ne_b200_make_transform": (C.c_int, [pf32, pf32, pf32, pf32, pf32]),
     "ne_b200_camera_make": (C.c_int, [pf32, pf32, pf32, f32, f32, f32, f32, C.POINTER(Camera)]),
+    "ne_b200_host_build_bricks": (C.c_int, [C.POINTER(Volume), pi32, pi32, pf32, pf32, pf32]),
+    "ne_b200_host_build_bvh": (C.c_int, [pf32, i32, pu32, i32, pi32, C.c_void_p, pf32]),
     "ne_b200_last_error": (C.c_char_p, []),
     "ne_b200_device_count": (C.c_int, []),
     "ne_b200_create": (C.c_int, [C.c_int, C.POINTER(_ctx)]),

@@ -5,9 +5,11 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <thread>
 
 namespace ne {
+void set_error(const std::string& s);  // ne_api.cu
 
 // ---------------------------------------------------------------------------------------------------------------
 // Transform arithmetic in glm 0.9.9.4's operation order (includes/glm):
@@ -487,3 +489,41 @@ void host_build_bricks(const ne_b200_volume& v, HostBricks& out) {
 }
 
 }  // namespace ne
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI of the builders (include/ne_b200.h "Host-side scene builders")
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ne_b200_host_build_bricks(const ne_b200_volume* v, int32_t dims[4], int32_t* table, float* inv_majorant, float* pool, float* max_density) {
+	if (!v || !dims) { ne::set_error("null argument"); return NE_B200_ERR_INVALID; }
+	if (v->width <= 0 || v->height <= 0 || v->depth <= 0 || (!v->dense && v->n_leaves > 0 && (!v->leaf_origin || !v->leaf_values))) {
+		ne::set_error("bad volume");
+		return NE_B200_ERR_INVALID;
+	}
+	ne::HostBricks hb;
+	ne::host_build_bricks(*v, hb);
+	dims[0] = hb.bx; dims[1] = hb.by; dims[2] = hb.bz;
+	dims[3] = int32_t(hb.pool.size() / ne::BRICK_VOX);
+	if (table) memcpy(table, hb.table.data(), hb.table.size() * sizeof(int32_t));
+	if (inv_majorant) memcpy(inv_majorant, hb.binv.data(), hb.binv.size() * sizeof(float));
+	if (pool) memcpy(pool, hb.pool.data(), hb.pool.size() * sizeof(float));
+	if (max_density) *max_density = hb.maxDensity;
+	return NE_B200_OK;
+}
+
+int ne_b200_host_build_bvh(const float* positions, int32_t n_vertices, const uint32_t* indices, int32_t n_triangles, int32_t counts[2], void* nodes,
+                           float* triangles) {
+	if (!counts || n_vertices < 0 || n_triangles < 0 || (n_triangles > 0 && (!positions || !indices))) { ne::set_error("bad argument"); return NE_B200_ERR_INVALID; }
+	for (int t = 0; t < 3 * n_triangles; t++)
+		if (indices[t] >= uint32_t(n_vertices)) { ne::set_error("mesh index out of range"); return NE_B200_ERR_INVALID; }
+	ne::HostBvh hb;
+	ne::host_build_bvh(positions, n_vertices, indices, n_triangles, hb);
+	counts[0] = int32_t(hb.nodes.size());
+	counts[1] = int32_t(hb.tri.size() / 12);
+	if (nodes) memcpy(nodes, hb.nodes.data(), hb.nodes.size() * sizeof(ne::BvhNode));
+	if (triangles) memcpy(triangles, hb.tri.data(), hb.tri.size() * sizeof(float));
+	return NE_B200_OK;
+}
+
+}  // extern "C"

@@ -481,6 +481,42 @@ float neref_ggx_pdf(float alpha, const float* wi, const float* h) { GGXDistribut
 float neref_fresnel(float c) { FresnelSchilck f; return f.eval(c).x; }
 float neref_hg_eval(float g, const float* in, const float* out) { HG hg(g); return hg.eval(v3(in), v3(out)); }
 void neref_hg_sample(float g, uint32_t seed, float* out) { neref_seed(seed); HG hg(g); put3(out, hg.sample(glm::vec3(0, 0, 1))); }
+// -- primitive-level entry points: the objects the reference's own unit tests exercise (unitTests/tests.cpp) ------
+void neref_to_lcs(const float* v, const float* ns, const float* ss, const float* ts, float* out) { put3(out, toLCS(v3(v), v3(ns), v3(ss), v3(ts))); }
+void neref_to_world(const float* v, const float* ns, const float* ss, const float* ts, float* out) { put3(out, toWorld(v3(v), v3(ns), v3(ss), v3(ts))); }
+// Triangle::intersect (primitives/Triangle.cpp:49-81) on a stand-alone triangle of 3 position-only vertices.
+int neref_triangle_intersect(const float* v0, const float* v1, const float* v2, const float* o, const float* d, float* tNearFar, float* hitPoint, float* normal) {
+	float data[9] = {v0[0], v0[1], v0[2], v1[0], v1[1], v1[2], v2[0], v2[1], v2[2]};
+	Triangle t(&data[0], &data[3], &data[6]);
+	RayIntersection ri;
+	bool did = t.intersect(Ray(v3(o), v3(d)), ri);
+	tNearFar[0] = ri.tNear; tNearFar[1] = ri.tFar;
+	put3(hitPoint, ri.hitPoint); put3(normal, ri.normal);
+	return did ? 1 : 0;
+}
+void neref_triangle_barycentric(const float* v0, const float* v1, const float* v2, const float* p, float* out) {
+	float data[9] = {v0[0], v0[1], v0[2], v1[0], v1[1], v1[2], v2[0], v2[1], v2[2]};
+	Triangle t(&data[0], &data[3], &data[6]);
+	put3(out, t.barycentricCoordinates(v3(p), v3(v0), v3(v1), v3(v2)));
+}
+int neref_point_in_triangle_range(const float* p, const float* a, const float* b, const float* c) { return isPointInsideTriangleRange(v3(p), v3(a), v3(b), v3(c)) ? 1 : 0; }
+// AABB::intersect (primitives/AABB.cpp:48-79).
+int neref_aabb_intersect(const float* bmin, const float* bmax, const float* o, const float* d, float* tNearFar, float* hitPoint, float* normal) {
+	AABB box(v3(bmin), v3(bmax));
+	RayIntersection ri;
+	bool did = box.intersect(Ray(v3(o), v3(d)), ri);
+	tNearFar[0] = ri.tNear; tNearFar[1] = ri.tFar;
+	put3(hitPoint, ri.hitPoint); put3(normal, ri.normal);
+	return did ? 1 : 0;
+}
+// IsotropicPhaseFunction::sample / pdf after mt.seed(seed) (materials/Medium.h:43-63).
+float neref_isotropic_sample(uint32_t seed, float* out) {
+	neref_seed(seed);
+	IsotropicPhaseFunction p;
+	glm::vec3 s = p.sample(glm::vec3(0, 0, 1));
+	put3(out, s);
+	return p.pdf(glm::vec3(0, 0, 1), s);
+}
 void neref_tonemap(const float* in, int n, float* out) {
 	// OfflineEngine::postProcessing (OfflineEngine.cpp:39-52) through a real OfflineEngine object.
 	static OfflineEngine* eng = nullptr;

@@ -33,7 +33,7 @@ class RefOracle:
         L.neref_scene_destroy.argtypes = [C.c_void_p]
         L.neref_render.restype = C.c_double
         for n in ("neref_area_to_solid_angle", "neref_power_heuristic", "neref_roughness_to_alpha", "neref_ggx_D",
-                  "neref_ggx_G", "neref_ggx_pdf", "neref_fresnel", "neref_hg_eval"):
+                  "neref_ggx_G", "neref_ggx_pdf", "neref_fresnel", "neref_hg_eval", "neref_isotropic_sample"):
             getattr(L, n).restype = C.c_float
 
     # ---- pure functions
@@ -93,6 +93,40 @@ class RefOracle:
         o = np.zeros(3, np.float32)
         self.lib.neref_hg_sample(f32(g), C.c_uint32(seed), _p(o))
         return o
+
+    # ---- primitive-level entry points (the objects unitTests/tests.cpp exercises)
+    def to_lcs(self, v, ns, ss, ts):
+        o = np.zeros(3, np.float32)
+        self.lib.neref_to_lcs(_p(f32a(v)), _p(f32a(ns)), _p(f32a(ss)), _p(f32a(ts)), _p(o))
+        return o
+
+    def to_world(self, v, ns, ss, ts):
+        o = np.zeros(3, np.float32)
+        self.lib.neref_to_world(_p(f32a(v)), _p(f32a(ns)), _p(f32a(ss)), _p(f32a(ts)), _p(o))
+        return o
+
+    def triangle_intersect(self, v0, v1, v2, o, d):
+        t, p, n = np.zeros(2, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        did = self.lib.neref_triangle_intersect(_p(f32a(v0)), _p(f32a(v1)), _p(f32a(v2)), _p(f32a(o)), _p(f32a(d)), _p(t), _p(p), _p(n))
+        return bool(did), t, p, n
+
+    def triangle_barycentric(self, v0, v1, v2, p):
+        o = np.zeros(3, np.float32)
+        self.lib.neref_triangle_barycentric(_p(f32a(v0)), _p(f32a(v1)), _p(f32a(v2)), _p(f32a(p)), _p(o))
+        return o
+
+    def point_in_triangle_range(self, p, a, b, c):
+        return bool(self.lib.neref_point_in_triangle_range(_p(f32a(p)), _p(f32a(a)), _p(f32a(b)), _p(f32a(c))))
+
+    def aabb_intersect(self, bmin, bmax, o, d):
+        t, p, n = np.zeros(2, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        did = self.lib.neref_aabb_intersect(_p(f32a(bmin)), _p(f32a(bmax)), _p(f32a(o)), _p(f32a(d)), _p(t), _p(p), _p(n))
+        return bool(did), t, p, n
+
+    def isotropic_sample(self, seed):
+        o = np.zeros(3, np.float32)
+        pdf = self.lib.neref_isotropic_sample(C.c_uint32(seed), _p(o))
+        return o, pdf
 
     def tonemap(self, rgb):
         a = f32a(rgb).reshape(-1, 3)
