@@ -77,13 +77,15 @@ def test_sample_ranges_are_additive(ctx):
 @pytest.mark.parametrize("name", ["volume", "mixed"])
 def test_bounded_walks_are_unbiased(ctx, name, monkeypatch):
     """Stopping every tracking walk after a handful of events and resuming it in the next pass (memoryless restart)
-    must not change the estimate: compare a 3-event budget with unbounded walks at high spp."""
+    must not change the estimate: compare a 3-event budget with unbounded walks at high spp. Same seed on both sides
+    (common random numbers: only the walks that were actually cut diverge), because two independent seeds of the mixed
+    scene differ by rel-MSE 8e-3 on fireflies alone (measured, tools/diag_budget.py) - above any useful gate."""
     mk, cam = CASES[name]
     b = mk()
     monkeypatch.setenv("NE_B200_TRACK_BUDGET", "3")
     a = render(ctx, b, cam, 24, 16, 8192, seed=11)
     monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
-    u = render(ctx, b, cam, 24, 16, 8192, seed=12)
+    u = render(ctx, b, cam, 24, 16, 8192, seed=11)
     assert abs(luminance(a).mean() - luminance(u).mean()) / luminance(u).mean() < 0.01
     assert rel_mse(a, u) < 5e-3
 
