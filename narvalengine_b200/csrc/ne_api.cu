@@ -475,9 +475,15 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 		o.W = hb.W; o.H = hb.H; o.D = hb.D; o.bx = hb.bx; o.by = hb.by; o.bz = hb.bz;
 		o.max_density = hb.maxDensity;
 		o.inv_max_density = 1.0f / hb.maxDensity;
-		if ((rc = push_alloc(ctx, hb.table.data(), hb.table.size(), &o.table))) return rc;
+		// one 8-byte cell per brick: {slot, 1/majorant}; a brick without a record has nothing to collide with
+		std::vector<int2> cells(hb.table.size());
+		for (size_t b = 0; b < cells.size(); b++) {
+			float inv = hb.table[b] >= 0 ? hb.binv[b] : 0.0f;
+			cells[b].x = hb.table[b];
+			memcpy(&cells[b].y, &inv, 4);
+		}
+		if ((rc = push_alloc(ctx, cells.data(), cells.size(), &o.cells))) return rc;
 		if ((rc = push_alloc(ctx, hb.pool.data(), hb.pool.size(), &o.pool))) return rc;
-		if ((rc = push_alloc(ctx, hb.binv.data(), hb.binv.size(), &o.binv))) return rc;
 	}
 
 	// ---- instances + meshes

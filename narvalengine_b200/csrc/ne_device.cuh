@@ -484,7 +484,7 @@ NE_D float interpolated_density(const DVolume& v, V3 g) {
 	g = gmin(gmax(V3(0.0f), g), V3(float(v.W), float(v.H), float(v.D)));
 	int ix = int(floorf(g.x)), iy = int(floorf(g.y)), iz = int(floorf(g.z));
 	if (ix >= v.W || iy >= v.H || iz >= v.D) return 0.0f;  // every corner is at or beyond the grid: density() = 0
-	int b = __ldg(v.table + ((iz >> 3) * v.by + (iy >> 3)) * v.bx + (ix >> 3));
+	int b = __ldg(&v.cells[((iz >> 3) * v.by + (iy >> 3)) * v.bx + (ix >> 3)].x);
 	if (b < 0) return 0.0f;
 	V3 d = g - V3(float(ix), float(iy), float(iz));
 	// apron layout: all eight corners are in this brick's 9^3 record
@@ -500,36 +500,57 @@ NE_D float interpolated_density(const DVolume& v, V3 g) {
 NE_D V3 ocs_to_gcs(const DVolume& v, V3 p) { return (p + V3(0.5f)) * V3(float(v.W), float(v.H), float(v.D)); }
 NE_D float density_at(const DVolume& v, const Ray& rayO, float t) { return interpolated_density(v, ocs_to_gcs(v, rayO.at(t))); }
 
-// Brick DDA over the ray segment [0, tFar] of an OCS ray (origin already moved to the segment start).
+// Trilinear density at grid point g, known to lie in brick (bx,by,bz) whose record is `slot` (>= 0): no table
+// look-up, eight loads from ONE 9^3 record. The local cell is clamped into the record, so a point that rounding put a
+// hair outside the brick is evaluated on the brick's own face (the brick majorant still bounds it).
+NE_D float brick_density(const float* __restrict__ pool, int slot, V3 g, int bx, int by, int bz) {
+	float lx = g.x - float(bx << 3), ly = g.y - float(by << 3), lz = g.z - float(bz << 3);
+	lx = fminf(fmaxf(lx, 0.0f), 8.0f); ly = fminf(fmaxf(ly, 0.0f), 8.0f); lz = fminf(fmaxf(lz, 0.0f), 8.0f);
+	int ix = min(int(lx), 7), iy = min(int(ly), 7), iz = min(int(lz), 7);
+	float fx = lx - float(ix), fy = ly - float(iy), fz = lz - float(iz);
+	const float* p = pool + size_t(slot) * BRICK_VOX + (iz * 9 + iy) * 9 + ix;
+	float v000 = __ldg(p), v100 = __ldg(p + 1);
+	float v010 = __ldg(p + 9), v110 = __ldg(p + 10);
+	float v001 = __ldg(p + 81), v101 = __ldg(p + 82);
+	float v011 = __ldg(p + 90), v111 = __ldg(p + 91);
+	float d00 = fmaf(fx, v100 - v000, v000), d10 = fmaf(fx, v110 - v010, v010);
+	float d01 = fmaf(fx, v101 - v001, v001), d11 = fmaf(fx, v111 - v011, v011);
+	float d0 = fmaf(fy, d10 - d00, d00), d1 = fmaf(fy, d11 - d01, d01);
+	return fmaf(fz, d1 - d0, d0);
+}
+
+// Brick DDA over the grid-space ray g(t) = g0 + t * gd. Branch-free step: the axis with the nearest crossing
+// advances; all lanes of a warp run the same instructions whatever axis each of them crosses.
 struct BrickDDA {
 	int bx, by, bz;       // current brick
-	int sx, sy, sz;       // step direction
 	float nx, ny, nz;     // ray parameter of the next boundary crossing per axis
-	float dx, dy, dz;     // parameter distance between crossings per axis
-	NE_D void init(const DVolume& v, const Ray& r) {
-		V3 g = ocs_to_gcs(v, r.o);
-		V3 res(float(v.W), float(v.H), float(v.D));
-		V3 gd = r.d * res;  // d(grid coord)/dt
-		float fx = g.x * 0.125f, fy = g.y * 0.125f, fz = g.z * 0.125f;
-		bx = min(max(int(floorf(fx)), 0), v.bx - 1);
-		by = min(max(int(floorf(fy)), 0), v.by - 1);
-		bz = min(max(int(floorf(fz)), 0), v.bz - 1);
-		sx = gd.x > 0 ? 1 : -1; sy = gd.y > 0 ? 1 : -1; sz = gd.z > 0 ? 1 : -1;
-		dx = gd.x != 0 ? 8.0f / fabsf(gd.x) : INFINITY;
-		dy = gd.y != 0 ? 8.0f / fabsf(gd.y) : INFINITY;
-		dz = gd.z != 0 ? 8.0f / fabsf(gd.z) : INFINITY;
-		nx = gd.x != 0 ? (float((gd.x > 0 ? bx + 1 : bx) * 8) - g.x) / gd.x : INFINITY;
-		ny = gd.y != 0 ? (float((gd.y > 0 ? by + 1 : by) * 8) - g.y) / gd.y : INFINITY;
-		nz = gd.z != 0 ? (float((gd.z > 0 ? bz + 1 : bz) * 8) - g.z) / gd.z : INFINITY;
+	float dx, dy, dz;     // parameter distance between crossings per axis (sign of gd folded into the step below)
+	NE_D void init(int nbx, int nby, int nbz, V3 g, V3 gd) {
+		bx = min(max(int(floorf(g.x * 0.125f)), 0), nbx - 1);
+		by = min(max(int(floorf(g.y * 0.125f)), 0), nby - 1);
+		bz = min(max(int(floorf(g.z * 0.125f)), 0), nbz - 1);
+		float ix = 1.0f / gd.x, iy = 1.0f / gd.y, iz = 1.0f / gd.z;  // +-inf for an axis-parallel ray
+		dx = gd.x != 0 ? 8.0f * fabsf(ix) : INFINITY;
+		dy = gd.y != 0 ? 8.0f * fabsf(iy) : INFINITY;
+		dz = gd.z != 0 ? 8.0f * fabsf(iz) : INFINITY;
+		nx = gd.x != 0 ? (float((gd.x > 0 ? bx + 1 : bx) << 3) - g.x) * ix : INFINITY;
+		ny = gd.y != 0 ? (float((gd.y > 0 ? by + 1 : by) << 3) - g.y) * iy : INFINITY;
+		nz = gd.z != 0 ? (float((gd.z > 0 ? bz + 1 : bz) << 3) - g.z) * iz : INFINITY;
 	}
 	NE_D float exit_t() const { return fminf(nx, fminf(ny, nz)); }
 	// advance to the next brick; false when the walk leaves the table
-	NE_D bool step(const DVolume& v) {
-		if (nx <= ny && nx <= nz) { bx += sx; nx += dx; return bx >= 0 && bx < v.bx; }
-		if (ny <= nz) { by += sy; ny += dy; return by >= 0 && by < v.by; }
-		bz += sz; nz += dz; return bz >= 0 && bz < v.bz;
+	NE_D bool step(int nbx, int nby, int nbz, V3 gd) {
+		bool cx = nx <= ny && nx <= nz;
+		bool cy = !cx && ny <= nz;
+		bool cz = !cx && !cy;
+		bx += cx ? (gd.x > 0 ? 1 : -1) : 0;
+		by += cy ? (gd.y > 0 ? 1 : -1) : 0;
+		bz += cz ? (gd.z > 0 ? 1 : -1) : 0;
+		nx += cx ? dx : 0.0f;
+		ny += cy ? dy : 0.0f;
+		nz += cz ? dz : 0.0f;
+		return (unsigned(bx) < unsigned(nbx)) & (unsigned(by) < unsigned(nby)) & (unsigned(bz) < unsigned(nbz));
 	}
-	NE_D float inv_majorant(const DVolume& v) const { return __ldg(v.binv + (bz * v.by + by) * v.bx + bx); }  // 0 = empty
 };
 
 }  // namespace ne

@@ -47,6 +47,11 @@ NE_D bool intersect_tr(const DScene& s, Ray ray, float& Tr, R& rng, Stats& st) {
 		if (!hitSurface) return false;
 		int mi = s.inst[h.inst].material;
 		if (mi >= 0 && s.mat[mi].has_medium && s.mat[mi].volume >= 0) {
+			if (!FAITHFUL) {  // the wavefront's transmittance requests move the origin to the medium's entry in WCS
+				ray.o = ray.at(h.tNear);
+				h.tFar -= h.tNear;
+				h.tNear = 0;
+			}
 			Tr *= grid_tr<R, BRICKMAJ>(s.inst[h.inst], s.mat[mi], s.vol[s.mat[mi].volume], ray, h.tNear, h.tFar, rng, st);
 			return true;
 		}
@@ -223,9 +228,11 @@ NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& 
 	const DVolume& v = s.vol[m.volume];
 	volume_enter(ps, isect);
 	Ray rayO = transform_ray(ps.ray, in.Mi);
+	typename WalkRngOf<BRICKMAJ, R>::type wr;
+	wr.start(rng);
 	Tracker<BRICKMAJ> trk;
-	trk.init(v, m, rayO, 0.0f, isect.tFar, st);
-	if (delta_walk<R, BRICKMAJ>(v, trk, rng, st, NE_NO_BUDGET) != TRACK_CANDIDATE) return volume_escape(ps, isect);
+	trk.init(v, m, rayO, 0.0f, isect.tFar, wr, st);
+	if (delta_walk(v, trk, wr, st, NE_NO_BUDGET) != TRACK_CANDIDATE) return volume_escape(ps, isect);
 	return volume_scatter(s, ps, isect, rayO, trk.t, rng, sink, st);
 }
 

@@ -17,7 +17,9 @@ struct TapeRng {
 		if (pos >= n) { overflow = true; return 0.5f; }
 		return tape[pos++];
 	}
-	NE_D void begin_event() {}
+	NE_D void next_block(uint32_t w[4]) {
+		for (int k = 0; k < 4; k++) w[k] = uint32_t(next() * 16777216.0f) * 2654435761u;
+	}
 };
 
 NE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
@@ -42,18 +44,9 @@ NE_HD float u32_to_unit(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f
 struct PhiloxRng {
 	uint32_t k0, k1, pixel, sample, dim, stream;
 	uint32_t b0, b1, b2, b3;
-	bool fresh;  // the block of the current (4-aligned) dimension is already in b0..b3
 	NE_D void init(uint64_t seed, uint32_t px, uint32_t smp, uint32_t dimension = 0, uint32_t strm = 0) {
 		k0 = uint32_t(seed); k1 = uint32_t(seed >> 32); pixel = px; sample = smp; dim = dimension; stream = strm;
-		fresh = false;
 		if (dim & 3) refill();
-	}
-	// Start a tracking event on a fresh block: all lanes of a warp generate their block HERE, together, instead of
-	// each lane refilling inside whichever next() happens to cross a multiple of four (a divergent ~70-instruction branch).
-	NE_D void begin_event() {
-		dim = (dim + 3u) & ~3u;
-		refill();
-		fresh = true;
 	}
 	NE_D void refill() {
 		uint32_t o[4];
@@ -62,13 +55,53 @@ struct PhiloxRng {
 	}
 	NE_D float next() {
 		uint32_t l = dim & 3;
-		if (l == 0 && !fresh) refill();
-		fresh = false;
+		if (l == 0) refill();
 		dim++;
 		uint32_t x = l == 0 ? b0 : (l == 1 ? b1 : (l == 2 ? b2 : b3));
 		return u32_to_unit(x);
 	}
+	// One whole block (128 bits) at the next 4-aligned dimension: the key of a tracking walk's own stream (PcgRng).
+	NE_D void next_block(uint32_t w[4]) {
+		dim = (dim + 3u) & ~3u;
+		philox4x32_10(pixel, sample, dim >> 2, stream, k0, k1, w);
+		dim += 4;
+	}
 };
+
+// The uniform stream of ONE tracking walk in production (per-brick-majorant) mode: PCG32 (XSH-RR 64/32, O'Neill 2014)
+// whose 64-bit state and stream selector are one Philox block of the path's (seed, pixel, sample, dimension) counter.
+// Every walk is therefore still a pure function of the Philox key - reproducible on any GPU in any order - but a
+// free-flight/acceptance draw costs ~10 instructions instead of a share of a 10-round Philox block generated at a
+// divergent point of the event loop. A walk that is cut (budget) and resumed re-keys from the next Philox block.
+struct PcgRng {
+	uint64_t state, inc;
+	template <class R>
+	NE_D void start(R& base) {
+		uint32_t w[4];
+		base.next_block(w);
+		state = (uint64_t(w[0]) << 32) | w[1];
+		inc = ((uint64_t(w[2]) << 32) | w[3]) | 1ull;
+		state = state * 6364136223846793005ull + inc;
+	}
+	NE_D float next() {
+		uint64_t old = state;
+		state = old * 6364136223846793005ull + inc;
+		uint32_t xs = uint32_t(((old >> 18u) ^ old) >> 27u);
+		uint32_t rot = uint32_t(old >> 59u);
+		return u32_to_unit((xs >> rot) | (xs << ((32u - rot) & 31u)));
+	}
+};
+// Reference-order walks (global majorant, tape tests) draw straight from the path's own source.
+template <class R>
+struct PassRng {
+	R* r;
+	NE_D void start(R& base) { r = &base; }
+	NE_D float next() { return r->next(); }
+};
+template <bool BRICKMAJ, class R>
+struct WalkRngOf { typedef PassRng<R> type; };
+template <class R>
+struct WalkRngOf<true, R> { typedef PcgRng type; };
 
 // A side stream for work that is evaluated out of line (the transmittance walk of a next-event request runs in
 // its own wavefront kernel): Philox forks to counter word 3 = `stream`, dimension 0; a tape just continues.
@@ -85,7 +118,6 @@ struct Fork<PhiloxRng> {
 		f = base;
 		f.stream = stream;
 		f.dim = 0;
-		f.fresh = false;
 	}
 	NE_D PhiloxRng& get() { return f; }
 };

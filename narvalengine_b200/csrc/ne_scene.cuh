@@ -15,16 +15,16 @@ struct DTexture {
 	const void* texels;
 };
 
-// Brick-sparse density grid (GridMedia's Texture, src/materials/GridMedia.h). table[bz][by][bx] = brick slot or
-// -1 (nothing but zeros within reach); pool[slot*729 + 81*z + 9*y + x] holds the 9^3 voxels [8b, 8b+8]^3 (apron
-// layout: the trilinear stencil of any cell of the brick is inside its own record); binv[bz][by][bx] = 1 / (max voxel
-// over [8b-1, 8b+8]^3), the reciprocal per-brick majorant, or 0 when that support is empty.
+// Brick-sparse density grid (GridMedia's Texture, src/materials/GridMedia.h). cells[bz][by][bx] = {slot, invMaj}:
+// slot = brick record or -1 (nothing but zeros within reach); invMaj = float bits of 1 / (max voxel over
+// [8b-1, 8b+8]^3), the reciprocal per-brick majorant, 0 when the brick has nothing to collide with. One 8-byte
+// load per brick entered. pool[slot*729 + 81*z + 9*y + x] holds the 9^3 voxels [8b, 8b+8]^3 (apron layout: the
+// trilinear stencil of any cell of the brick is inside its own record).
 struct DVolume {
 	int W, H, D;
 	int bx, by, bz;
-	const int* table;
+	const int2* cells;
 	const float* pool;
-	const float* binv;
 	float max_density, inv_max_density;  // GridMedia::invMaxDensity, GridMedia.cpp:12
 };
 

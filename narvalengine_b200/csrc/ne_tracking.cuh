@@ -1,118 +1,166 @@
 // ne_tracking.cuh — GridMedia::Tr (ratio tracking, materials/GridMedia.cpp:45-69) and GridMedia::sample (delta
 // tracking, :71-100) as RESUMABLE walks made of single EVENTS. Included by ne_device.cuh (needs density_at,
-// BrickDDA, bsdf_sample).
+// brick_density, BrickDDA, bsdf_sample).
 //
-// A Tracker walks the OCS ray segment [0, tFar]; one event() either proposes a candidate collision point or moves
-// to the next brick:
-//   BRICKMAJ = false   the reference's walk: t -= log(1 - xi) * invMaxDensity / sigma_bar with the single global majorant
-//                      (draw for draw what GridMedia does; used by the tape tests and NE_B200_RENDER_GLOBAL_MAJORANT)
-//   BRICKMAJ = true    the same exponential walk against the majorant of the 8^3 brick the point is in, re-started at
-//                      every brick boundary (memoryless, so the free-flight distribution is unchanged); empty bricks
-//                      are crossed without a sample
-// Because walks are sequences of independent events they can be stopped anywhere: the wavefront's tracking kernels
-// keep all lanes of a warp busy by handing a lane the next queued walk as soon as its own ends, and bound the events
-// of one pass (`budget`); a stopped walk moves its origin to the point reached and continues in the next pass.
+// A Tracker walks the OCS ray segment [tStart, tFar]:
+//   Tracker<false>  the reference's walk: t -= log(1 - xi) * invMaxDensity / sigma_bar against the single global majorant,
+//                   draw for draw what GridMedia does (tape tests, NE_B200_RENDER_GLOBAL_MAJORANT).
+//   Tracker<true>   production: the same exponential free flights measured in OPTICAL DEPTH against the piecewise-
+//                   constant majorant of the 8^3 bricks the ray crosses. One exponential variate `tau` is drawn per
+//                   candidate; crossing a brick only subtracts (length x sigma_bar x brick majorant) from it - no
+//                   uniform, no logarithm, no density look-up - and empty bricks subtract nothing. The free-flight
+//                   distribution is exactly that of delta tracking with a local majorant (unbiased).
+// One event() = one brick crossing or one candidate. Because walks are sequences of independent events they can be
+// stopped anywhere: the wavefront's tracking kernels hand a lane the next queued walk as soon as its own ends, and bound
+// the events of one pass (`budget`); a stopped walk moves its origin to the point reached, and the next pass draws a
+// fresh tau (memoryless).
 #pragma once
 
 namespace ne {
 
 enum { TRACK_END = 0, TRACK_CANDIDATE = 1, TRACK_BUDGET = 2, TRACK_MOVED = 3 };
 
-template <bool BRICKMAJ>
-struct Tracker {
-	Ray ray;  // OCS, origin at the segment start
-	float t, tFar;
-	float invSig;  // 1 / sigma_bar-per-unit-density = 1 / avg(extinction * densityMultiplier)
-	float sig;
-	float invMaj;  // 1 / current majorant density (global: GridMedia::invMaxDensity); 0 = empty brick
-	float step;    // invMaj / sig: mean free path against the current majorant
-	float tExit;   // end of the current brick (BRICKMAJ)
-	BrickDDA dda;
+template <class W>
+NE_D float exp_variate(W& wr) { return -logf(1 - wr.next()); }
 
-	NE_D void init(const DVolume& v, const DMaterial& m, Ray rayOCS, float tStart, float tEnd, Stats& st) {
+template <bool BRICKMAJ>
+struct Tracker;
+
+template <>
+struct Tracker<false> {
+	Ray ray;  // OCS
+	float t, tFar;
+	float sig;     // sigma_bar per unit density = avg(extinction * densityMultiplier)
+	float invMaj;  // GridMedia::invMaxDensity
+	template <class W>
+	NE_D void init(const DVolume& v, const DMaterial& m, Ray rayOCS, float tStart, float tEnd, W&, Stats&) {
 		ray = rayOCS;
 		t = tStart;
 		tFar = tEnd;
 		V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
 		sig = avg(ext * m.density_mult);
-		if (BRICKMAJ) {
-			invSig = 1.0f / sig;
-			dda.init(v, ray);  // tStart is 0 for every brick walk (the origin has been moved to the segment start)
-			enter_brick(v, st);
-		} else {
-			invMaj = v.inv_max_density;
-		}
+		invMaj = v.inv_max_density;
 	}
-	NE_D void enter_brick(const DVolume& v, Stats& st) {
+	// TRACK_CANDIDATE: `dens` is the density at the proposed collision point t; TRACK_END: the segment is finished.
+	template <class W>
+	NE_D int advance(const DVolume& v, W& wr, float& dens, Stats&) {
+		t -= logf(1 - wr.next()) * invMaj / sig;  // GridMedia.cpp:56 / :82
+		if (t >= tFar) return TRACK_END;
+		dens = density_at(v, ray, t);
+		return TRACK_CANDIDATE;
+	}
+	template <class W>
+	NE_D void after_candidate(W&) {}
+};
+
+template <>
+struct Tracker<true> {
+	const int2* __restrict__ cells;
+	const float* __restrict__ pool;
+	int nbx, nby, nbz;
+	V3 g0, gd;      // grid-space ray g(t) = g0 + t * gd
+	float t, tFar;
+	float tExit;    // where the ray leaves the current brick (clipped to tFar)
+	float sig;      // sigma_bar per unit density per unit t
+	float invSig;
+	float invMaj;   // 1 / majorant of the current brick, 0 = nothing to collide with
+	float sigMaj;   // sigma_bar x majorant of the current brick: optical depth per unit t (0 in an empty brick)
+	float tau;      // optical depth left before the next candidate
+	int slot;       // record of the current brick
+	BrickDDA dda;
+
+	template <class W>
+	NE_D void init(const DVolume& v, const DMaterial& m, Ray rayOCS, float tStart, float tEnd, W& wr, Stats& st) {
+		cells = v.cells;
+		pool = v.pool;
+		nbx = v.bx; nby = v.by; nbz = v.bz;
+		V3 res(float(v.W), float(v.H), float(v.D));
+		g0 = (rayOCS.o + V3(0.5f)) * res;
+		gd = rayOCS.d * res;
+		t = tStart;
+		tFar = tEnd;
+		V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+		sig = avg(ext * m.density_mult);
+		invSig = 1.0f / sig;
+		dda.init(nbx, nby, nbz, point(tStart), gd);
+		dda.nx += tStart; dda.ny += tStart; dda.nz += tStart;
+		enter_brick(st);
+		tau = exp_variate(wr);
+	}
+	NE_D V3 point(float tt) const { return V3(fmaf(gd.x, tt, g0.x), fmaf(gd.y, tt, g0.y), fmaf(gd.z, tt, g0.z)); }
+	NE_D void enter_brick(Stats& st) {
 		st.brick_visits++;
+		int2 c = __ldg(cells + (dda.bz * nby + dda.by) * nbx + dda.bx);
+		slot = c.x;
+		invMaj = __int_as_float(c.y);
+		sigMaj = invMaj > 0 ? sig * __fdividef(1.0f, invMaj) : 0.0f;
 		tExit = fminf(dda.exit_t(), tFar);
-		invMaj = dda.inv_majorant(v);
-		step = invMaj * invSig;
 	}
-	// One event. TRACK_CANDIDATE: look the density up at `t`; TRACK_MOVED: entered the next brick; TRACK_END: the
-	// segment is finished. One uniform per exponential sample.
-	template <class R>
-	NE_D int event(const DVolume& v, R& rng, Stats& st) {
-		if (!BRICKMAJ) {
-			t -= logf(1 - rng.next()) * invMaj / sig;  // GridMedia.cpp:56 / :82
-			return t >= tFar ? TRACK_END : TRACK_CANDIDATE;
+	template <class W>
+	NE_D int advance(const DVolume&, W&, float& dens, Stats& st) {
+		float cap = (tExit - t) * sigMaj;  // optical depth of the rest of this brick
+		if (tau < cap) {
+			t = fmaf(tau * invSig, invMaj, t);
+			dens = brick_density(pool, slot, point(t), dda.bx, dda.by, dda.bz);
+			return TRACK_CANDIDATE;
 		}
-		if (invMaj > 0) {
-			rng.begin_event();
-			t -= logf(1 - rng.next()) * step;
-			if (t < tExit) return TRACK_CANDIDATE;
-		}
+		tau -= cap;
 		t = tExit;
 		if (tExit >= tFar) return TRACK_END;
-		if (!dda.step(v)) return TRACK_END;
-		enter_brick(v, st);
+		if (!dda.step(nbx, nby, nbz, gd)) return TRACK_END;
+		enter_brick(st);
 		return TRACK_MOVED;
 	}
+	template <class W>
+	NE_D void after_candidate(W& wr) { tau = exp_variate(wr); }
 };
 
 #define NE_NO_BUDGET 0x7fffffff
 
 // One ratio-tracking event with pbrt's Russian roulette (GridMedia.cpp:58-66). Returns TRACK_END when the walk is
-// over (Tr final, possibly 0 = killed), otherwise TRACK_MOVED / TRACK_CANDIDATE (keep going).
-template <class R, bool BRICKMAJ>
-NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, R& rng, Stats& st) {
-	int e = trk.event(v, rng, st);
+// over (Tr final, possibly 0 = killed), otherwise TRACK_MOVED (keep going).
+template <class W, bool BRICKMAJ>
+NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr, Stats& st) {
+	float density;
+	int e = trk.advance(v, wr, density, st);
 	if (e != TRACK_CANDIDATE) return e;
 	st.ratio_steps++;
-	float density = density_at(v, trk.ray, trk.t);
 	Tr *= 1 - fmaxf(0.0f, density * trk.invMaj);
 	const float rrThreshold = .1f;
 	if (Tr < rrThreshold) {
 		float q = fmaxf(0.05f, 1.0f - Tr);
-		if (rng.next() < q) { Tr = 0.0f; return TRACK_END; }
+		if (wr.next() < q) { Tr = 0.0f; return TRACK_END; }
 		Tr /= 1 - q;
 	}
+	trk.after_candidate(wr);
 	return TRACK_MOVED;
 }
 // One delta-tracking event (GridMedia.cpp:80-95). TRACK_CANDIDATE = REAL collision at trk.t, TRACK_END = escaped,
 // TRACK_MOVED = keep going.
-template <class R, bool BRICKMAJ>
-NE_D int delta_event(const DVolume& v, Tracker<BRICKMAJ>& trk, R& rng, Stats& st) {
-	int e = trk.event(v, rng, st);
+template <class W, bool BRICKMAJ>
+NE_D int delta_event(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st) {
+	float density;
+	int e = trk.advance(v, wr, density, st);
 	if (e != TRACK_CANDIDATE) return e;
 	st.delta_steps++;
-	float density = density_at(v, trk.ray, trk.t);
-	float ra = rng.next();
-	return density * trk.invMaj > ra ? TRACK_CANDIDATE : TRACK_MOVED;
+	float ra = wr.next();
+	if (density * trk.invMaj > ra) return TRACK_CANDIDATE;
+	trk.after_candidate(wr);
+	return TRACK_MOVED;
 }
 
-template <class R, bool BRICKMAJ>
-NE_D int ratio_walk(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, R& rng, Stats& st, int budget) {
+template <class W, bool BRICKMAJ>
+NE_D int ratio_walk(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr, Stats& st, int budget) {
 	while (true) {
 		if (budget-- <= 0) return TRACK_BUDGET;
-		if (ratio_event<R, BRICKMAJ>(v, trk, Tr, rng, st) == TRACK_END) return TRACK_END;
+		if (ratio_event<W, BRICKMAJ>(v, trk, Tr, wr, st) == TRACK_END) return TRACK_END;
 	}
 }
-template <class R, bool BRICKMAJ>
-NE_D int delta_walk(const DVolume& v, Tracker<BRICKMAJ>& trk, R& rng, Stats& st, int budget) {
+template <class W, bool BRICKMAJ>
+NE_D int delta_walk(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st, int budget) {
 	while (true) {
 		if (budget-- <= 0) return TRACK_BUDGET;
-		int e = delta_event<R, BRICKMAJ>(v, trk, rng, st);
+		int e = delta_event<W, BRICKMAJ>(v, trk, wr, st);
 		if (e != TRACK_MOVED) return e;
 	}
 }
@@ -122,10 +170,12 @@ template <class R, bool BRICKMAJ>
 NE_D float grid_tr(const DInstance& in, const DMaterial& m, const DVolume& v, Ray rayW, float tNear, float tFar, R& rng, Stats& st) {
 	Ray ray = transform_ray(rayW, in.Mi);
 	ray.o = ray.at(tNear);
+	typename WalkRngOf<BRICKMAJ, R>::type wr;
+	wr.start(rng);
 	Tracker<BRICKMAJ> trk;
-	trk.init(v, m, ray, 0.0f, tFar - tNear, st);
+	trk.init(v, m, ray, 0.0f, tFar - tNear, wr, st);
 	float Tr = 1;
-	ratio_walk<R, BRICKMAJ>(v, trk, Tr, rng, st, NE_NO_BUDGET);
+	ratio_walk(v, trk, Tr, wr, st, NE_NO_BUDGET);
 	return Tr;
 }
 
@@ -147,9 +197,11 @@ NE_D V3 grid_sample(const DScene& s, const DInstance& in, const DMaterial& m, co
                     const Hit& isect, Ray& scattered, R& rng, Stats& st) {
 	scattered = incomingW;
 	Ray ray = transform_ray(incomingW, in.Mi);
+	typename WalkRngOf<BRICKMAJ, R>::type wr;
+	wr.start(rng);
 	Tracker<BRICKMAJ> trk;
-	trk.init(v, m, ray, tNear, tFar, st);  // GridMedia.cpp:79 starts at tNear; Li always passes 0
-	if (delta_walk<R, BRICKMAJ>(v, trk, rng, st, NE_NO_BUDGET) != TRACK_CANDIDATE) return V3(1.0f);
+	trk.init(v, m, ray, tNear, tFar, wr, st);  // GridMedia.cpp:79 starts at tNear; Li always passes 0
+	if (delta_walk(v, trk, wr, st, NE_NO_BUDGET) != TRACK_CANDIDATE) return V3(1.0f);
 	scattered = grid_scatter(s, in, m, ray, trk.t, isect, rng, st);
 	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
 	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;

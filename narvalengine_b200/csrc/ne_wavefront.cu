@@ -28,7 +28,7 @@ using namespace ne;
 namespace {
 
 struct WfCounts {
-	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, gen, done;
+	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, done;
 	unsigned long long workNext, workTotal;
 };
 
@@ -53,7 +53,7 @@ struct WfParams {
 	DScene s;
 	DCamera cam;
 	float* accum;
-	int W, H, sppBegin, bounces, budget;
+	int W, H, sppBegin, bounces, budget, refill;
 	uint64_t seed;
 	DCounters* counters;
 };
@@ -197,6 +197,7 @@ __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 	c.vol = c.volNext;
 	c.volNext = 0;
 	c.tr = c.trNext;
+	c.trNew0 = c.trNext;  // requests pushed from here on are new: k_wf_trfind locates their medium
 	c.trNext = 0;
 	c.scat = c.surf = c.shadow = 0;
 	c.volHead = c.trHead = 0;
@@ -284,40 +285,47 @@ __device__ __forceinline__ uint32_t warp_fetch(uint32_t* head, bool want) {
 	base = __shfl_sync(0xffffffffu, base, 0);
 	return base + __popc(need & ((1u << lane) - 1));
 }
-#define NE_REFILL_LANES 12  // refill a warp once this many lanes are idle (amortises the set-up code)
+#define NE_TRACK_THREADS 256
+#define NE_TRACK_BLOCKS 4  // resident blocks per SM the tracking kernels are compiled for (64 registers per thread)
 
 // Delta tracking (GridMedia::sample's loop) for every path of the volume queue. PERSISTENT warps: a lane whose walk
-// ends (collision, escape, or P.budget events) writes its result and takes the next queued walk, so a warp is never
-// left with one lane grinding through a long walk while 31 idle.
+// ends (collision, escape, or P.budget events) writes its result and takes the next queued walk once P.refill lanes
+// of the warp are idle, so a warp is never left with one lane grinding through a long walk while 31 idle. Only the
+// fields a walk changes are written back (origin, dimension, collision parameter, segment length).
 template <bool BRICKMAJ>
-__global__ void __launch_bounds__(256) k_wf_track(WfBuf b, WfParams P) {
+__global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(WfBuf b, WfParams P) {
+	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->vol;
 	Stats st;
 	st.clear();
 	bool active = false, exhausted = false;
 	uint32_t slot = 0;
-	PathRec r;
-	Hit h;
+	Ray ray;       // WCS, origin at the start of the segment
+	float tFar = 0;
 	PhiloxRng rng;
+	WalkRng wr;
 	Tracker<BRICKMAJ> trk;
 	const DVolume* vol = nullptr;
 	int budget = 0;
 	while (true) {
 		unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if (!exhausted && (__popc(idle) >= NE_REFILL_LANES)) {
+		if (!exhausted && (__popc(idle) >= P.refill)) {
 			uint32_t i = warp_fetch(&b.c->volHead, !active);
 			if (!active && i < n) {
 				slot = b.qVol[i];
-				r = load_path(b, slot);
-				h.tNear = b.hA[slot].w;
-				h.tFar = b.hB[slot].w;
-				h.inst = __float_as_int(b.hC[slot].z);
-				volume_enter(r.ps, h);
-				const DInstance& in = P.s.inst[h.inst];
+				float4 A = b.pA[slot], B = b.pB[slot], C = b.pC[slot];
+				float tNear = b.hA[slot].w;
+				tFar = b.hB[slot].w - tNear;  // volume_enter, Li :198-201
+				int inst = __float_as_int(b.hC[slot].z);
+				ray.o = V3(A.x, A.y, A.z);
+				ray.d = V3(A.w, B.x, B.y);
+				ray.o = ray.at(tNear);
+				const DInstance& in = P.s.inst[inst];
 				const DMaterial& m = P.s.mat[in.material];
 				vol = &P.s.vol[m.volume];
-				rng.init(P.seed, r.pixel, r.sample, r.dim);
-				trk.init(*vol, m, transform_ray(r.ps.ray, in.Mi), 0.0f, h.tFar, st);
+				rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(C.w));
+				wr.start(rng);
+				trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tFar, wr, st);
 				budget = P.budget;
 				active = true;
 			}
@@ -330,27 +338,32 @@ __global__ void __launch_bounds__(256) k_wf_track(WfBuf b, WfParams P) {
 #pragma unroll 1
 		for (int k = 0; k < 8; k++) {
 			if (active) {
-				int e = budget-- > 0 ? delta_event<PhiloxRng, BRICKMAJ>(*vol, trk, rng, st) : TRACK_BUDGET;
+				int e = budget-- > 0 ? delta_event<WalkRng, BRICKMAJ>(*vol, trk, wr, st) : TRACK_BUDGET;
 				if (e != TRACK_MOVED) {
 					active = false;
-					r.dim = rng.dim;
+					b.pC[slot].w = __uint_as_float(rng.dim);
+					b.hA[slot].w = 0.0f;
 					if (e == TRACK_CANDIDATE) {
-						r.tHit = trk.t;
-						store_path(b, slot, r);
-						b.hA[slot].w = 0.0f;
-						b.hB[slot].w = h.tFar;
+						b.pA[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+						b.pD[slot].z = __float_as_uint(trk.t);
+						b.hB[slot].w = tFar;
 						b.qScat[warp_push(&b.c->scat)] = slot;
 					} else if (e == TRACK_BUDGET) {
-						r.ps.ray.o = r.ps.ray.at(trk.t);
-						store_path(b, slot, r);
-						b.hA[slot].w = 0.0f;
-						b.hB[slot].w = h.tFar - trk.t;
+						V3 o = ray.at(trk.t);
+						b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
+						b.hB[slot].w = tFar - trk.t;
 						b.qVolNext[warp_push(&b.c->volNext)] = slot;
-					} else if (volume_escape(r.ps, h) == PATH_DONE) {
-						b.qFree[warp_push(&b.c->freeN)] = slot;
 					} else {
-						store_path(b, slot, r);
-						b.qNext[warp_push(&b.c->next)] = slot;
+						// volume_escape (Li :209-213, Q1): step past the far side, same bounce
+						V3 o = ray.at(tFar + 0.01f);
+						uint32_t bg = b.pD[slot].x + 256u;  // guard lives in bits 8..31
+						if ((bg >> 8) > NE_MAX_NULL_SEGMENTS) {
+							b.qFree[warp_push(&b.c->freeN)] = slot;
+						} else {
+							b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
+							b.pD[slot].x = bg;
+							b.qNext[warp_push(&b.c->next)] = slot;
+						}
 					}
 				}
 			}
@@ -433,60 +446,76 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 	flush_stats_wf(st, P.counters);
 }
 
-// intersectTr requests: walk through surfaces to the first medium (first pass), ratio-track through it (at most
-// P.budget events per pass), splat weight * Tr. Persistent warps like k_wf_track.
+// intersectTr :13-31 for the requests pushed in this iteration: march THROUGH non-medium surfaces until a medium
+// (the request gets its instance, entry point and segment length) or nothing (the request is dropped: Li = 0).
+__global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
+	const uint32_t first = b.c->trNew0, n = b.c->tr;
+	Stats st;
+	st.clear();
+	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		float4 A = b.tA[i], B = b.tB[i];
+		Ray ray;
+		ray.o = V3(A.x, A.y, A.z);
+		ray.d = V3(A.w, B.x, B.y);
+		int inst = -2;
+		float tRemain = 0;
+		for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
+			Hit hh;
+			st.shadow_rays++;
+			if (!intersect_scene(P.s, ray, hh, float(NE_EPSILON3), INFINITY, st)) break;
+			int mi = P.s.inst[hh.inst].material;
+			if (mi >= 0 && P.s.mat[mi].has_medium && P.s.mat[mi].volume >= 0) {
+				inst = hh.inst;
+				ray.o = ray.at(hh.tNear);
+				tRemain = hh.tFar - hh.tNear;
+				break;
+			}
+			ray.o = hh.p;
+		}
+		b.tA[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+		b.tD[i] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
+	}
+	flush_stats_wf(st, P.counters);
+}
+
+// Transmittance requests whose medium is known: ratio tracking through it (at most P.budget events per pass), splat
+// weight * Tr. Persistent warps like k_wf_track; the weight and pixel are re-read from the request when the walk ends.
 template <bool BRICKMAJ>
-__global__ void __launch_bounds__(256) k_wf_tr(WfBuf b, WfParams P) {
+__global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfBuf b, WfParams P) {
+	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->tr;
 	Stats st;
 	st.clear();
 	bool active = false, exhausted = false;
-	float4 B, C;
-	Ray ray;
-	float Tr = 1, tRemain = 0, tStart = 0;
+	uint32_t req = 0;
+	Ray ray;  // WCS, origin at the start of the remaining segment
+	float Tr = 1, tRemain = 0;
 	int inst = -1;
 	PhiloxRng rng;
+	WalkRng wr;
 	Tracker<BRICKMAJ> trk;
 	const DVolume* vol = nullptr;
 	int budget = 0;
 	while (true) {
 		unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if (!exhausted && (__popc(idle) >= NE_REFILL_LANES)) {
+		if (!exhausted && (__popc(idle) >= P.refill)) {
 			uint32_t i = warp_fetch(&b.c->trHead, !active);
 			if (!active && i < n) {
-				float4 A = b.tA[i], D = b.tD[i];
-				B = b.tB[i];
-				C = b.tC[i];
-				ray.o = V3(A.x, A.y, A.z);
-				ray.d = V3(A.w, B.x, B.y);
-				Tr = D.x;
-				tRemain = D.y;
+				float4 D = b.tD[i];
 				inst = __float_as_int(D.z);
-				rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
-				tStart = 0;
-				if (inst < 0) {
-					// intersectTr :13-31: through non-medium surfaces until a medium or nothing
-					for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
-						Hit hh;
-						st.shadow_rays++;
-						if (!intersect_scene(P.s, ray, hh, float(NE_EPSILON3), INFINITY, st)) break;
-						int mi = P.s.inst[hh.inst].material;
-						if (mi >= 0 && P.s.mat[mi].has_medium && P.s.mat[mi].volume >= 0) {
-							inst = hh.inst;
-							tStart = hh.tNear;
-							tRemain = hh.tFar - hh.tNear;
-							break;
-						}
-						ray.o = hh.p;
-					}
-				}
-				if (inst >= 0) {  // else nothing found: Li = 0, the request is dropped
+				if (inst >= 0) {  // else no medium along the ray: the request is dropped
+					float4 A = b.tA[i], B = b.tB[i], C = b.tC[i];
+					req = i;
+					ray.o = V3(A.x, A.y, A.z);
+					ray.d = V3(A.w, B.x, B.y);
+					Tr = D.x;
+					tRemain = D.y;
+					rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
 					const DInstance& in = P.s.inst[inst];
 					const DMaterial& m = P.s.mat[in.material];
 					vol = &P.s.vol[m.volume];
-					Ray rayO = transform_ray(ray, in.Mi);
-					rayO.o = rayO.at(tStart);  // GridMedia::Tr :49
-					trk.init(*vol, m, rayO, 0.0f, tRemain, st);
+					wr.start(rng);
+					trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tRemain, wr, st);  // GridMedia::Tr :49
 					budget = P.budget;
 					active = true;
 				}
@@ -500,18 +529,21 @@ __global__ void __launch_bounds__(256) k_wf_tr(WfBuf b, WfParams P) {
 #pragma unroll 1
 		for (int k = 0; k < 8; k++) {
 			if (active) {
-				int e = budget-- > 0 ? ratio_event<PhiloxRng, BRICKMAJ>(*vol, trk, Tr, rng, st) : TRACK_BUDGET;
+				int e = budget-- > 0 ? ratio_event<WalkRng, BRICKMAJ>(*vol, trk, Tr, wr, st) : TRACK_BUDGET;
 				if (e == TRACK_BUDGET) {
 					active = false;
 					uint32_t j = warp_push(&b.c->trNext);
-					V3 o = ray.at(tStart + trk.t);
+					V3 o = ray.at(trk.t);
 					b.uA[j] = make_float4(o.x, o.y, o.z, ray.d.x);
-					b.uB[j] = B;
-					b.uC[j] = C;
+					b.uB[j] = b.tB[req];
+					b.uC[j] = b.tC[req];
 					b.uD[j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
 				} else if (e == TRACK_END) {
 					active = false;
-					if (Tr != 0) splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+					if (Tr != 0) {
+						float4 B = b.tB[req], C = b.tC[req];
+						splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+					}
 				}
 			}
 		}
@@ -527,7 +559,7 @@ struct ne_wavefront_state {
 	std::vector<void*> allocs;
 	uint32_t* hostDone = nullptr;  // pinned, mapped
 	uint32_t* devDone = nullptr;
-	int gridBlocks = 0;
+	int gridBlocks = 0, smCount = 0;
 	std::vector<cudaEvent_t> events;
 };
 
@@ -567,6 +599,7 @@ static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
 	NE_CUDA_OK(cudaHostGetDevicePointer(&w->devDone, w->hostDone, 0));
 	cudaDeviceProp prop;
 	NE_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+	w->smCount = prop.multiProcessorCount;
 	w->gridBlocks = prop.multiProcessorCount * 8;  // 148 SMs x 8 resident 256-thread blocks
 	return NE_B200_OK;
 }
@@ -594,11 +627,13 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	P.sppBegin = sppBegin;
 	P.bounces = bounces;
 	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
+	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 12))));  // refill a warp once this many lanes are idle
 	P.seed = seed;
 	P.counters = ctx->dCounters;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
 	cudaStream_t st = ctx->stream;
 	const int G = w->gridBlocks, B = 256;
+	const int GT = w->smCount * NE_TRACK_BLOCKS;  // persistent tracking kernels: exactly the resident blocks
 
 	// event pool for per-stage device times, resolved after every host poll
 	size_t evUsed = 0;
@@ -639,16 +674,17 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 			cudaEvent_t e0 = timeStages ? ev() : nullptr;
 			k_wf_extend<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e1 = timeStages ? ev() : nullptr;
-			if (brick) k_wf_track<true><<<G, B, 0, st>>>(b, P);
-			else k_wf_track<false><<<G, B, 0, st>>>(b, P);
+			if (brick) k_wf_track<true><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			else k_wf_track<false><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 			cudaEvent_t e2 = timeStages ? ev() : nullptr;
 			k_wf_scatter<<<G, B, 0, st>>>(b, P);
 			k_wf_surface<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e3 = timeStages ? ev() : nullptr;
 			k_wf_shadow<<<G, B, 0, st>>>(b, P);
+			k_wf_trfind<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e4 = timeStages ? ev() : nullptr;
-			if (brick) k_wf_tr<true><<<G, B, 0, st>>>(b, P);
-			else k_wf_tr<false><<<G, B, 0, st>>>(b, P);
+			if (brick) k_wf_tr<true><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			else k_wf_tr<false><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 			cudaEvent_t e5 = timeStages ? ev() : nullptr;
 			if (timeStages) {
 				spans.push_back({e0, e1, 0});  // extend
@@ -657,7 +693,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 				spans.push_back({e3, e4, 0});  // shadow rays
 				spans.push_back({e4, e5, 1});  // ratio tracking
 			}
-			ctx->kernelLaunches += 9;
+			ctx->kernelLaunches += 10;
 			iter++;
 		}
 		NE_CUDA_OK(cudaStreamSynchronize(st));
