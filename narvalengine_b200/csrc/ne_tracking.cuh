@@ -41,14 +41,17 @@ struct Tracker<false> {
 		sig = avg(ext * m.density_mult);
 		invMaj = v.inv_max_density;
 	}
-	// TRACK_CANDIDATE: `dens` is the density at the proposed collision point t; TRACK_END: the segment is finished.
+	// The three phases of one event (the wavefront kernels run them as separate warp-wide steps):
+	//   wants_candidate  does the walk propose a collision point next (true) or does it have to move on (false)?
+	//   move             cross into the next brick; TRACK_END when the segment is finished
+	//   candidate_density  density at the proposed point (trk.t)
 	template <class W>
-	NE_D int advance(const DVolume& v, W& wr, float& dens, Stats&) {
+	NE_D bool wants_candidate(W& wr) {
 		t -= logf(1 - wr.next()) * invMaj / sig;  // GridMedia.cpp:56 / :82
-		if (t >= tFar) return TRACK_END;
-		dens = density_at(v, ray, t);
-		return TRACK_CANDIDATE;
+		return t < tFar;
 	}
+	NE_D int move(Stats&) { return TRACK_END; }
+	NE_D float candidate_density(const DVolume& v) { return density_at(v, ray, t); }
 	template <class W>
 	NE_D void after_candidate(W&) {}
 };
@@ -66,6 +69,7 @@ struct Tracker<true> {
 	float invMaj;   // 1 / majorant of the current brick, 0 = nothing to collide with
 	float sigMaj;   // sigma_bar x majorant of the current brick: optical depth per unit t (0 in an empty brick)
 	float tau;      // optical depth left before the next candidate
+	float cap;      // scratch of wants_candidate(): optical depth of the rest of the current brick
 	int slot;       // record of the current brick
 	BrickDDA dda;
 
@@ -97,13 +101,11 @@ struct Tracker<true> {
 		tExit = fminf(dda.exit_t(), tFar);
 	}
 	template <class W>
-	NE_D int advance(const DVolume&, W&, float& dens, Stats& st) {
-		float cap = (tExit - t) * sigMaj;  // optical depth of the rest of this brick
-		if (tau < cap) {
-			t = fmaf(tau * invSig, invMaj, t);
-			dens = brick_density(pool, slot, point(t), dda.bx, dda.by, dda.bz);
-			return TRACK_CANDIDATE;
-		}
+	NE_D bool wants_candidate(W&) {
+		cap = (tExit - t) * sigMaj;  // optical depth of the rest of this brick
+		return tau < cap;
+	}
+	NE_D int move(Stats& st) {
 		tau -= cap;
 		t = tExit;
 		if (tExit >= tFar) return TRACK_END;
@@ -111,19 +113,30 @@ struct Tracker<true> {
 		enter_brick(st);
 		return TRACK_MOVED;
 	}
+	NE_D float candidate_density(const DVolume&) {
+		t = fmaf(tau * invSig, invMaj, t);
+		return brick_density(pool, slot, point(t), dda.bx, dda.by, dda.bz);
+	}
 	template <class W>
 	NE_D void after_candidate(W& wr) { tau = exp_variate(wr); }
 };
 
+// One event: TRACK_CANDIDATE (`dens` = density at the proposed collision point trk.t), TRACK_MOVED, or TRACK_END.
+template <class W, bool BRICKMAJ>
+NE_D int track_advance(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, float& dens, Stats& st) {
+	if (trk.wants_candidate(wr)) {
+		dens = trk.candidate_density(v);
+		return TRACK_CANDIDATE;
+	}
+	return trk.move(st);
+}
+
 #define NE_NO_BUDGET 0x7fffffff
 
-// One ratio-tracking event with pbrt's Russian roulette (GridMedia.cpp:58-66). Returns TRACK_END when the walk is
-// over (Tr final, possibly 0 = killed), otherwise TRACK_MOVED (keep going).
+// What a candidate does to a ratio-tracking walk, with pbrt's Russian roulette (GridMedia.cpp:58-66). TRACK_END =
+// killed (Tr = 0), TRACK_MOVED = keep going.
 template <class W, bool BRICKMAJ>
-NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr, Stats& st) {
-	float density;
-	int e = trk.advance(v, wr, density, st);
-	if (e != TRACK_CANDIDATE) return e;
+NE_D int ratio_candidate(Tracker<BRICKMAJ>& trk, float density, float& Tr, W& wr, Stats& st) {
 	st.ratio_steps++;
 	Tr *= 1 - fmaxf(0.0f, density * trk.invMaj);
 	const float rrThreshold = .1f;
@@ -135,18 +148,30 @@ NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr,
 	trk.after_candidate(wr);
 	return TRACK_MOVED;
 }
-// One delta-tracking event (GridMedia.cpp:80-95). TRACK_CANDIDATE = REAL collision at trk.t, TRACK_END = escaped,
-// TRACK_MOVED = keep going.
+// What a candidate does to a delta-tracking walk (GridMedia.cpp:84-95). TRACK_CANDIDATE = REAL collision at trk.t.
 template <class W, bool BRICKMAJ>
-NE_D int delta_event(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st) {
-	float density;
-	int e = trk.advance(v, wr, density, st);
-	if (e != TRACK_CANDIDATE) return e;
+NE_D int delta_candidate(Tracker<BRICKMAJ>& trk, float density, W& wr, Stats& st) {
 	st.delta_steps++;
 	float ra = wr.next();
 	if (density * trk.invMaj > ra) return TRACK_CANDIDATE;
 	trk.after_candidate(wr);
 	return TRACK_MOVED;
+}
+// One ratio-tracking event. Returns TRACK_END when the walk is over (Tr final, possibly 0 = killed), else TRACK_MOVED.
+template <class W, bool BRICKMAJ>
+NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr, Stats& st) {
+	float density;
+	int e = track_advance(v, trk, wr, density, st);
+	if (e != TRACK_CANDIDATE) return e;
+	return ratio_candidate(trk, density, Tr, wr, st);
+}
+// One delta-tracking event. TRACK_CANDIDATE = REAL collision at trk.t, TRACK_END = escaped, TRACK_MOVED = keep going.
+template <class W, bool BRICKMAJ>
+NE_D int delta_event(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st) {
+	float density;
+	int e = track_advance(v, trk, wr, density, st);
+	if (e != TRACK_CANDIDATE) return e;
+	return delta_candidate(trk, density, wr, st);
 }
 
 template <class W, bool BRICKMAJ>

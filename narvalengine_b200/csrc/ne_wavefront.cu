@@ -275,31 +275,49 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 	flush_stats_wf(st, P.counters);
 }
 
-// Warp-level work fetch for the persistent tracking kernels: every idle lane takes the next index of the queue.
-// Returns the index (>= n when the queue is exhausted).
-__device__ __forceinline__ uint32_t warp_fetch(uint32_t* head, bool want) {
-	unsigned need = __ballot_sync(0xffffffffu, want);
-	unsigned lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == 0 && need) base = atomicAdd(head, (uint32_t)__popc(need));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	return base + __popc(need & ((1u << lane) - 1));
-}
 #define NE_TRACK_THREADS 256
 #define NE_TRACK_BLOCKS 4  // resident blocks per SM the tracking kernels are compiled for (64 registers per thread)
+#define NE_TRACK_MOVES 4   // brick crossings per lane between two candidate phases
 
-// Delta tracking (GridMedia::sample's loop) for every path of the volume queue. PERSISTENT warps: a lane whose walk
-// ends (collision, escape, or P.budget events) writes its result and takes the next queued walk once P.refill lanes
-// of the warp are idle, so a warp is never left with one lane grinding through a long walk while 31 idle. Only the
-// fields a walk changes are written back (origin, dimension, collision parameter, segment length).
+// Lane states of the persistent tracking kernels.
+enum { L_IDLE = 0, L_MOVING = 1, L_CAND = 2, L_FIN_HIT = 3, L_FIN_BUDGET = 4, L_FIN_END = 5 };
+
+// Reserve `popc(mask)` entries of a queue for the lanes in `mask`: one atomicAdd per warp. All 32 lanes call it.
+// Returns this lane's entry (meaningful for lanes in the mask). The atomics of consecutive calls are independent,
+// so their round trips to L2 overlap; the shuffle that needs the result comes after all of them have been issued.
+struct WarpReserve {
+	uint32_t base;
+	unsigned mask;
+	__device__ __forceinline__ void issue(uint32_t* counter, bool mine) {
+		mask = __ballot_sync(0xffffffffu, mine);
+		base = 0;
+		if ((threadIdx.x & 31) == 0 && mask) base = atomicAdd(counter, (uint32_t)__popc(mask));
+	}
+	__device__ __forceinline__ uint32_t get() const {
+		uint32_t b0 = __shfl_sync(0xffffffffu, base, 0);
+		return b0 + __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
+	}
+};
+
+// Delta tracking (GridMedia::sample's loop) for every path of the volume queue, by PERSISTENT warps that run three
+// warp-wide phases in turn so that lanes doing the same kind of work run together:
+//   finish + refill  (when P.refill lanes are not walking) finished walks write back the fields they changed and are
+//                    queued for the next stage; idle lanes take the next queued walks. All queue atomics of the phase
+//                    (three pushes and the fetch) are issued back to back, one L2 round trip for the lot.
+//   move             up to NE_TRACK_MOVES brick crossings per walking lane (one 8-byte cell load each, no density)
+//   candidate        every lane that proposed a collision point looks the density up (eight loads from one brick
+//                    record) and accepts or rejects it
+// A walk ends on a real collision, on leaving the medium, or after P.budget events (it then continues from the point
+// reached in the next pass), so a warp is never left with one lane grinding through a long walk while 31 idle.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(WfBuf b, WfParams P) {
 	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->vol;
 	Stats st;
 	st.clear();
-	bool active = false, exhausted = false;
-	uint32_t slot = 0;
+	int state = L_IDLE;
+	bool exhausted = false;
+	uint32_t slot = 0, bg = 0;
 	Ray ray;       // WCS, origin at the start of the segment
 	float tFar = 0;
 	PhiloxRng rng;
@@ -308,65 +326,83 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 	const DVolume* vol = nullptr;
 	int budget = 0;
 	while (true) {
-		unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if (!exhausted && (__popc(idle) >= P.refill)) {
-			uint32_t i = warp_fetch(&b.c->volHead, !active);
-			if (!active && i < n) {
-				slot = b.qVol[i];
-				float4 A = b.pA[slot], B = b.pB[slot], C = b.pC[slot];
-				float tNear = b.hA[slot].w;
-				tFar = b.hB[slot].w - tNear;  // volume_enter, Li :198-201
-				int inst = __float_as_int(b.hC[slot].z);
-				ray.o = V3(A.x, A.y, A.z);
-				ray.d = V3(A.w, B.x, B.y);
-				ray.o = ray.at(tNear);
-				const DInstance& in = P.s.inst[inst];
-				const DMaterial& m = P.s.mat[in.material];
-				vol = &P.s.vol[m.volume];
-				rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(C.w));
-				wr.start(rng);
-				trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tFar, wr, st);
-				budget = P.budget;
-				active = true;
-			}
-			if (__ballot_sync(0xffffffffu, !active && i >= n)) exhausted = true;
-		}
-		if (__ballot_sync(0xffffffffu, active) == 0) {
-			if (exhausted) break;
-			continue;
-		}
-#pragma unroll 1
-		for (int k = 0; k < 8; k++) {
-			if (active) {
-				int e = budget-- > 0 ? delta_event<WalkRng, BRICKMAJ>(*vol, trk, wr, st) : TRACK_BUDGET;
-				if (e != TRACK_MOVED) {
-					active = false;
-					b.pC[slot].w = __uint_as_float(rng.dim);
-					b.hA[slot].w = 0.0f;
-					if (e == TRACK_CANDIDATE) {
-						b.pA[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-						b.pD[slot].z = __float_as_uint(trk.t);
-						b.hB[slot].w = tFar;
-						b.qScat[warp_push(&b.c->scat)] = slot;
-					} else if (e == TRACK_BUDGET) {
-						V3 o = ray.at(trk.t);
-						b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
-						b.hB[slot].w = tFar - trk.t;
-						b.qVolNext[warp_push(&b.c->volNext)] = slot;
-					} else {
-						// volume_escape (Li :209-213, Q1): step past the far side, same bounce
-						V3 o = ray.at(tFar + 0.01f);
-						uint32_t bg = b.pD[slot].x + 256u;  // guard lives in bits 8..31
-						if ((bg >> 8) > NE_MAX_NULL_SEGMENTS) {
-							b.qFree[warp_push(&b.c->freeN)] = slot;
-						} else {
-							b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
-							b.pD[slot].x = bg;
-							b.qNext[warp_push(&b.c->next)] = slot;
-						}
-					}
+		unsigned walking = __ballot_sync(0xffffffffu, state == L_MOVING || state == L_CAND);
+		if (walking == 0 || (!exhausted && 32 - __popc(walking) >= P.refill)) {
+			// ---- finish + refill
+			const bool fin = state >= L_FIN_HIT;
+			const bool esc = state == L_FIN_END;
+			const uint32_t bg2 = bg + 256u;  // volume_escape (Li :209-213, Q1): the guard lives in bits 8..31
+			const bool dead = esc && (bg2 >> 8) > NE_MAX_NULL_SEGMENTS;
+			WarpReserve rScat, rVolNext, rNext, rFree, rFetch;
+			rScat.issue(&b.c->scat, state == L_FIN_HIT);
+			rVolNext.issue(&b.c->volNext, state == L_FIN_BUDGET);
+			rNext.issue(&b.c->next, esc && !dead);
+			rFree.issue(&b.c->freeN, dead);
+			rFetch.issue(&b.c->volHead, !exhausted && (state == L_IDLE || fin));
+			// the shuffles are warp-wide: resolve every reservation before the lanes part ways
+			const uint32_t iScat = rScat.get(), iVolNext = rVolNext.get(), iNext = rNext.get(), iFree = rFree.get(), iFetch = rFetch.get();
+			if (fin) {
+				if (state == L_FIN_HIT) {
+					b.pA[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+					b.pD[slot].z = __float_as_uint(trk.t);
+					b.hB[slot].w = tFar;
+					b.qScat[iScat] = slot;
+				} else if (state == L_FIN_BUDGET) {
+					V3 o = ray.at(trk.t);
+					b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
+					b.hB[slot].w = tFar - trk.t;
+					b.qVolNext[iVolNext] = slot;
+				} else if (dead) {
+					b.qFree[iFree] = slot;
+				} else {
+					V3 o = ray.at(tFar + 0.01f);  // step past the far side, same bounce
+					b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
+					b.pD[slot].x = bg2;
+					b.qNext[iNext] = slot;
 				}
+				b.pC[slot].w = __uint_as_float(rng.dim);
+				b.hA[slot].w = 0.0f;
+				state = L_IDLE;
 			}
+			if (!exhausted) {
+				const uint32_t i = iFetch;
+				if (state == L_IDLE && i < n) {
+					slot = b.qVol[i];
+					float4 A = b.pA[slot], B = b.pB[slot], C = b.pC[slot];
+					bg = b.pD[slot].x;
+					float tNear = b.hA[slot].w;
+					tFar = b.hB[slot].w - tNear;  // volume_enter, Li :198-201
+					int inst = __float_as_int(b.hC[slot].z);
+					ray.o = V3(A.x, A.y, A.z);
+					ray.d = V3(A.w, B.x, B.y);
+					ray.o = ray.at(tNear);
+					const DInstance& in = P.s.inst[inst];
+					const DMaterial& m = P.s.mat[in.material];
+					vol = &P.s.vol[m.volume];
+					rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(C.w));
+					wr.start(rng);
+					trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tFar, wr, st);
+					budget = P.budget;
+					state = L_MOVING;
+				}
+				if (__ballot_sync(0xffffffffu, state == L_IDLE && i >= n)) exhausted = true;
+			}
+			if (__ballot_sync(0xffffffffu, state != L_IDLE) == 0) break;  // nothing walking, nothing left to fetch
+		}
+		// ---- move
+#pragma unroll 1
+		for (int k = 0; k < NE_TRACK_MOVES; k++) {
+			if (state == L_MOVING) {
+				if (budget-- <= 0) state = L_FIN_BUDGET;
+				else if (trk.wants_candidate(wr)) state = L_CAND;
+				else if (trk.move(st) == TRACK_END) state = L_FIN_END;
+			}
+			if (!__any_sync(0xffffffffu, state == L_MOVING)) break;
+		}
+		// ---- candidate
+		if (state == L_CAND) {
+			float density = trk.candidate_density(*vol);
+			state = delta_candidate(trk, density, wr, st) == TRACK_CANDIDATE ? L_FIN_HIT : L_MOVING;
 		}
 	}
 	flush_stats_wf(st, P.counters);
@@ -479,14 +515,16 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 }
 
 // Transmittance requests whose medium is known: ratio tracking through it (at most P.budget events per pass), splat
-// weight * Tr. Persistent warps like k_wf_track; the weight and pixel are re-read from the request when the walk ends.
+// weight * Tr. Persistent warps and phases like k_wf_track; the weight and pixel are re-read from the request when the
+// walk ends.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfBuf b, WfParams P) {
 	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->tr;
 	Stats st;
 	st.clear();
-	bool active = false, exhausted = false;
+	int state = L_IDLE;
+	bool exhausted = false;
 	uint32_t req = 0;
 	Ray ray;  // WCS, origin at the start of the remaining segment
 	float Tr = 1, tRemain = 0;
@@ -497,55 +535,71 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 	const DVolume* vol = nullptr;
 	int budget = 0;
 	while (true) {
-		unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if (!exhausted && (__popc(idle) >= P.refill)) {
-			uint32_t i = warp_fetch(&b.c->trHead, !active);
-			if (!active && i < n) {
-				float4 D = b.tD[i];
-				inst = __float_as_int(D.z);
-				if (inst >= 0) {  // else no medium along the ray: the request is dropped
-					float4 A = b.tA[i], B = b.tB[i], C = b.tC[i];
-					req = i;
-					ray.o = V3(A.x, A.y, A.z);
-					ray.d = V3(A.w, B.x, B.y);
-					Tr = D.x;
-					tRemain = D.y;
-					rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
-					const DInstance& in = P.s.inst[inst];
-					const DMaterial& m = P.s.mat[in.material];
-					vol = &P.s.vol[m.volume];
-					wr.start(rng);
-					trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tRemain, wr, st);  // GridMedia::Tr :49
-					budget = P.budget;
-					active = true;
-				}
-			}
-			if (__ballot_sync(0xffffffffu, !active && i >= n)) exhausted = true;
-		}
-		if (__ballot_sync(0xffffffffu, active) == 0) {
-			if (exhausted) break;
-			continue;
-		}
-#pragma unroll 1
-		for (int k = 0; k < 8; k++) {
-			if (active) {
-				int e = budget-- > 0 ? ratio_event<WalkRng, BRICKMAJ>(*vol, trk, Tr, wr, st) : TRACK_BUDGET;
-				if (e == TRACK_BUDGET) {
-					active = false;
-					uint32_t j = warp_push(&b.c->trNext);
+		unsigned walking = __ballot_sync(0xffffffffu, state == L_MOVING || state == L_CAND);
+		if (walking == 0 || (!exhausted && 32 - __popc(walking) >= P.refill)) {
+			// ---- finish + refill
+			const bool fin = state >= L_FIN_HIT;
+			WarpReserve rNext, rFetch;
+			rNext.issue(&b.c->trNext, state == L_FIN_BUDGET);
+			rFetch.issue(&b.c->trHead, !exhausted && (state == L_IDLE || fin));
+			const uint32_t iNext = rNext.get(), iFetch = rFetch.get();  // warp-wide shuffles: before the lanes part ways
+			if (fin) {
+				float4 B = b.tB[req], C = b.tC[req];
+				if (state == L_FIN_BUDGET) {
+					uint32_t j = iNext;
 					V3 o = ray.at(trk.t);
 					b.uA[j] = make_float4(o.x, o.y, o.z, ray.d.x);
-					b.uB[j] = b.tB[req];
-					b.uC[j] = b.tC[req];
+					b.uB[j] = B;
+					b.uC[j] = C;
 					b.uD[j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
-				} else if (e == TRACK_END) {
-					active = false;
-					if (Tr != 0) {
-						float4 B = b.tB[req], C = b.tC[req];
-						splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+				} else if (Tr != 0) {
+					splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+				}
+				state = L_IDLE;
+			}
+			if (!exhausted) {
+				const uint32_t i = iFetch;
+				if (state == L_IDLE && i < n) {
+					float4 D = b.tD[i];
+					inst = __float_as_int(D.z);
+					if (inst >= 0) {  // else no medium along the ray: the request is dropped
+						float4 A = b.tA[i], B = b.tB[i], C = b.tC[i];
+						req = i;
+						ray.o = V3(A.x, A.y, A.z);
+						ray.d = V3(A.w, B.x, B.y);
+						Tr = D.x;
+						tRemain = D.y;
+						rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
+						const DInstance& in = P.s.inst[inst];
+						const DMaterial& m = P.s.mat[in.material];
+						vol = &P.s.vol[m.volume];
+						wr.start(rng);
+						trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tRemain, wr, st);  // GridMedia::Tr :49
+						budget = P.budget;
+						state = L_MOVING;
 					}
 				}
+				if (__ballot_sync(0xffffffffu, state == L_IDLE && i >= n)) exhausted = true;
 			}
+			if (__ballot_sync(0xffffffffu, state != L_IDLE) == 0) {
+				if (exhausted) break;
+				continue;  // every request of this batch was a dropped one: fetch again
+			}
+		}
+		// ---- move
+#pragma unroll 1
+		for (int k = 0; k < NE_TRACK_MOVES; k++) {
+			if (state == L_MOVING) {
+				if (budget-- <= 0) state = L_FIN_BUDGET;
+				else if (trk.wants_candidate(wr)) state = L_CAND;
+				else if (trk.move(st) == TRACK_END) state = L_FIN_END;
+			}
+			if (!__any_sync(0xffffffffu, state == L_MOVING)) break;
+		}
+		// ---- candidate
+		if (state == L_CAND) {
+			float density = trk.candidate_density(*vol);
+			state = ratio_candidate(trk, density, Tr, wr, st) == TRACK_END ? L_FIN_END : L_MOVING;
 		}
 	}
 	flush_stats_wf(st, P.counters);

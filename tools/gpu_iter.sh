@@ -2,10 +2,10 @@
 # Quick iteration call: GPU tests (optional) + one short bench without the CPU legs.  usage: bash tools/gpu_iter.sh [tests] [bench] [env...]
 mkdir -p gpurun_out
 if [[ " $* " == *" tests "* ]]; then
-  timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+  timeout 240 python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -15
 fi
 if [[ " $* " == *" bench "* ]]; then
-  timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/iter_bench.json 2> gpurun_out/iter_bench.err
+  timeout 180 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/iter_bench.json 2> gpurun_out/iter_bench.err
   python - <<'PY'
 import json
 d=json.load(open('gpurun_out/iter_bench.json'))
