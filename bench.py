@@ -12,7 +12,7 @@ renderer. With N GPUs every rank holds a scene replica and renders 64 samples/pi
 
 Printed JSON (rank 0, one line): see README / the driver contract. `value` = device-timed render (scene resident in
 HBM); `e2e` = the same frame through ne_b200_scene_upload + ne_b200_render_frame with HOST buffers (scene H2D, frame
-D2H inside the timed region); `roofline` = the volume-tracking kernels (delta tracking `k_wf_shade<volume>` + ratio
+D2H inside the timed region); `roofline` = the volume-tracking kernels (delta tracking `k_wf_track` + ratio
 tracking `k_wf_tr`), algorithmic bytes = 40 B per tracking step (SURVEY 8d) over their CUDA-event time;
 `cpu_baseline` = the reference's own integrator (oracle/_ref, thread-local RNG build) on this box's host cores over a
 bounded sample of the same frame.
@@ -246,7 +246,7 @@ def main():
             traffic = None
     launches_volume = max(1, int(c.wavefront_iterations) * 2)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_wf_shade<volume> (delta tracking) + k_wf_tr (ratio tracking)", "peak_source": peak_src,
+                "kernel": "k_wf_track (delta tracking) + k_wf_tr (ratio tracking)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / launches_volume, "tracking_steps_per_frame": steps_tracked / args.steps,
                 "kernel_ms_per_frame": c.ms_volume_kernel / args.steps,
                 "share_of_step": c.ms_volume_kernel / (c.ms_volume_kernel + c.ms_extend_kernel + c.ms_shade_kernel + 1e-9),
@@ -298,7 +298,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [DEBUG spp={spp}]", "resolution": [W, H], "spp_per_gpu": spp,
                            "bounces": BOUNCES, "grid": [GRID] * 3, "partition": f"sample-index x{world} + NCCL reduce" if world > 1 else "single GPU",
-                           "l2": "flushed between timed steps (256 MiB write)", "majorant": "per-brick (8^3) DDA", "pool_slots": 1 << 21},
+                           "l2": "flushed between timed steps (256 MiB write)", "majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 24))},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "counters": {k: int(getattr(c, k)) for k in ("paths", "extend_rays", "shadow_rays", "delta_steps", "ratio_steps", "brick_visits",
                                                               "scatter_events", "wavefront_iterations")},

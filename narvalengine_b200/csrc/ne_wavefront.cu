@@ -1,8 +1,9 @@
 // ne_wavefront.cu — the production renderer: OfflineEngine::renderTile's pixel x sample loops
 // (core/OfflineEngine.cpp:61-71) over the whole frame as a WAVEFRONT of SoA path records.
 //
-//   pool      N path slots (SoA float4 arrays, 64 B of state each) that are refilled with new camera samples as
-//             paths terminate, so the wavefront stays full until the work runs out
+//   pool      N path slots (one 128-byte record each: 64 B path state + 48 B hit) that are refilled with new camera
+//             samples as paths terminate, so the wavefront stays full until the work runs out. 16 Mi slots by default
+//             (5.4 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
 //   queues    arrays of slot indices: extend -> {volume, surface}; volume -> {scatter, volume (walk not finished),
 //             next extend}; free slots. All pushes are warp-aggregated (one atomicAdd per warp per queue)
 //   kernels   plan (1 thread: queue bookkeeping) · generate (camera rays) · extend (Scene::intersectScene fold, BVH)
@@ -32,12 +33,19 @@ struct WfCounts {
 	unsigned long long workNext, workTotal;
 };
 
+struct __align__(128) PathSlot {
+	float4 pA, pB, pC;
+	uint4 pD;
+	float4 hA, hB, hC;
+	float4 spare;
+};
+
 struct WfBuf {
-	// path record: A=(o.xyz,d.x) B=(d.yz,T.xy) C=(T.z,pixel,sample,dim) D=(bounce|guard<<8, nee, collision t, -)
-	float4 *pA, *pB, *pC;
-	uint4* pD;
-	// hit record: A=(p.xyz,tNear) B=(n.xyz,tFar) C=(u,v,inst,prim)
-	float4 *hA, *hB, *hC;
+	// One 128-byte record per path slot (path state + hit), so that a slot reached through a queue index - a random
+	// address - costs exactly one L2 line, every byte of it used:
+	//   path  pA=(o.xyz,d.x) pB=(d.yz,T.xy) pC=(T.z,pixel,sample,dim) pD=(bounce|guard<<8, nee, collision t, -)
+	//   hit   hA=(p.xyz,tNear) hB=(n.xyz,tFar) hC=(u,v,inst,prim)
+	PathSlot* rec;
 	// shadow request: A=(o.xyz,C.x) B=(C.yz,w.xy) C=(w.z,pixel)
 	float4 *sA, *sB;
 	float2* sC;
@@ -53,7 +61,7 @@ struct WfParams {
 	DScene s;
 	DCamera cam;
 	float* accum;
-	int W, H, sppBegin, bounces, budget, refill;
+	int W, H, sppBegin, bounces, budget, refill, moves;
 	uint64_t seed;
 	DCounters* counters;
 };
@@ -102,8 +110,8 @@ struct PathRec {
 	float tHit;  // collision parameter handed from track to scatter
 };
 __device__ __forceinline__ PathRec load_path(const WfBuf& b, uint32_t slot) {
-	float4 A = b.pA[slot], B = b.pB[slot], C = b.pC[slot];
-	uint4 D = b.pD[slot];
+	float4 A = b.rec[slot].pA, B = b.rec[slot].pB, C = b.rec[slot].pC;
+	uint4 D = b.rec[slot].pD;
 	PathRec r;
 	r.ps.ray.o = V3(A.x, A.y, A.z);
 	r.ps.ray.d = V3(A.w, B.x, B.y);
@@ -118,13 +126,13 @@ __device__ __forceinline__ PathRec load_path(const WfBuf& b, uint32_t slot) {
 	return r;
 }
 __device__ __forceinline__ void store_path(const WfBuf& b, uint32_t slot, const PathRec& r) {
-	b.pA[slot] = make_float4(r.ps.ray.o.x, r.ps.ray.o.y, r.ps.ray.o.z, r.ps.ray.d.x);
-	b.pB[slot] = make_float4(r.ps.ray.d.y, r.ps.ray.d.z, r.ps.T.x, r.ps.T.y);
-	b.pC[slot] = make_float4(r.ps.T.z, __uint_as_float(r.pixel), __uint_as_float(r.sample), __uint_as_float(r.dim));
-	b.pD[slot] = make_uint4(uint32_t(r.ps.bounce) | (uint32_t(r.ps.guard) << 8), r.ps.nee, __float_as_uint(r.tHit), 0u);
+	b.rec[slot].pA = make_float4(r.ps.ray.o.x, r.ps.ray.o.y, r.ps.ray.o.z, r.ps.ray.d.x);
+	b.rec[slot].pB = make_float4(r.ps.ray.d.y, r.ps.ray.d.z, r.ps.T.x, r.ps.T.y);
+	b.rec[slot].pC = make_float4(r.ps.T.z, __uint_as_float(r.pixel), __uint_as_float(r.sample), __uint_as_float(r.dim));
+	b.rec[slot].pD = make_uint4(uint32_t(r.ps.bounce) | (uint32_t(r.ps.guard) << 8), r.ps.nee, __float_as_uint(r.tHit), 0u);
 }
 __device__ __forceinline__ Hit load_hit(const WfBuf& b, uint32_t slot) {
-	float4 A = b.hA[slot], B = b.hB[slot], C = b.hC[slot];
+	float4 A = b.rec[slot].hA, B = b.rec[slot].hB, C = b.rec[slot].hC;
 	Hit h;
 	h.p = V3(A.x, A.y, A.z);
 	h.tNear = A.w;
@@ -137,9 +145,9 @@ __device__ __forceinline__ Hit load_hit(const WfBuf& b, uint32_t slot) {
 	return h;
 }
 __device__ __forceinline__ void store_hit(const WfBuf& b, uint32_t slot, const Hit& h) {
-	b.hA[slot] = make_float4(h.p.x, h.p.y, h.p.z, h.tNear);
-	b.hB[slot] = make_float4(h.n.x, h.n.y, h.n.z, h.tFar);
-	b.hC[slot] = make_float4(h.u, h.v, __int_as_float(h.inst), __int_as_float(h.prim));
+	b.rec[slot].hA = make_float4(h.p.x, h.p.y, h.p.z, h.tNear);
+	b.rec[slot].hB = make_float4(h.n.x, h.n.y, h.n.z, h.tFar);
+	b.rec[slot].hC = make_float4(h.u, h.v, __int_as_float(h.inst), __int_as_float(h.prim));
 }
 
 // Turns the two next-event queries of estimateDirect into requests; emission and request weights go straight to
@@ -277,7 +285,6 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 
 #define NE_TRACK_THREADS 256
 #define NE_TRACK_BLOCKS 4  // resident blocks per SM the tracking kernels are compiled for (64 registers per thread)
-#define NE_TRACK_MOVES 4   // brick crossings per lane between two candidate phases
 
 // Lane states of the persistent tracking kernels.
 enum { L_IDLE = 0, L_MOVING = 1, L_CAND = 2, L_FIN_HIT = 3, L_FIN_BUDGET = 4, L_FIN_END = 5 };
@@ -304,7 +311,7 @@ struct WarpReserve {
 //   finish + refill  (when P.refill lanes are not walking) finished walks write back the fields they changed and are
 //                    queued for the next stage; idle lanes take the next queued walks. All queue atomics of the phase
 //                    (three pushes and the fetch) are issued back to back, one L2 round trip for the lot.
-//   move             up to NE_TRACK_MOVES brick crossings per walking lane (one 8-byte cell load each, no density)
+//   move             up to P.moves brick crossings per walking lane (one 8-byte cell load each, no density)
 //   candidate        every lane that proposed a collision point looks the density up (eight loads from one brick
 //                    record) and accepts or rejects it
 // A walk ends on a real collision, on leaving the medium, or after P.budget events (it then continues from the point
@@ -343,36 +350,36 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 			const uint32_t iScat = rScat.get(), iVolNext = rVolNext.get(), iNext = rNext.get(), iFree = rFree.get(), iFetch = rFetch.get();
 			if (fin) {
 				if (state == L_FIN_HIT) {
-					b.pA[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-					b.pD[slot].z = __float_as_uint(trk.t);
-					b.hB[slot].w = tFar;
+					b.rec[slot].pA = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+					b.rec[slot].pD.z = __float_as_uint(trk.t);
+					b.rec[slot].hB.w = tFar;
 					b.qScat[iScat] = slot;
 				} else if (state == L_FIN_BUDGET) {
 					V3 o = ray.at(trk.t);
-					b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
-					b.hB[slot].w = tFar - trk.t;
+					b.rec[slot].pA = make_float4(o.x, o.y, o.z, ray.d.x);
+					b.rec[slot].hB.w = tFar - trk.t;
 					b.qVolNext[iVolNext] = slot;
 				} else if (dead) {
 					b.qFree[iFree] = slot;
 				} else {
 					V3 o = ray.at(tFar + 0.01f);  // step past the far side, same bounce
-					b.pA[slot] = make_float4(o.x, o.y, o.z, ray.d.x);
-					b.pD[slot].x = bg2;
+					b.rec[slot].pA = make_float4(o.x, o.y, o.z, ray.d.x);
+					b.rec[slot].pD.x = bg2;
 					b.qNext[iNext] = slot;
 				}
-				b.pC[slot].w = __uint_as_float(rng.dim);
-				b.hA[slot].w = 0.0f;
+				b.rec[slot].pC.w = __uint_as_float(rng.dim);
+				b.rec[slot].hA.w = 0.0f;
 				state = L_IDLE;
 			}
 			if (!exhausted) {
 				const uint32_t i = iFetch;
 				if (state == L_IDLE && i < n) {
 					slot = b.qVol[i];
-					float4 A = b.pA[slot], B = b.pB[slot], C = b.pC[slot];
-					bg = b.pD[slot].x;
-					float tNear = b.hA[slot].w;
-					tFar = b.hB[slot].w - tNear;  // volume_enter, Li :198-201
-					int inst = __float_as_int(b.hC[slot].z);
+					float4 A = b.rec[slot].pA, B = b.rec[slot].pB, C = b.rec[slot].pC;
+					bg = b.rec[slot].pD.x;
+					float tNear = b.rec[slot].hA.w;
+					tFar = b.rec[slot].hB.w - tNear;  // volume_enter, Li :198-201
+					int inst = __float_as_int(b.rec[slot].hC.z);
 					ray.o = V3(A.x, A.y, A.z);
 					ray.d = V3(A.w, B.x, B.y);
 					ray.o = ray.at(tNear);
@@ -391,7 +398,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 		}
 		// ---- move
 #pragma unroll 1
-		for (int k = 0; k < NE_TRACK_MOVES; k++) {
+		for (int k = 0; k < P.moves; k++) {
 			if (state == L_MOVING) {
 				if (budget-- <= 0) state = L_FIN_BUDGET;
 				else if (trk.wants_candidate(wr)) state = L_CAND;
@@ -588,7 +595,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 		}
 		// ---- move
 #pragma unroll 1
-		for (int k = 0; k < NE_TRACK_MOVES; k++) {
+		for (int k = 0; k < P.moves; k++) {
 			if (state == L_MOVING) {
 				if (budget-- <= 0) state = L_FIN_BUDGET;
 				else if (trk.wants_candidate(wr)) state = L_CAND;
@@ -645,7 +652,7 @@ static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
 	int rc;
 	WfBuf& b = w->b;
 #define A(field) if ((rc = wf_alloc(w, &b.field, nSlots))) return rc;
-	A(pA) A(pB) A(pC) A(pD) A(hA) A(hB) A(hC) A(sA) A(sB) A(sC) A(tA) A(tB) A(tC) A(tD) A(uA) A(uB) A(uC) A(uD)
+	A(rec) A(sA) A(sB) A(sC) A(tA) A(tB) A(tC) A(tD) A(uA) A(uB) A(uC) A(uD)
 	A(qExtend) A(qNext) A(qVol) A(qVolNext) A(qScat) A(qSurf) A(qFree)
 #undef A
 	if ((rc = wf_alloc(w, &b.c, 1))) return rc;
@@ -666,7 +673,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
 	const unsigned long long work = (unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin);
 	if (work == 0 || bounces == 0) return NE_B200_OK;
-	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 21));
+	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 24));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
 	int rc = wavefront_ensure(ctx, nSlots);
 	if (rc) return rc;
@@ -681,6 +688,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	P.sppBegin = sppBegin;
 	P.bounces = bounces;
 	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
+	P.moves = int(std::max(1u, env_u32("NE_B200_TRACK_MOVES", 4)));  // brick crossings per lane between two candidate phases
 	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 12))));  // refill a warp once this many lanes are idle
 	P.seed = seed;
 	P.counters = ctx->dCounters;
