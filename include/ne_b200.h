@@ -323,6 +323,12 @@ int ne_b200_test_sample_one_light(ne_b200_ctx* ctx, int n, const float* incoming
  * grid's invMaxDensity (GridMedia.cpp:12). */
 int ne_b200_test_density(ne_b200_ctx* ctx, int n, int instance, const float* ocs_points, float* density, float* inv_max_density);
 
+/* The brick-sparse grid of scene volume `volume` as it lives in HBM, in the format of ne_b200_host_build_bricks (two-call
+ * pattern: NULL arrays to get dims = {bx, by, bz, n_slots}). Dense grids are bricked by GPU kernels during
+ * ne_b200_scene_upload; this hook lets a test check them against the host builder bit for bit. */
+int ne_b200_test_read_bricks(ne_b200_ctx* ctx, int volume, int32_t dims[4], int32_t* table, float* inv_majorant, float* pool,
+                             float* max_density);
+
 /* Philox4x32-10 uniforms: out[i] = u(seed, pixel, sample, dimension i), for KATs of the generator. */
 int ne_b200_test_philox(ne_b200_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out);
 

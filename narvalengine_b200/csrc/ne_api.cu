@@ -368,6 +368,7 @@ void ne_b200_destroy(ne_b200_ctx* ctx) {
 	wavefront_free(ctx);
 	free_scene(ctx);
 	if (ctx->accum) cudaFree(ctx->accum);
+	if (ctx->scratch) cudaFree(ctx->scratch);
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->evA) cudaEventDestroy(ctx->evA);
 	if (ctx->evB) cudaEventDestroy(ctx->evB);
@@ -469,9 +470,13 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 			set_error("bad volume");
 			return NE_B200_ERR_INVALID;
 		}
-		HostBricks hb;
-		host_build_bricks(v, hb);
 		DVolume& o = vols[i];
+		if (v.dense) {  // dense grid: copied once, bricked by three kernels (ne_bricks.cu)
+			if ((rc = device_build_bricks(ctx, v, o))) return rc;
+			continue;
+		}
+		HostBricks hb;
+		host_build_bricks(v, hb);  // OpenVDB leaves: scattered input, bricked on the host
 		o.W = hb.W; o.H = hb.H; o.D = hb.D; o.bx = hb.bx; o.by = hb.by; o.bz = hb.bz;
 		o.max_density = hb.maxDensity;
 		o.inv_max_density = 1.0f / hb.maxDensity;
@@ -482,6 +487,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 			cells[b].x = hb.table[b];
 			memcpy(&cells[b].y, &inv, 4);
 		}
+		o.n_slots = int(hb.pool.size() / BRICK_VOX);
 		if ((rc = push_alloc(ctx, cells.data(), cells.size(), &o.cells))) return rc;
 		if ((rc = push_alloc(ctx, hb.pool.data(), hb.pool.size(), &o.pool))) return rc;
 	}
@@ -547,6 +553,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	if ((rc = push_alloc(ctx, vols.data(), vols.size(), &s.vol))) return rc;
 	if ((rc = push_alloc(ctx, meshes.data(), meshes.size(), &s.mesh))) return rc;
 	ctx->scene = s;
+	ctx->nVolumes = d->n_volumes;
 	ctx->haveScene = true;
 	ctx->msUpload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	return NE_B200_OK;
@@ -645,14 +652,14 @@ static int read_resolved(ne_b200_ctx* ctx, float* linear, float* tonemapped) {
 	if (rc) return rc;
 	if (!ctx->accum || ctx->samples <= 0) { set_error("nothing rendered yet"); return NE_B200_ERR_STATE; }
 	size_t n = size_t(ctx->W) * ctx->H * 3;
-	DevBuf<float> lin, tm;
-	if (linear) NE_CUDA_OK(lin.alloc(n));
-	if (tonemapped) NE_CUDA_OK(tm.alloc(n));
-	k_resolve<<<blocks(n, 256), 256, 0, ctx->stream>>>(ctx->accum, 1.0f / float(ctx->samples), n, linear ? lin.p : nullptr, tonemapped ? tm.p : nullptr);
+	if ((rc = scratch_reserve(ctx, 2 * n * sizeof(float)))) return rc;  // resolved frames live in the context's scratch
+	float* lin = static_cast<float*>(ctx->scratch);
+	float* tm = lin + n;
+	k_resolve<<<blocks(n, 256), 256, 0, ctx->stream>>>(ctx->accum, 1.0f / float(ctx->samples), n, linear ? lin : nullptr, tonemapped ? tm : nullptr);
 	ctx->kernelLaunches++;
 	NE_CUDA_OK(cudaGetLastError());
-	if (linear) NE_CUDA_OK(cudaMemcpyAsync(linear, lin.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-	if (tonemapped) NE_CUDA_OK(cudaMemcpyAsync(tonemapped, tm.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	if (linear) NE_CUDA_OK(cudaMemcpyAsync(linear, lin, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	if (tonemapped) NE_CUDA_OK(cudaMemcpyAsync(tonemapped, tm, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NE_B200_OK;
 }
@@ -898,6 +905,30 @@ int ne_b200_test_density(ne_b200_ctx* ctx, int n, int instance, const float* ocs
 	k_test_density<<<blocks(n, 128), 128, 0, ctx->stream>>>(ctx->scene, n, instance, p.p, o.p);
 	NE_FINISH();
 	NE_CUDA_OK(o.download(density));
+	return NE_B200_OK;
+}
+
+int ne_b200_test_read_bricks(ne_b200_ctx* ctx, int volume, int32_t dims[4], int32_t* table, float* inv_majorant, float* pool, float* max_density) {
+	int rc = check_ctx(ctx, true);
+	if (rc) return rc;
+	if (!dims) { set_error("null dims"); return NE_B200_ERR_INVALID; }
+	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	std::vector<DVolume> vols(std::max(1, ctx->nVolumes));
+	if (volume < 0 || volume >= ctx->nVolumes) { set_error("volume index out of range"); return NE_B200_ERR_INVALID; }
+	NE_CUDA_OK(cudaMemcpy(vols.data(), ctx->scene.vol, sizeof(DVolume) * ctx->nVolumes, cudaMemcpyDeviceToHost));
+	const DVolume& v = vols[volume];
+	dims[0] = v.bx; dims[1] = v.by; dims[2] = v.bz; dims[3] = v.n_slots;
+	if (max_density) *max_density = v.max_density;
+	size_t nb = size_t(v.bx) * v.by * v.bz;
+	if (table || inv_majorant) {
+		std::vector<int2> cells(nb);
+		NE_CUDA_OK(cudaMemcpy(cells.data(), v.cells, nb * sizeof(int2), cudaMemcpyDeviceToHost));
+		for (size_t b = 0; b < nb; b++) {
+			if (table) table[b] = cells[b].x;
+			if (inv_majorant) memcpy(&inv_majorant[b], &cells[b].y, 4);
+		}
+	}
+	if (pool && v.n_slots) NE_CUDA_OK(cudaMemcpy(pool, v.pool, size_t(v.n_slots) * BRICK_VOX * sizeof(float), cudaMemcpyDeviceToHost));
 	return NE_B200_OK;
 }
 

@@ -1,0 +1,163 @@
+// ne_bricks.cu — the brick-sparse density grid built ON THE GPU from a dense W*H*D grid (the Texture that
+// ResourceManager::loadVolasTexture / loadVDBasTexture hand to GridMedia, core/ResourceManager.cpp:165-286).
+// ne_b200_scene_upload copies the caller's dense grid to HBM once and three kernels turn it into the layout the
+// tracking kernels walk (ne_scene.cuh DVolume): per brick {slot, 1/majorant} cells, 9^3 apron records, global maximum.
+// The result is bit-identical to the host builder ne_b200_host_build_bricks (ne_host.cpp), which stays the
+// inspectable definition and serves leaf (.vdb) input; tests/test_gpu_parity.py compares the two.
+#include <algorithm>
+#include <vector>
+
+#include "ne_ctx.h"
+
+using namespace ne;
+
+namespace {
+
+// One warp per brick: need = any voxel != 0 in the record's [8b, 8b+8]^3; maj = max(0, voxels of [8b-1, 8b+8]^3)
+// (the trilinear stencil of any point of the brick, +-1 voxel); voxels at or beyond the grid count as 0
+// (GridMedia::density :17-18). Also the grid's global maximum (GridMedia::calculateMaxDensity, GridMedia.h:16-21).
+__global__ void __launch_bounds__(256) k_brick_scan(const float* __restrict__ dense, int W, int H, int D, int nbx, int nby, int nbz,
+                                                    uint32_t* __restrict__ need, float* __restrict__ maj, unsigned int* gmaxBits) {
+	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const int nb = nbx * nby * nbz;
+	if (warp >= nb) return;
+	const int bx = warp % nbx, by = (warp / nbx) % nby, bz = warp / (nbx * nby);
+	bool any = false;
+	float m = 0.0f;
+	for (int k = lane; k < 1000; k += 32) {  // the 10^3 voxels [8b-1, 8b+8]^3
+		int lx = k % 10 - 1, ly = (k / 10) % 10 - 1, lz = k / 100 - 1;
+		int x = bx * 8 + lx, y = by * 8 + ly, z = bz * 8 + lz;
+		if (x < 0 || y < 0 || z < 0 || x >= W || y >= H || z >= D) continue;
+		float v = dense[(size_t(z) * H + y) * W + x];
+		m = v > m ? v : m;  // std::max(m, v) of the host builder
+		if (lx >= 0 && ly >= 0 && lz >= 0 && v != 0.0f) any = true;
+	}
+	for (int o = 16; o; o >>= 1) {
+		float t = __shfl_xor_sync(0xffffffffu, m, o);
+		m = t > m ? t : m;
+	}
+	any = __any_sync(0xffffffffu, any);
+	if (lane == 0) {
+		need[warp] = any ? 1u : 0u;
+		maj[warp] = m;
+		if (m > 0) atomicMax(gmaxBits, __float_as_uint(m));  // positive floats order like their bit patterns
+	}
+}
+
+// Exclusive prefix sum of need[] (raster order over bricks = the host builder's slot order) by one block.
+__global__ void __launch_bounds__(1024) k_brick_slots(const uint32_t* __restrict__ need, int nb, int* __restrict__ slot, int* total) {
+	__shared__ uint32_t warpSum[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int base = 0; base < nb; base += 1024) {
+		int i = base + threadIdx.x;
+		uint32_t v = i < nb ? need[i] : 0u, x = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += t;
+		}
+		if (lane == 31) warpSum[w] = x;
+		__syncthreads();
+		if (w == 0) {
+			uint32_t s = warpSum[lane], y = s;
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t t = __shfl_up_sync(0xffffffffu, y, o);
+				if (lane >= o) y += t;
+			}
+			warpSum[lane] = y - s;  // exclusive over warps
+		}
+		__syncthreads();
+		uint32_t excl = carry + warpSum[w] + x - v;
+		if (i < nb) slot[i] = v ? int(excl) : -1;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = excl + v;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *total = int(carry);
+}
+
+// One block per brick: the {slot, 1/majorant} cell and, for bricks with storage, the 9^3 apron record.
+__global__ void __launch_bounds__(256) k_brick_fill(const float* __restrict__ dense, int W, int H, int D, int nbx, int nby, const int* __restrict__ slot,
+                                                    const float* __restrict__ maj, int2* __restrict__ cells, float* __restrict__ pool) {
+	const int b = blockIdx.x;
+	const int s = slot[b];
+	if (threadIdx.x == 0) {
+		float m = maj[b];
+		float inv = (s >= 0 && m > 0) ? 1.0f / m : 0.0f;
+		cells[b] = make_int2(s, __float_as_int(inv));
+	}
+	if (s < 0) return;
+	const int bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
+	float* dst = pool + size_t(s) * BRICK_VOX;
+	for (int k = threadIdx.x; k < BRICK_VOX; k += blockDim.x) {
+		int x = bx * 8 + k % 9, y = by * 8 + (k / 9) % 9, z = bz * 8 + k / 81;
+		dst[k] = (x < W && y < H && z < D) ? dense[(size_t(z) * H + y) * W + x] : 0.0f;
+	}
+}
+
+}  // namespace
+
+namespace ne {
+
+int scratch_reserve(ne_b200_ctx* ctx, size_t bytes) {
+	if (ctx->scratchBytes >= bytes) return NE_B200_OK;
+	if (ctx->scratch) {
+		NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->scratch);
+		ctx->scratch = nullptr;
+		ctx->scratchBytes = 0;
+	}
+	NE_CUDA_OK(cudaMalloc(&ctx->scratch, bytes));
+	ctx->scratchBytes = bytes;
+	return NE_B200_OK;
+}
+
+// dense (host) -> DVolume in HBM. Allocations that belong to the scene are pushed to ctx->sceneAllocs.
+int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out) {
+	const size_t nvox = size_t(v.width) * v.height * v.depth;
+	const int nbx = (v.width + 7) / 8, nby = (v.height + 7) / 8, nbz = (v.depth + 7) / 8;
+	const size_t nb = size_t(nbx) * nby * nbz;
+	if (nb > size_t(1) << 30) { set_error("grid too large"); return NE_B200_ERR_INVALID; }
+	// scratch: dense grid | need | maj | slot | {total, gmax}
+	auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+	const size_t oDense = 0, oNeed = up(nvox * 4), oMaj = oNeed + up(nb * 4), oSlot = oMaj + up(nb * 4), oTot = oSlot + up(nb * 4);
+	int rc = scratch_reserve(ctx, oTot + 256);
+	if (rc) return rc;
+	char* base = static_cast<char*>(ctx->scratch);
+	float* dDense = reinterpret_cast<float*>(base + oDense);
+	uint32_t* dNeed = reinterpret_cast<uint32_t*>(base + oNeed);
+	float* dMaj = reinterpret_cast<float*>(base + oMaj);
+	int* dSlot = reinterpret_cast<int*>(base + oSlot);
+	int* dTot = reinterpret_cast<int*>(base + oTot);
+	cudaStream_t st = ctx->stream;
+	NE_CUDA_OK(cudaMemsetAsync(dTot, 0, 8, st));
+	NE_CUDA_OK(cudaMemcpyAsync(dDense, v.dense, nvox * 4, cudaMemcpyHostToDevice, st));
+	k_brick_scan<<<unsigned((nb * 32 + 255) / 256), 256, 0, st>>>(dDense, v.width, v.height, v.depth, nbx, nby, nbz, dNeed, dMaj,
+	                                                             reinterpret_cast<unsigned int*>(dTot + 1));
+	k_brick_slots<<<1, 1024, 0, st>>>(dNeed, int(nb), dSlot, dTot);
+	ctx->kernelLaunches += 2;
+	int tot[2] = {0, 0};
+	NE_CUDA_OK(cudaMemcpyAsync(tot, dTot, 8, cudaMemcpyDeviceToHost, st));
+	NE_CUDA_OK(cudaStreamSynchronize(st));
+	int2* dCells = nullptr;
+	float* dPool = nullptr;
+	NE_CUDA_OK(cudaMalloc(&dCells, nb * sizeof(int2)));
+	ctx->sceneAllocs.push_back(dCells);
+	NE_CUDA_OK(cudaMalloc(&dPool, std::max<size_t>(1, size_t(tot[0]) * BRICK_VOX) * sizeof(float)));
+	ctx->sceneAllocs.push_back(dPool);
+	k_brick_fill<<<unsigned(nb), 256, 0, st>>>(dDense, v.width, v.height, v.depth, nbx, nby, dSlot, dMaj, dCells, dPool);
+	ctx->kernelLaunches++;
+	NE_CUDA_OK(cudaGetLastError());
+	out.W = v.width; out.H = v.height; out.D = v.depth;
+	out.bx = nbx; out.by = nby; out.bz = nbz;
+	out.n_slots = tot[0];
+	out.cells = dCells;
+	out.pool = dPool;
+	memcpy(&out.max_density, &tot[1], 4);
+	out.inv_max_density = 1.0f / out.max_density;
+	return NE_B200_OK;
+}
+
+}  // namespace ne

@@ -31,6 +31,7 @@ struct ne_b200_ctx {
 	std::vector<void*> sceneAllocs;  // device allocations owned by the uploaded scene
 	ne::DScene scene{};
 	bool haveScene = false;
+	int nVolumes = 0;
 	ne::DCamera cam{};
 	bool haveCamera = false;
 	float* accum = nullptr;  // W*H*3 fp32 radiance sums
@@ -41,10 +42,15 @@ struct ne_b200_ctx {
 	double msRender = 0, msVolume = 0, msExtend = 0, msShade = 0, msUpload = 0;
 	cudaEvent_t evA = nullptr, evB = nullptr;
 	ne_wavefront_state* wf = nullptr;
+	void* scratch = nullptr;  // reusable device scratch (dense grid staging of the brick builder, resolve buffers)
+	size_t scratchBytes = 0;
 };
 
 namespace ne {
 // ne_wavefront.cu
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags);
 void wavefront_free(ne_b200_ctx* ctx);
+// ne_bricks.cu
+int scratch_reserve(ne_b200_ctx* ctx, size_t bytes);
+int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out);
 }  // namespace ne

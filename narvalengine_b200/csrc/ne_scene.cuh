@@ -23,6 +23,7 @@ struct DTexture {
 struct DVolume {
 	int W, H, D;
 	int bx, by, bz;
+	int n_slots;
 	const int2* cells;
 	const float* pool;
 	float max_density, inv_max_density;  // GridMedia::invMaxDensity, GridMedia.cpp:12

@@ -300,6 +300,35 @@ def test_density_and_tracking(ctx, oracle, leaves):
     assert_close(sd[coll], rsd[coll], what="sample.d", rtol=1e-4, atol=1e-5, frac=0.999)
 
 
+@pytest.mark.parametrize("res", [(40, 24, 33), (64, 64, 64), (9, 8, 7)])
+def test_gpu_brick_builder_equals_host_builder(ctx, res):
+    """Dense grids are bricked by GPU kernels during ne_b200_scene_upload (csrc/ne_bricks.cu); the result must be the
+    host builder's (ne_b200_host_build_bricks, the inspectable definition checked voxel by voxel in test_host.py):
+    same slot order, same records, same reciprocal majorants, same global maximum - bit for bit."""
+    import ctypes as C
+    b = scenes.noise_volume_scene(res=res, density=30.0)
+    ctx.upload(b)
+    lib = ctx.lib
+    vol = b.desc().volumes[0]
+    dims = (C.c_int32 * 4)()
+    mx = C.c_float()
+    assert lib.ne_b200_host_build_bricks(C.byref(vol), dims, None, None, None, C.byref(mx)) == 0
+    bx, by, bz, slots = list(dims)
+    ht, hi, hp = np.zeros((bz, by, bx), np.int32), np.zeros((bz, by, bx), np.float32), np.zeros((max(slots, 1), 729), np.float32)
+    assert lib.ne_b200_host_build_bricks(C.byref(vol), dims, ht.ctypes.data_as(abi.pi32), hi.ctypes.data_as(abi.pf32),
+                                         hp.ctypes.data_as(abi.pf32), C.byref(mx)) == 0
+    ddims = (C.c_int32 * 4)()
+    dmx = C.c_float()
+    assert lib.ne_b200_test_read_bricks(ctx.h, 0, ddims, None, None, None, C.byref(dmx)) == 0
+    assert list(ddims) == [bx, by, bz, slots] and dmx.value == mx.value
+    dt, di, dp = np.zeros_like(ht), np.zeros_like(hi), np.zeros_like(hp)
+    assert lib.ne_b200_test_read_bricks(ctx.h, 0, ddims, dt.ctypes.data_as(abi.pi32), di.ctypes.data_as(abi.pf32),
+                                        dp.ctypes.data_as(abi.pf32), None) == 0
+    assert np.array_equal(dt, ht)
+    assert np.array_equal(di.view(np.uint32), np.where(ht >= 0, hi, 0).astype(np.float32).view(np.uint32))
+    assert np.array_equal(dp[:slots].view(np.uint32), hp[:slots].view(np.uint32))
+
+
 def test_golden_tracking_appendix_e(ctx, oracle):
     """SURVEY E15 (Tr, seed 5: killed by RR after 5 draws) and E17 (sample, seed 6)."""
     ctx.upload(scenes.s2_volume())
