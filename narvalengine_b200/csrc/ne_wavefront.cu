@@ -2,8 +2,8 @@
 // (core/OfflineEngine.cpp:61-71) over the whole frame as a WAVEFRONT of SoA path records.
 //
 //   pool      N path slots (one 128-byte record each: 64 B path state + 48 B hit) that are refilled with new camera
-//             samples as paths terminate, so the wavefront stays full until the work runs out. 16 Mi slots by default
-//             (5.4 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
+//             samples as paths terminate, so the wavefront stays full until the work runs out. 32 Mi slots by default
+//             (10.4 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
 //   queues    arrays of slot indices: extend -> {volume, surface}; volume -> {scatter, volume (walk not finished),
 //             next extend}; free slots. All pushes are warp-aggregated (one atomicAdd per warp per queue)
 //   kernels   plan (1 thread: queue bookkeeping) · generate (camera rays) · extend (Scene::intersectScene fold, BVH)
@@ -283,8 +283,12 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 	flush_stats_wf(st, P.counters);
 }
 
+#ifndef NE_TRACK_THREADS
 #define NE_TRACK_THREADS 256
+#endif
+#ifndef NE_TRACK_BLOCKS
 #define NE_TRACK_BLOCKS 4  // resident blocks per SM the tracking kernels are compiled for (64 registers per thread)
+#endif
 
 // Lane states of the persistent tracking kernels.
 enum { L_IDLE = 0, L_MOVING = 1, L_CAND = 2, L_FIN_HIT = 3, L_FIN_BUDGET = 4, L_FIN_END = 5 };
@@ -673,7 +677,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
 	const unsigned long long work = (unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin);
 	if (work == 0 || bounces == 0) return NE_B200_OK;
-	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 24));
+	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 25));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
 	int rc = wavefront_ensure(ctx, nSlots);
 	if (rc) return rc;
