@@ -182,6 +182,53 @@ int ne_b200_host_build_bvh(const float* positions, int32_t n_vertices, const uin
                            int32_t counts[2], void* nodes, float* triangles);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Scene front end and framebuffer consumers (pure host code): what SceneReader / ResourceManager / saveImage do.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* SceneSettings as SceneReader::processCameraAndRenderer fills it (src/io/SceneReader.cpp:669-674, core/Settings.h). */
+typedef struct ne_b200_render_settings {
+	int32_t width, height;        /* renderer.resolution */
+	int32_t spp, bounces;
+	int32_t hdr;                  /* stored, unused by the offline path (OfflineEngine.cpp:39-52) */
+} ne_b200_render_settings;
+
+/* A scene file loaded into a ne_b200_scene_desc: replaces SceneReader::loadScene (src/io/SceneReader.cpp:10-53) with
+ * processMaterial :67-222, processPrimitives :224-648 (obj meshes through this library's own OBJ reader: one vertex
+ * per face corner, fan triangulation, V flipped, like assimp with Triangulate|FlipUVs, ResourceManager.cpp:59),
+ * processCameraAndRenderer :650-675, ResourceManager::loadVolasTexture (.vol, ResourceManager.cpp:222-286) and
+ * loadTexture (PNG -> RGBA8, mirror wrap, :288-315). `resources_dir` is the reference's RESOURCES_DIR: asset paths in
+ * the JSON are relative to it. The object owns every array its descriptor points to.
+ * Not covered: .vdb (needs OpenVDB: pass leaf bricks through ne_b200_volume), gltf, infiniteAreaLight -> error. */
+typedef struct ne_b200_scene_file ne_b200_scene_file;
+int ne_b200_scene_file_load(const char* json_path, const char* resources_dir, ne_b200_scene_file** out);
+int ne_b200_scene_file_parse(const char* json_text, const char* resources_dir, ne_b200_scene_file** out);
+const ne_b200_scene_desc* ne_b200_scene_file_desc(const ne_b200_scene_file* file);
+/* Camera(position, lookAt, (0,1,0), vfov, W/H, 1e-4, focus): SceneReader ignores the JSON's `up` and `aperture`, and
+ * autoFocus yields 3 (Q26, SceneReader.cpp:660-668). */
+int ne_b200_scene_file_camera(const ne_b200_scene_file* file, ne_b200_camera* out);
+int ne_b200_scene_file_settings(const ne_b200_scene_file* file, ne_b200_render_settings* out);
+void ne_b200_scene_file_free(ne_b200_scene_file* file);
+
+/* `.vol` density grids, the text format of ResourceManager::loadVolasTexture (ResourceManager.cpp:222-286): "W H D \n",
+ * one discarded line, then densities x fastest, every token followed by one space. Two-call pattern: voxels = NULL
+ * returns dims only. The writer emits exactly what that parser captures. */
+int ne_b200_vol_read(const char* path, int32_t dims[3], float* voxels);
+int ne_b200_vol_write(const char* path, const int32_t dims[3], const float* voxels);
+
+/* stbi_load(path, ..., STBI_rgb_alpha) for PNG files (ResourceManager::loadTexture, ResourceManager.cpp:288-315):
+ * dims = {width, height}; rgba = NULL returns dims only. */
+int ne_b200_image_read_png(const char* path, int32_t dims[2], uint8_t* rgba);
+
+/* saveImage(pixels, W, H, RGB32F, PNG | EXR, path), src/materials/Texture.h:44-75: PNG = clamp, (uint8_t)(v*255),
+ * 3 channels; EXR = three float32 channels (tinyexr SaveEXR(..., 3, 0, ...)), here written uncompressed.
+ * rgb = width*height*3 floats, row-major, row 0 first (the layout of OfflineEngine::pixels). */
+int ne_b200_image_write_png(const char* path, int width, int height, const float* rgb);
+int ne_b200_image_write_exr(const char* path, int width, int height, const float* rgb);
+/* OfflineEngine::coreLoop's output.ppm (OfflineEngine.cpp:82,119-138): P6, maxval 65535, big-endian 16-bit samples,
+ * pixels written last to first. rgb = the tone-mapped frame. */
+int ne_b200_image_write_ppm(const char* path, int width, int height, const float* rgb);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Context, scene, render (replaces OfflineEngine, src/core/OfflineEngine.cpp).
  * ---------------------------------------------------------------------------------------------------------- */
 

@@ -62,6 +62,10 @@ class Camera(C.Structure):
                 ("side", f32 * 3), ("up", f32 * 3), ("lens_radius", f32)]
 
 
+class RenderSettings(C.Structure):
+    _fields_ = [("width", i32), ("height", i32), ("spp", i32), ("bounces", i32), ("hdr", i32)]
+
+
 class Hit(C.Structure):
     _fields_ = [("hit_point", f32 * 3), ("normal", f32 * 3), ("uv", f32 * 2), ("t_near", f32), ("t_far", f32),
                 ("hit", i32), ("instance", i32), ("is_light", i32), ("primitive", i32)]
@@ -85,6 +89,18 @@ SYMBOLS = {
     "ne_b200_camera_make": (C.c_int, [pf32, pf32, pf32, f32, f32, f32, f32, C.POINTER(Camera)]),
     "ne_b200_host_build_bricks": (C.c_int, [C.POINTER(Volume), pi32, pi32, pf32, pf32, pf32]),
     "ne_b200_host_build_bvh": (C.c_int, [pf32, i32, pu32, i32, pi32, C.c_void_p, pf32]),
+    "ne_b200_scene_file_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ne_b200_scene_file_parse": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ne_b200_scene_file_desc": (C.POINTER(SceneDesc), [C.c_void_p]),
+    "ne_b200_scene_file_camera": (C.c_int, [C.c_void_p, C.POINTER(Camera)]),
+    "ne_b200_scene_file_settings": (C.c_int, [C.c_void_p, C.POINTER(RenderSettings)]),
+    "ne_b200_scene_file_free": (None, [C.c_void_p]),
+    "ne_b200_vol_read": (C.c_int, [C.c_char_p, pi32, pf32]),
+    "ne_b200_vol_write": (C.c_int, [C.c_char_p, pi32, pf32]),
+    "ne_b200_image_read_png": (C.c_int, [C.c_char_p, pi32, C.POINTER(C.c_uint8)]),
+    "ne_b200_image_write_png": (C.c_int, [C.c_char_p, C.c_int, C.c_int, pf32]),
+    "ne_b200_image_write_exr": (C.c_int, [C.c_char_p, C.c_int, C.c_int, pf32]),
+    "ne_b200_image_write_ppm": (C.c_int, [C.c_char_p, C.c_int, C.c_int, pf32]),
     "ne_b200_last_error": (C.c_char_p, []),
     "ne_b200_device_count": (C.c_int, []),
     "ne_b200_create": (C.c_int, [C.c_int, C.POINTER(_ctx)]),

@@ -191,3 +191,71 @@ class CameraParams:
         abi.check(lib, lib.ne_b200_camera_make(_f3(self.look_from), _f3(self.look_at), _f3(self.up), self.vfov,
                                                aspect, self.aperture, self.focus, C.byref(cam)), "camera_make")
         return cam
+
+
+class SceneFile:
+    """A JSON scene file loaded by the library's front end (ne_b200_scene_file_*, csrc/ne_frontend.cpp): the
+    counterpart of `SceneReader(filePath)` + `getScene() / getMainCamera() / getSettings()` (reference
+    src/io/SceneReader.cpp:10-53,676-690). Can be handed to Context.upload() like a SceneBuilder."""
+
+    def __init__(self, path=None, resources_dir="", text=None, lib=None):
+        self.lib = lib or abi.load_library()
+        h = C.c_void_p()
+        res = resources_dir.encode() if resources_dir is not None else None
+        if text is not None:
+            rc = self.lib.ne_b200_scene_file_parse(text.encode(), res, C.byref(h))
+        else:
+            rc = self.lib.ne_b200_scene_file_load(str(path).encode(), res, C.byref(h))
+        abi.check(self.lib, rc, "ne_b200_scene_file_load")
+        self.h = h
+
+    def desc(self):
+        return self.lib.ne_b200_scene_file_desc(self.h).contents
+
+    def camera(self):
+        cam = abi.Camera()
+        abi.check(self.lib, self.lib.ne_b200_scene_file_camera(self.h, C.byref(cam)), "ne_b200_scene_file_camera")
+        return cam
+
+    def settings(self):
+        st = abi.RenderSettings()
+        abi.check(self.lib, self.lib.ne_b200_scene_file_settings(self.h, C.byref(st)), "ne_b200_scene_file_settings")
+        return st
+
+    def close(self):
+        if self.h:
+            self.lib.ne_b200_scene_file_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def read_vol(path, lib=None):
+    """ResourceManager::loadVolasTexture's .vol parser -> array indexed [z, y, x]."""
+    lib = lib or abi.load_library()
+    dims = (C.c_int32 * 3)()
+    abi.check(lib, lib.ne_b200_vol_read(str(path).encode(), dims, None), "ne_b200_vol_read")
+    g = np.zeros((dims[2], dims[1], dims[0]), np.float32)
+    abi.check(lib, lib.ne_b200_vol_read(str(path).encode(), dims, g.ctypes.data_as(abi.pf32)), "ne_b200_vol_read")
+    return g
+
+
+def write_vol(path, grid, lib=None):
+    lib = lib or abi.load_library()
+    g = np.ascontiguousarray(grid, np.float32)
+    dims = (C.c_int32 * 3)(g.shape[2], g.shape[1], g.shape[0])
+    abi.check(lib, lib.ne_b200_vol_write(str(path).encode(), dims, g.ctypes.data_as(abi.pf32)), "ne_b200_vol_write")
+
+
+def save_image(path, rgb, lib=None):
+    """saveImage(pixels, W, H, RGB32F, PNG|EXR) (reference materials/Texture.h:44-75) / output.ppm by extension."""
+    lib = lib or abi.load_library()
+    a = np.ascontiguousarray(rgb, np.float32)
+    h, w = a.shape[:2]
+    fn = {".png": lib.ne_b200_image_write_png, ".exr": lib.ne_b200_image_write_exr, ".ppm": lib.ne_b200_image_write_ppm}[
+        str(path)[-4:].lower()]
+    abi.check(lib, fn(str(path).encode(), w, h, a.ctypes.data_as(abi.pf32)), "ne_b200_image_write")

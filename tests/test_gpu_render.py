@@ -134,3 +134,42 @@ def test_offline_engine_tile_protocol(ctx):
     assert eng.pixels.min() >= 0 and eng.pixels.max() <= 1
     np.testing.assert_allclose(eng.pixels, oracle.tonemap(eng.linear).reshape(eng.pixels.shape), rtol=1e-5, atol=1e-6)
     eng.close()
+
+
+def test_json_scene_file_renders_like_the_builder(ctx, tmp_path):
+    """The front end's descriptor (ne_b200_scene_file_load: JSON + .vol, csrc/ne_frontend.cpp) through the GPU gives the
+    image of the hand-built descriptor of the same scene."""
+    import json
+    from narvalengine_b200.scene import SceneFile, write_vol
+    grid = scenes.cloud_density((24, 20, 28), seed=3)
+    (tmp_path / "vol").mkdir()
+    write_vol(tmp_path / "vol" / "c.vol", grid, ctx.lib)
+    doc = {"version": "1", "materials": [
+        {"name": "cloud", "type": "volume", "scattering": [1.1, 1.1, 1.1], "absorption": [.01, .01, .01], "phaseFunction": "hg", "g": 0.0, "density": 30,
+         "path": "vol/c.vol"},
+        {"name": "floor", "type": "microfacet", "roughness": 0.95, "metallic": 0.0, "albedo": [.8, .7, .6]},
+        {"name": "light", "type": "emitter", "albedo": [300, 300, 260]}],
+        "primitives": [
+        {"name": "v", "type": "volume", "materialName": "cloud", "transform": {"position": [0, 1.2, 0], "rotation": [0, 30, 0], "scale": [2, 1.6, 2]}},
+        {"name": "f", "type": "rectangle", "materialName": "floor", "transform": {"position": [0, 0, 0], "rotation": [90, 0, 0], "scale": [8, 8, 1]}},
+        {"name": "l", "type": "rectangle", "materialName": "light", "transform": {"position": [0, 3.9, 0], "rotation": [-89, 0, 0], "scale": [1, 1, 1]}}],
+        "camera": {"position": [0, 2, -5], "lookAt": [0, 1, 0], "up": [0, 1, 0], "speed": 1, "vfov": 45, "aperture": 0.1, "autoFocus": True},
+        "renderer": {"resolution": [64, 48], "spp": 16, "bounces": 6, "mode": "offline", "HDR": False}}
+    (tmp_path / "s.json").write_text(json.dumps(doc))
+    sf = SceneFile(tmp_path / "s.json", str(tmp_path), lib=ctx.lib)
+    st = sf.settings()
+    ctx.upload(sf)
+    a = np.zeros((st.height, st.width, 3), np.float32)
+    ctx.render_frame(sf.camera(), st.width, st.height, st.spp, st.bounces, 1, 0, None, a)
+    b = scenes.SceneBuilder()
+    vol = b.add_volume_dense(grid)
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 30.0, vol, "hg", 0.0)
+    b.add_microfacet("floor", (.8, .7, .6), 0.95, 0.0)
+    b.add_emitter("light", (300, 300, 260))
+    b.add_volume("cloud", (0, 1.2, 0), (0, 30, 0), (2, 1.6, 2))
+    b.add_rectangle("floor", (0, 0, 0), (90, 0, 0), (8, 8, 1))
+    b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
+    m = render(ctx, b, scenes.CameraParams((0, 2, -5), (0, 1, 0), 45.0), st.width, st.height, st.spp)
+    assert m.mean() > 0
+    np.testing.assert_allclose(a, m, rtol=2e-4, atol=1e-5 * float(m.mean()))
+    sf.close()
