@@ -84,7 +84,7 @@ typedef enum ne_b200_material_type {
 	NE_B200_MAT_MICROFACET = 0,   /* GlossyBSDF(GGX, Schlick 0.04) :76-140 */
 	NE_B200_MAT_EMITTER = 1,      /* DiffuseLight :141-155 */
 	NE_B200_MAT_VOLUME = 2,       /* GridMedia (volume >= 0) or HomogeneousMedia (volume < 0) + VolumeBSDF :187-219 */
-	NE_B200_MAT_DIRECTIONAL = 3,  /* DirectionalLight :156-168   (next) */
+	NE_B200_MAT_DIRECTIONAL = 3,  /* DirectionalLight :156-168: `li` = le (JSON albedo), `direction` = normalize(-position) */
 	NE_B200_MAT_INFINITE = 4      /* InfiniteAreaLight :169-186  (next) */
 } ne_b200_material_type;
 

@@ -420,9 +420,13 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 			if (m.volume < 0) { set_error("HomogeneousMedia (volume material without a grid) is not covered yet (SURVEY 8f rank 3)"); return NE_B200_ERR_UNSUPPORTED; }
 			if (m.volume >= d->n_volumes) { set_error("material volume index out of range"); return NE_B200_ERR_INVALID; }
 			break;
-		case NE_B200_MAT_DIRECTIONAL:
+		case NE_B200_MAT_DIRECTIONAL:  // SceneReader.cpp:156-168: le = albedo (in `li` here), direction = normalize(-position)
+			o.has_light = 1;
+			o.directional = 1;
+			for (int k = 0; k < 3; k++) o.direction[k] = m.direction[k];
+			break;
 		case NE_B200_MAT_INFINITE:
-			set_error("directional / infinite-area lights are not covered yet (SURVEY 8f rank 3)");
+			set_error("infinite-area lights are not covered yet (SURVEY 8f rank 3)");
 			return NE_B200_ERR_UNSUPPORTED;
 		default: set_error("unknown material type"); return NE_B200_ERR_INVALID;
 		}
@@ -547,6 +551,8 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	s.n_models = int(models.size());
 	s.n_lights = int(lights.size());
 	s.has_medium = hasMedium ? 1 : 0;
+	for (size_t f = models.size(); f < fold.size(); f++)
+		if (mats[d->primitives[fold[f]].material].directional) s.n_directional++;
 	if ((rc = push_alloc(ctx, insts.data(), insts.size(), &s.inst))) return rc;
 	if ((rc = push_alloc(ctx, mats.data(), mats.size(), &s.mat))) return rc;
 	if ((rc = push_alloc(ctx, texs.data(), texs.size(), &s.tex))) return rc;

@@ -271,6 +271,10 @@ NE_D void tri_uv(const DMesh& m, int tri, V3 p, float& u, float& v) {
 NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st) {
 	const DInstance& in = s.inst[i];
 	if (!in.collision) return false;
+	if (in_lights) {  // Model.cpp:429-432: a light whose Le(ray) is not black (directional) is never intersected
+		const DMaterial& lm = s.mat[in.material];
+		if (lm.directional && !is_black(V3(lm.li[0], lm.li[1], lm.li[2]))) return false;
+	}
 	Ray ray = transform_ray(rayW, in.Mi);
 	bool did = false;
 	st.prim_tests++;

@@ -96,13 +96,23 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	V3 Lrad(lm.li[0], lm.li[1], lm.li[2]);
 
-	// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
-	V3 A = light_sample_point(lprim, li, isect, rng);
 	Ray wo;
 	wo.o = isect.p;
-	wo.d = normalize(A - wo.o);
-	float lightPdf = light_pdf(lprim, li, isect, rng);
-	V3 Li = Lrad;
+	float lightPdf;
+	V3 Li;
+	if (lm.directional) {
+		// DirectionalLight::sampleLi, lights/DirectionalLight.cpp:13-20: no draws, pdf 1, returns Light::li = 0 (Q23: the
+		// light half is dead; wo.d still feeds the medium's phase evaluation of the BSDF half, Q18)
+		wo.d = -V3(lm.direction[0], lm.direction[1], lm.direction[2]);
+		lightPdf = 1;
+		Li = V3(0.0f);
+	} else {
+		// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
+		V3 A = light_sample_point(lprim, li, isect, rng);
+		wo.d = normalize(A - wo.o);
+		lightPdf = light_pdf(lprim, li, isect, rng);
+		Li = Lrad;
+	}
 	V3 f(0.0f);
 	float scatteringPdf = 0;
 	bool isSurface = !m.has_medium;
@@ -180,7 +190,14 @@ NE_D int classify_hit(const DScene& s, bool did, const Hit& isect, const PathSta
 		const DMaterial& m = s.mat[mi];
 		sink.emit(ps.T * V3(m.li[0], m.li[1], m.li[2]));
 	}
-	// else at bounce 0: sum of Light::Le over all lights = 0 for DiffuseLight (lights/Light.h:20-22)
+	// else at bounce 0 (:249-256): the sum of Light::Le over every light model - 0 for DiffuseLight (lights/Light.h:20-22),
+	// le for DirectionalLight (lights/DirectionalLight.cpp:4-6)
+	else if (ps.bounce == 0 && s.n_directional) {
+		for (int i = s.n_models; i < s.n_inst; i++) {
+			const DMaterial& lm = s.mat[s.inst[i].material];
+			if (lm.directional) sink.emit(ps.T * V3(lm.li[0], lm.li[1], lm.li[2]));
+		}
+	}
 	if (!did || mi < 0 || !s.mat[mi].has_bsdf) return HIT_TERMINATE;
 	return HIT_SURFACE;
 }

@@ -41,6 +41,8 @@ struct DMaterial {
 	int has_bsdf;     // Material::bsdf != nullptr
 	int transmissive; // bsdf->hasType(BxDF_TRANSMISSION)
 	int has_light, has_medium;
+	int directional;   // DirectionalLight (lights/DirectionalLight.cpp): Le = Li() = li, sampleLi returns 0 (Q23); never hit
+	float direction[3];
 	int light_owner;  // fold index of the instance whose primitive Light::primitive points at (Q7: last one built)
 };
 
@@ -82,6 +84,7 @@ struct DScene {
 	const DTexture* tex;
 	const DVolume* vol;
 	const DMesh* mesh;
+	int n_directional;  // light instances with a DirectionalLight material (their Le is added to camera rays)
 	int has_medium;  // any instance with a medium material (intersectTr can only return true then, Q12)
 };
 

@@ -102,6 +102,18 @@ class SceneBuilder:
         m.env_tex = -1
         return self._mat(name, m)
 
+    def add_directional(self, name, le, position):
+        """directionalLight material (SceneReader.cpp:156-168): le = albedo, direction = normalize(-position)."""
+        m = abi.Material()
+        m.type = abi.MAT_DIRECTIONAL
+        m.li = _f3(le)
+        p = np.asarray(position, np.float32)
+        m.direction = _f3((np.float32(0) - p) / np.sqrt((p * p).sum(dtype=np.float32)))
+        m.albedo_tex = m.roughness_tex = m.metallic_tex = m.normal_tex = -1
+        m.volume = -1
+        m.env_tex = -1
+        return self._mat(name, m)
+
     def add_volume_material(self, name, scattering, absorption, density, volume, phase="isotropic", g=0.0):
         m = abi.Material()
         m.type = abi.MAT_VOLUME

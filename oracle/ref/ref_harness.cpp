@@ -39,6 +39,7 @@
 #include "core/ResourceManager.h"
 #include "integrators/VolumetricPathIntegrator.h"
 #include "lights/DiffuseLight.h"
+#include "lights/DirectionalLight.h"
 #include "primitives/Rectangle.h"
 #include "primitives/Sphere.h"
 #include "primitives/Point.h"
@@ -169,6 +170,12 @@ Material* buildMaterial(RefScene& rs, const ne_b200_material& m, const std::stri
 	} else if (m.type == NE_B200_MAT_EMITTER) {
 		DiffuseLight* l = new DiffuseLight();
 		l->li = v3(m.li);
+		mat->light = l;
+	} else if (m.type == NE_B200_MAT_DIRECTIONAL) {
+		// SceneReader.cpp:156-168: only `le` and `direction` are set (li stays 0, Q23)
+		DirectionalLight* l = new DirectionalLight();
+		l->le = v3(m.li);
+		l->direction = v3(m.direction);
 		mat->light = l;
 	} else if (m.type == NE_B200_MAT_VOLUME) {
 		PhaseFunction* pf = m.phase == NE_B200_PHASE_HG ? (PhaseFunction*)new HG(m.g) : (PhaseFunction*)new IsotropicPhaseFunction();

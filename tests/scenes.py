@@ -220,3 +220,22 @@ def cornell_c1(transform_fn=None):
     b.add_emitter("bulb", (200, 160, 120))
     b.add_sphere("bulb", (.9, .8, .3), 0.15)
     return b
+
+
+def directional_scene(transform_fn=None, res=(20, 16, 24)):
+    """A `directionalLight` sun (carried by a point primitive) over a cloud and a floor, plus a small area light: the sun
+    reaches the image only through Light::Le on camera rays and through the BSDF half of estimateDirect (Q23, Q12)."""
+    b = SceneBuilder(transform_fn)
+    vol = b.add_volume_dense(cloud_density(res, seed=5))
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 20.0, vol, "hg", 0.2)
+    b.add_microfacet("floor", (.8, .8, .8), 0.95, 0.0)
+    b.add_directional("sun", (0.6, 0.5, 0.4), (3, 5, -2))
+    b.add_emitter("light", (200, 200, 180))
+    b.add_volume("cloud", (0, 1.2, 0), (0, 15, 0), (2.2, 1.6, 2.0))
+    b.add_rectangle("floor", (0, 0, 0), (90, 0, 0), (8, 8, 1))
+    b.add_point("sun", (3, 5, -2))
+    b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
+    return b
+
+
+DIRECTIONAL_CAMERA = CameraParams((0, 2, -5), (0, 1, 0), 45.0)

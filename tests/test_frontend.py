@@ -164,6 +164,18 @@ def test_loader_errors_do_not_abort(lib, resources, mutate, needle):
     assert lib.ne_b200_scene_file_parse(b"{ not json", None, C.byref(h)) == abi.ERR_INVALID
 
 
+def test_directional_light_material(lib):
+    """SceneReader.cpp:156-168: le = albedo, direction = normalize(vec3(0) - position)."""
+    s = {"version": "1", "materials": [{"name": "sun", "type": "directionalLight", "albedo": [1, 2, 3], "position": [3, 4, 0]}],
+         "primitives": [{"name": "p", "type": "point", "materialName": "sun", "transform": {"position": [3, 4, 0], "scale": [1, 1, 1], "rotation": [0, 0, 0]}}],
+         "camera": SCENE["camera"], "renderer": SCENE["renderer"]}
+    sf = SceneFile(text=json.dumps(s), resources_dir="")
+    m = sf.desc().materials[0]
+    assert m.type == abi.MAT_DIRECTIONAL and list(m.li) == [1, 2, 3]
+    assert np.allclose(list(m.direction), [-0.6, -0.8, 0], atol=1e-7)
+    sf.close()
+
+
 def test_vol_reader_follows_the_reference_token_rules(lib, tmp_path):
     """ResourceManager.cpp:222-286: only space-terminated tokens count; line 2 is discarded; a value glued to a newline
     is dropped (std::stof stops at the newline); a last token without a trailing space is not captured."""

@@ -427,3 +427,18 @@ def test_li_tape_mixed(ctx, oracle):
     same = used == rused
     assert same.mean() > 0.97, f"Li(mixed) draw-count agreement {same.mean()}"
     assert_close(L[same], rL[same], what="Li mixed", rtol=2e-4, atol=1e-5, frac=0.99)
+
+
+def test_li_tape_directional_light(ctx, oracle):
+    """DirectionalLight (lights/DirectionalLight.cpp, Q23): Le on camera rays, a dead light half that draws nothing, Li()
+    through the BSDF half only - whole Li paths draw for draw against the reference."""
+    b = scenes.directional_scene()
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    cam_o, cam_d = oracle.camera_rays(scenes.DIRECTIONAL_CAMERA, 1.0, 7, np.random.default_rng(4).uniform(0, 1, (2000, 2)))
+    seeds = np.arange(len(cam_o), dtype=np.uint32) + 90000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, cam_o, cam_d, 6, seeds, stride=16384)
+    same = used == rused
+    assert same.mean() > 0.97, f"Li(directional) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li directional", rtol=2e-4, atol=1e-5, frac=0.99)
+    assert (rL.min(axis=1) >= 0.4 - 1e-6).mean() > 0.9  # nearly every camera ray carries the sun's Le

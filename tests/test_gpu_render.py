@@ -36,6 +36,7 @@ CASES = {
                scenes.CameraParams((0, 1, -6), (0, 1, 0), 45.0)),
     "mixed": (scenes.mixed_scene, scenes.MIXED_CAMERA),
     "mesh": (lambda: scenes.mesh_scene(n=64), scenes.MESH_CAMERA),
+    "directional": (scenes.directional_scene, scenes.DIRECTIONAL_CAMERA),
 }
 
 
