@@ -274,6 +274,13 @@ int ne_b200_clear(ne_b200_ctx* ctx);
 int ne_b200_accum_buffer(ne_b200_ctx* ctx, void** device_ptr, size_t* n_floats, int* samples_accumulated);
 int ne_b200_set_samples_accumulated(ne_b200_ctx* ctx, int samples);
 
+/* Progressive / resumable rendering: the accumulation buffer is a plain sum over sample indices, so
+ * a frame can be checkpointed and continued later - in another context, process or GPU - by rendering further sample
+ * ranges on top of it. download: sums[W*H*3] (host) and the number of samples they hold; upload: (re)allocates a
+ * width x height buffer, fills it with `sums` and sets the sample count. Philox keys make [0,a) + [a,b) = [0,b). */
+int ne_b200_accum_download(ne_b200_ctx* ctx, float* sums, int* samples_accumulated);
+int ne_b200_accum_upload(ne_b200_ctx* ctx, int width, int height, const float* sums, int samples_accumulated);
+
 /* rgb[W*H*3] = accumulation / samples (what `color / float(spp)` is at OfflineEngine.cpp:70). Host pointers. */
 int ne_b200_read_linear(ne_b200_ctx* ctx, float* rgb);
 /* rgb[W*H*3] = OfflineEngine::postProcessing(mean) = clamp(pow(1-exp(-0.5c), 1/2.2), 0, 1) (OfflineEngine.cpp:39-52):

@@ -113,6 +113,8 @@ SYMBOLS = {
     "ne_b200_clear": (C.c_int, [_ctx]),
     "ne_b200_accum_buffer": (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "ne_b200_set_samples_accumulated": (C.c_int, [_ctx, C.c_int]),
+    "ne_b200_accum_download": (C.c_int, [_ctx, pf32, C.POINTER(C.c_int)]),
+    "ne_b200_accum_upload": (C.c_int, [_ctx, C.c_int, C.c_int, pf32, C.c_int]),
     "ne_b200_read_linear": (C.c_int, [_ctx, pf32]),
     "ne_b200_read_tonemapped": (C.c_int, [_ctx, pf32]),
     "ne_b200_render_frame": (C.c_int, [_ctx, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, u64, u32,

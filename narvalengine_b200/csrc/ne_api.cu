@@ -653,6 +653,35 @@ int ne_b200_set_samples_accumulated(ne_b200_ctx* ctx, int samples) {
 	return NE_B200_OK;
 }
 
+int ne_b200_accum_download(ne_b200_ctx* ctx, float* sums, int* samples_accumulated) {
+	int rc = check_ctx(ctx, false);
+	if (rc) return rc;
+	if (!ctx->accum) { set_error("nothing rendered yet"); return NE_B200_ERR_STATE; }
+	if (!sums) { set_error("null buffer"); return NE_B200_ERR_INVALID; }
+	NE_CUDA_OK(cudaMemcpyAsync(sums, ctx->accum, size_t(ctx->W) * ctx->H * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if (samples_accumulated) *samples_accumulated = ctx->samples;
+	return NE_B200_OK;
+}
+
+int ne_b200_accum_upload(ne_b200_ctx* ctx, int width, int height, const float* sums, int samples_accumulated) {
+	int rc = check_ctx(ctx, false);
+	if (rc) return rc;
+	if (!sums || width <= 0 || height <= 0 || samples_accumulated < 0) { set_error("bad argument"); return NE_B200_ERR_INVALID; }
+	if (!ctx->accum || width != ctx->W || height != ctx->H) {
+		NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->accum) cudaFree(ctx->accum);
+		ctx->accum = nullptr;
+		NE_CUDA_OK(cudaMalloc(&ctx->accum, size_t(width) * height * 3 * sizeof(float)));
+		ctx->W = width;
+		ctx->H = height;
+	}
+	NE_CUDA_OK(cudaMemcpyAsync(ctx->accum, sums, size_t(width) * height * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	ctx->samples = samples_accumulated;
+	return NE_B200_OK;
+}
+
 static int read_resolved(ne_b200_ctx* ctx, float* linear, float* tonemapped) {
 	int rc = check_ctx(ctx, false);
 	if (rc) return rc;

@@ -83,6 +83,17 @@ class Context:
     def set_samples_accumulated(self, n):
         check(self.lib, self.lib.ne_b200_set_samples_accumulated(self.h, n), "ne_b200_set_samples_accumulated")
 
+    def accum_download(self, W, H):
+        """Checkpoint: (sums[H,W,3], samples) of the accumulation buffer."""
+        out, n = np.empty((H, W, 3), np.float32), C.c_int()
+        check(self.lib, self.lib.ne_b200_accum_download(self.h, _p(out), C.byref(n)), "ne_b200_accum_download")
+        return out, n.value
+
+    def accum_upload(self, sums, samples):
+        """Resume: continue rendering further sample ranges on top of a checkpoint."""
+        a = np.ascontiguousarray(sums, np.float32)
+        check(self.lib, self.lib.ne_b200_accum_upload(self.h, a.shape[1], a.shape[0], _p(a), samples), "ne_b200_accum_upload")
+
     def read_linear(self, W, H, out=None):
         out = np.empty((H, W, 3), np.float32) if out is None else out
         check(self.lib, self.lib.ne_b200_read_linear(self.h, _p(out)), "ne_b200_read_linear")

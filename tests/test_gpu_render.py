@@ -75,6 +75,34 @@ def test_sample_ranges_are_additive(ctx):
     np.testing.assert_allclose(two, one, rtol=2e-4, atol=1e-5 * float(one.mean()))
 
 
+def test_checkpoint_and_resume(ctx):
+    """Progressive rendering: samples [0,4), checkpoint to the host, resume in ANOTHER context with
+    samples [4,8) = one render of [0,8)."""
+    b = scenes.mixed_scene()
+    W, H = 48, 32
+    cam = scenes.MIXED_CAMERA.make(W / H, ctx.lib)
+    ctx.upload(b)
+    ctx.set_camera(cam)
+    ctx.render(W, H, 0, 0, 6)
+    ctx.clear()
+    ctx.render(W, H, 0, 4, 6, seed=9)
+    sums, n = ctx.accum_download(W, H)
+    assert n == 4
+    other = Context(0)
+    other.upload(b)
+    other.set_camera(cam)
+    other.accum_upload(sums, n)
+    other.render(W, H, 4, 8, 6, seed=9)
+    other.wait()
+    two = other.read_linear(W, H).copy()
+    other.close()
+    ctx.clear()
+    ctx.render(W, H, 0, 8, 6, seed=9)
+    ctx.wait()
+    one = ctx.read_linear(W, H)
+    np.testing.assert_allclose(two, one, rtol=2e-4, atol=1e-5 * float(one.mean()))
+
+
 @pytest.mark.parametrize("name", ["volume", "mixed"])
 def test_bounded_walks_are_unbiased(ctx, name, monkeypatch):
     """Stopping every tracking walk after a handful of events and resuming it in the next pass (memoryless restart)
