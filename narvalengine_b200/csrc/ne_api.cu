@@ -551,6 +551,8 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	s.n_models = int(models.size());
 	s.n_lights = int(lights.size());
 	s.has_medium = hasMedium ? 1 : 0;
+	s.n_mat = int(mats.size());
+	s.n_vol = int(vols.size());
 	for (size_t f = models.size(); f < fold.size(); f++)
 		if (mats[d->primitives[fold[f]].material].directional) s.n_directional++;
 	if ((rc = push_alloc(ctx, insts.data(), insts.size(), &s.inst))) return rc;

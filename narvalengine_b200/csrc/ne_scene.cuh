@@ -79,6 +79,7 @@ struct DScene {
 	int n_inst;    // fold order: instancedModels..., lights...
 	int n_models;  // first n_models entries are Scene::instancedModels
 	int n_lights;  // the rest are Scene::lights
+	int n_mat, n_vol;
 	const DInstance* inst;
 	const DMaterial* mat;
 	const DTexture* tex;

@@ -150,6 +150,40 @@ __device__ __forceinline__ void store_hit(const WfBuf& b, uint32_t slot, const H
 	b.rec[slot].hC = make_float4(h.u, h.v, __int_as_float(h.inst), __int_as_float(h.prim));
 }
 
+// The instance / material / volume tables are a few hundred bytes that every ray of every kernel reads through two or
+// three DEPENDENT loads (instance -> material -> volume). Each block stages them in shared memory once, so those
+// look-ups cost a shared-memory access instead of an L1/L2 round trip (36 % of k_wf_extend's stall samples before).
+// Scenes with more entries than fit keep reading them from global memory.
+#define NE_CACHE_INST 24
+#define NE_CACHE_MAT 24
+#define NE_CACHE_VOL 8
+struct SceneCache {
+	DInstance inst[NE_CACHE_INST];
+	DMaterial mat[NE_CACHE_MAT];
+	DVolume vol[NE_CACHE_VOL];
+};
+__device__ __forceinline__ DScene stage_scene(const DScene& g, SceneCache& sh) {
+	DScene s = g;
+	if (g.n_inst <= NE_CACHE_INST && g.n_mat <= NE_CACHE_MAT && g.n_vol <= NE_CACHE_VOL) {
+		const uint32_t* src;
+		uint32_t* dst;
+		src = reinterpret_cast<const uint32_t*>(g.inst); dst = reinterpret_cast<uint32_t*>(sh.inst);
+		for (uint32_t k = threadIdx.x; k < g.n_inst * (sizeof(DInstance) / 4); k += blockDim.x) dst[k] = src[k];
+		src = reinterpret_cast<const uint32_t*>(g.mat); dst = reinterpret_cast<uint32_t*>(sh.mat);
+		for (uint32_t k = threadIdx.x; k < g.n_mat * (sizeof(DMaterial) / 4); k += blockDim.x) dst[k] = src[k];
+		src = reinterpret_cast<const uint32_t*>(g.vol); dst = reinterpret_cast<uint32_t*>(sh.vol);
+		for (uint32_t k = threadIdx.x; k < g.n_vol * (sizeof(DVolume) / 4); k += blockDim.x) dst[k] = src[k];
+		__syncthreads();
+		s.inst = sh.inst;
+		s.mat = sh.mat;
+		s.vol = sh.vol;
+	}
+	return s;
+}
+#define NE_STAGE_SCENE()               \
+	__shared__ SceneCache sceneCache_; \
+	const DScene S = stage_scene(P.s, sceneCache_)
+
 // Turns the two next-event queries of estimateDirect into requests; emission and request weights go straight to
 // the accumulation buffer / request arrays.
 struct QueueSink {
@@ -259,6 +293,7 @@ __global__ void k_wf_commit(WfBuf b, DCounters* counters) {
 
 // Scene::intersectScene for every path of the extend queue + classify (Li :187-193, :244-260).
 __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	const uint32_t n = b.c->extend;
 	Stats st;
 	st.clear();
@@ -267,11 +302,11 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 		PathRec r = load_path(b, slot);
 		Hit h;
 		st.extend_rays++;
-		bool did = intersect_scene(P.s, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
+		bool did = intersect_scene(S, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
 		QueueSink sink;
 		sink.accum = P.accum;
 		sink.pixel = r.pixel;
-		int kind = classify_hit(P.s, did, h, r.ps, sink);
+		int kind = classify_hit(S, did, h, r.ps, sink);
 		if (kind == HIT_TERMINATE) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
 		} else {
@@ -322,6 +357,7 @@ struct WarpReserve {
 // reached in the next pass), so a warp is never left with one lane grinding through a long walk while 31 idle.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->vol;
 	Stats st;
@@ -387,9 +423,9 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 					ray.o = V3(A.x, A.y, A.z);
 					ray.d = V3(A.w, B.x, B.y);
 					ray.o = ray.at(tNear);
-					const DInstance& in = P.s.inst[inst];
-					const DMaterial& m = P.s.mat[in.material];
-					vol = &P.s.vol[m.volume];
+					const DInstance& in = S.inst[inst];
+					const DMaterial& m = S.mat[in.material];
+					vol = &S.vol[m.volume];
 					rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(C.w));
 					wr.start(rng);
 					trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tFar, wr, st);
@@ -421,6 +457,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 
 // Real collisions: phase function, next-event setup, continuation (Li :215-236).
 __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	const uint32_t n = b.c->scat;
 	Stats st;
 	st.clear();
@@ -435,8 +472,8 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 		sink.accum = P.accum;
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
-		Ray rayO = transform_ray(r.ps.ray, P.s.inst[h.inst].Mi);
-		int next = volume_scatter(P.s, r.ps, h, rayO, r.tHit, rng, sink, st);
+		Ray rayO = transform_ray(r.ps.ray, S.inst[h.inst].Mi);
+		int next = volume_scatter(S, r.ps, h, rayO, r.tHit, rng, sink, st);
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
 		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
@@ -451,6 +488,7 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 
 // Surface hits: GGX shading, next-event setup, continuation (Li :262-283).
 __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	const uint32_t n = b.c->surf;
 	Stats st;
 	st.clear();
@@ -465,7 +503,7 @@ __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
 		sink.accum = P.accum;
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
-		int next = shade_surface<PhiloxRng>(P.s, r.ps, h, rng, sink, st);
+		int next = shade_surface<PhiloxRng>(S, r.ps, h, rng, sink, st);
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
 		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
@@ -480,6 +518,7 @@ __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
 
 // visibilityTr requests: splat the weight when nothing or an emitter is hit first.
 __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	const uint32_t n = b.c->shadow;
 	Stats st;
 	st.clear();
@@ -487,7 +526,7 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 		float4 A = b.sA[i], B = b.sB[i];
 		float2 C = b.sC[i];
 		PhiloxRng dummy;
-		float vis = visibility_tr<PhiloxRng, false, true>(P.s, V3(A.x, A.y, A.z), V3(A.w, B.x, B.y), dummy, st);
+		float vis = visibility_tr<PhiloxRng, false, true>(S, V3(A.x, A.y, A.z), V3(A.w, B.x, B.y), dummy, st);
 		if (vis != 0) splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * vis);
 	}
 	flush_stats_wf(st, P.counters);
@@ -496,6 +535,7 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 // intersectTr :13-31 for the requests pushed in this iteration: march THROUGH non-medium surfaces until a medium
 // (the request gets its instance, entry point and segment length) or nothing (the request is dropped: Li = 0).
 __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	const uint32_t first = b.c->trNew0, n = b.c->tr;
 	Stats st;
 	st.clear();
@@ -509,9 +549,9 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 		for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
 			Hit hh;
 			st.shadow_rays++;
-			if (!intersect_scene(P.s, ray, hh, float(NE_EPSILON3), INFINITY, st)) break;
-			int mi = P.s.inst[hh.inst].material;
-			if (mi >= 0 && P.s.mat[mi].has_medium && P.s.mat[mi].volume >= 0) {
+			if (!intersect_scene(S, ray, hh, float(NE_EPSILON3), INFINITY, st)) break;
+			int mi = S.inst[hh.inst].material;
+			if (mi >= 0 && S.mat[mi].has_medium && S.mat[mi].volume >= 0) {
 				inst = hh.inst;
 				ray.o = ray.at(hh.tNear);
 				tRemain = hh.tFar - hh.tNear;
@@ -530,6 +570,7 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 // walk ends.
 template <bool BRICKMAJ>
 __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->tr;
 	Stats st;
@@ -581,9 +622,9 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 						Tr = D.x;
 						tRemain = D.y;
 						rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
-						const DInstance& in = P.s.inst[inst];
-						const DMaterial& m = P.s.mat[in.material];
-						vol = &P.s.vol[m.volume];
+						const DInstance& in = S.inst[inst];
+						const DMaterial& m = S.mat[in.material];
+						vol = &S.vol[m.volume];
 						wr.start(rng);
 						trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tRemain, wr, st);  // GridMedia::Tr :49
 						budget = P.budget;
