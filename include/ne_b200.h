@@ -85,7 +85,7 @@ typedef enum ne_b200_material_type {
 	NE_B200_MAT_EMITTER = 1,      /* DiffuseLight :141-155 */
 	NE_B200_MAT_VOLUME = 2,       /* GridMedia (volume >= 0) or HomogeneousMedia (volume < 0) + VolumeBSDF :187-219 */
 	NE_B200_MAT_DIRECTIONAL = 3,  /* DirectionalLight :156-168: `li` = le (JSON albedo), `direction` = normalize(-position) */
-	NE_B200_MAT_INFINITE = 4      /* InfiniteAreaLight :169-186  (next) */
+	NE_B200_MAT_INFINITE = 4      /* InfiniteAreaLight :169-186: `env_tex` = the lat-long map; carried by a sphere primitive */
 } ne_b200_material_type;
 
 typedef enum ne_b200_phase { NE_B200_PHASE_ISOTROPIC = 0, NE_B200_PHASE_HG = 1 } ne_b200_phase;
@@ -198,7 +198,7 @@ typedef struct ne_b200_render_settings {
  * processCameraAndRenderer :650-675, ResourceManager::loadVolasTexture (.vol, ResourceManager.cpp:222-286) and
  * loadTexture (PNG -> RGBA8, mirror wrap, :288-315). `resources_dir` is the reference's RESOURCES_DIR: asset paths in
  * the JSON are relative to it. The object owns every array its descriptor points to.
- * Not covered: .vdb (needs OpenVDB: pass leaf bricks through ne_b200_volume), gltf, infiniteAreaLight -> error. */
+ * Not covered: .vdb (needs OpenVDB: pass leaf bricks through ne_b200_volume) and gltf -> error. */
 typedef struct ne_b200_scene_file ne_b200_scene_file;
 int ne_b200_scene_file_load(const char* json_path, const char* resources_dir, ne_b200_scene_file** out);
 int ne_b200_scene_file_parse(const char* json_text, const char* resources_dir, ne_b200_scene_file** out);

@@ -307,6 +307,25 @@ void free_scene(ne_b200_ctx* ctx) {
 	memset(&ctx->scene, 0, sizeof(ctx->scene));
 }
 
+// Texture::sample on the host (materials/Texture.cpp:37-129), channel `ch` of the nearest texel: the same arithmetic as
+// tex_sample / tex_at in ne_device.cuh.
+float host_tex_sample(const ne_b200_texture& t, float u, float v, int ch) {
+	auto wrap = [](float x, int mode) {
+		if (mode == 1) { float f = std::fabs(x - float(int(x))); return f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f); }
+		return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+	};
+	u = wrap(u, t.wrap_u);
+	v = wrap(v, t.wrap_v);
+	int x = int(u * t.width), y = int(v * t.height);
+	if (x > 0 && x == t.width) x--;
+	if (y > 0 && y == t.height) y--;
+	size_t index = size_t(t.width) * y + x;
+	if (t.format == TEX_RGBA8) return static_cast<const uint8_t*>(t.texels)[4 * index + ch] / 255.0f;
+	const float* p = static_cast<const float*>(t.texels);
+	int n = t.format == TEX_R32F ? 1 : t.format == TEX_RG32F ? 2 : t.format == TEX_RGB32F ? 3 : 4;
+	return ch < n ? p[n * index + ch] : 0.0f;
+}
+
 size_t texel_bytes(int format) {
 	switch (format) {
 	case TEX_R32F: return 4;
@@ -394,6 +413,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 
 	// ---- validate + materials (SceneReader::processMaterial, io/SceneReader.cpp:67-222)
 	std::vector<DMaterial> mats(d->n_materials);
+	std::vector<int> envs;  // env_tex of every infiniteAreaLight material
 	for (int i = 0; i < d->n_materials; i++) {
 		const ne_b200_material& m = d->materials[i];
 		DMaterial& o = mats[i];
@@ -425,9 +445,14 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 			o.directional = 1;
 			for (int k = 0; k < 3; k++) o.direction[k] = m.direction[k];
 			break;
-		case NE_B200_MAT_INFINITE:
-			set_error("infinite-area lights are not covered yet (SURVEY 8f rank 3)");
-			return NE_B200_ERR_UNSUPPORTED;
+		case NE_B200_MAT_INFINITE:  // SceneReader.cpp:169-186: InfiniteAreaLight(tex); li and le stay 0
+			if (m.env_tex < 0 || m.env_tex >= d->n_textures) { set_error("infiniteAreaLight needs env_tex"); return NE_B200_ERR_INVALID; }
+			o.has_light = 1;
+			o.infinite = 1;
+			o.env = int(envs.size());
+			for (int k = 0; k < 3; k++) o.li[k] = 0.0f;
+			envs.push_back(m.env_tex);
+			break;
 		default: set_error("unknown material type"); return NE_B200_ERR_INVALID;
 		}
 	}
@@ -464,6 +489,45 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 		rc = push_alloc(ctx, (const uint8_t*)t.texels, size_t(t.width) * t.height * texel_bytes(t.format), &dev);
 		if (rc) return rc;
 		texs[i].texels = dev;
+	}
+
+	// ---- InfiniteAreaLight::InfiniteAreaLight(tex), lights/InfiniteAreaLight.h:20-41 + Distribution2D (Sampling.h:69-94)
+	std::vector<DEnvDist> envDists(envs.size());
+	for (size_t e = 0; e < envs.size(); e++) {
+		const ne_b200_texture& t = d->textures[envs[e]];
+		const int w = t.width, h = t.height, nc = h;  // Q27: every conditional is built with n = height
+		std::vector<float> img(size_t(w) * h + size_t(nc), 0.0f);  // zero padding where the reference reads past the array
+		for (int v = 0; v < h; v++) {
+			float vp = float(v) / float(h);
+			float sinTheta = float(std::sin(NE_PI * double(float(float(v) + 0.5f)) / double(float(h))));
+			for (int u = 0; u < w; u++) {
+				float up = float(u) / float(w);
+				img[u + size_t(v) * w] = host_tex_sample(t, up, vp, 1);
+				img[u + size_t(v) * w] *= sinTheta;
+			}
+		}
+		auto dist1d = [](const float* f, int n, std::vector<float>& cdf) {  // Distribution1D ctor, Sampling.h:12-29
+			cdf.assign(n + 1, 0.0f);
+			for (int i = 1; i < n + 1; i++) cdf[i] = cdf[i - 1] + f[i - 1] / n;
+			float funcInt = cdf[n];
+			if (funcInt == 0) for (int i = 1; i < n + 1; i++) cdf[i] = float(i) / float(n);
+			else for (int i = 1; i < n + 1; i++) cdf[i] /= funcInt;
+			return funcInt;
+		};
+		std::vector<float> cFunc(size_t(h) * nc), cCdf(size_t(h) * (nc + 1)), cInt(h), mCdf, tmp;
+		for (int v = 0; v < h; v++) {
+			memcpy(&cFunc[size_t(v) * nc], &img[size_t(v) * w], nc * sizeof(float));
+			cInt[v] = dist1d(&img[size_t(v) * w], nc, tmp);
+			memcpy(&cCdf[size_t(v) * (nc + 1)], tmp.data(), (nc + 1) * sizeof(float));
+		}
+		DEnvDist& o = envDists[e];
+		o.tex = envs[e]; o.w = w; o.h = h; o.nc = nc;
+		o.mInt = dist1d(cInt.data(), h, mCdf);
+		if ((rc = push_alloc(ctx, cFunc.data(), cFunc.size(), &o.cFunc))) return rc;
+		if ((rc = push_alloc(ctx, cCdf.data(), cCdf.size(), &o.cCdf))) return rc;
+		if ((rc = push_alloc(ctx, cInt.data(), cInt.size(), &o.cInt))) return rc;
+		if ((rc = push_alloc(ctx, cInt.data(), cInt.size(), &o.mFunc))) return rc;
+		if ((rc = push_alloc(ctx, mCdf.data(), mCdf.size(), &o.mCdf))) return rc;
 	}
 
 	// ---- volumes -> brick-sparse grids
@@ -553,13 +617,16 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	s.has_medium = hasMedium ? 1 : 0;
 	s.n_mat = int(mats.size());
 	s.n_vol = int(vols.size());
-	for (size_t f = models.size(); f < fold.size(); f++)
+	for (size_t f = models.size(); f < fold.size(); f++) {
 		if (mats[d->primitives[fold[f]].material].directional) s.n_directional++;
+		if (mats[d->primitives[fold[f]].material].infinite) s.n_infinite++;
+	}
 	if ((rc = push_alloc(ctx, insts.data(), insts.size(), &s.inst))) return rc;
 	if ((rc = push_alloc(ctx, mats.data(), mats.size(), &s.mat))) return rc;
 	if ((rc = push_alloc(ctx, texs.data(), texs.size(), &s.tex))) return rc;
 	if ((rc = push_alloc(ctx, vols.data(), vols.size(), &s.vol))) return rc;
 	if ((rc = push_alloc(ctx, meshes.data(), meshes.size(), &s.mesh))) return rc;
+	if ((rc = push_alloc(ctx, envDists.data(), envDists.size(), &s.env))) return rc;
 	ctx->scene = s;
 	ctx->nVolumes = d->n_volumes;
 	ctx->haveScene = true;

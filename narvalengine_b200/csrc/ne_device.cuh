@@ -62,6 +62,54 @@ NE_D V4 material_sample(const DScene& s, int tex, float u, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// InfiniteAreaLight (lights/InfiniteAreaLight.h:20-131) + Distribution1D/2D (utils/Sampling.h:5-112, Q27)
+// ---------------------------------------------------------------------------------------------------------------
+// binarySearch, utils/Math.h:1128-1146 (pbrt FindInterval): last index with cdf[index] <= u, clamped to [0, size-2]
+NE_D int dist_find(const float* cdf, int size, float u) {
+	int first = 0, len = size;
+	while (len > 0) {
+		int half = len >> 1, middle = first + half;
+		if (__ldg(cdf + middle) <= u) { first = middle + 1; len -= half + 1; }
+		else len = half;
+	}
+	return min(max(first - 1, 0), size - 2);
+}
+// Distribution1D::sampleContinuous, utils/Sampling.h:35-52
+NE_D float dist1d_sample(const float* func, const float* cdf, float funcInt, int n, float u, float& pdf, int& off) {
+	off = dist_find(cdf, n + 1, u);
+	float c0 = __ldg(cdf + off), c1 = __ldg(cdf + off + 1);
+	float du = u - c0;
+	if ((c1 - c0) > 0) du /= (c1 - c0);
+	pdf = (funcInt > 0) ? __ldg(func + off) / funcInt : 0.0f;
+	return (float(off) + du) / float(n);
+}
+// Distribution2D::sampleContinuous :96-104: u[1] picks the row, u[0] the column within that row's conditional
+NE_D void env_sample_continuous(const DEnvDist& e, float u0, float u1, float& d0, float& d1, float& pdf) {
+	float p0, p1;
+	int v, dummy;
+	d1 = dist1d_sample(e.mFunc, e.mCdf, e.mInt, e.h, u1, p1, v);
+	d0 = dist1d_sample(e.cFunc + size_t(v) * e.nc, e.cCdf + size_t(v) * (e.nc + 1), __ldg(e.cInt + v), e.nc, u0, p0, dummy);
+	pdf = p0 * p1;
+}
+// InfiniteAreaLight::Le :47-56 for a WCS direction: w = normalize(invM * d), local frame of normal (0,0,1)
+NE_D V3 env_le(const DScene& s, const DEnvDist& e, const float* invM, V3 dW) {
+	V3 w = normalize(xform_dir(invM, dW));
+	V3 normal(0.0f, 0.0f, 1.0f), ss, ts;
+	onb(normal, ss, ts);
+	V3 in = to_lcs(w, normal, ss, ts);
+	float p = atan2f(in.y, in.x);
+	float phi = (p < 0) ? float(double(p) + NE_TWO_PI) : p;
+	float theta = acosf(gclamp(in.z, -1.0f, 1.0f));
+	float su = float(double(phi) * 0.15915494309189533577), sv = float(double(theta) * 0.31830988618379067154);
+	V4 t = tex_sample(s.tex[e.tex], su, sv);
+	return V3(t.x, t.y, t.z);
+}
+NE_D V3 env_le_identity(const DScene& s, const DEnvDist& e, V3 dW) {
+	const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+	return env_le(s, e, I, dW);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Primitives
 // ---------------------------------------------------------------------------------------------------------------
 // AABB::intersect, primitives/AABB.cpp:48-79 (centre/half-size slab; true even when the box is behind the ray;
@@ -271,9 +319,10 @@ NE_D void tri_uv(const DMesh& m, int tri, V3 p, float& u, float& v) {
 NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st) {
 	const DInstance& in = s.inst[i];
 	if (!in.collision) return false;
-	if (in_lights) {  // Model.cpp:429-432: a light whose Le(ray) is not black (directional) is never intersected
+	if (in_lights) {  // Model.cpp:429-432: a light whose Le(ray, identity) is not black (directional, environment) is never intersected
 		const DMaterial& lm = s.mat[in.material];
 		if (lm.directional && !is_black(V3(lm.li[0], lm.li[1], lm.li[2]))) return false;
+		if (lm.infinite && !is_black(env_le_identity(s, s.env[lm.env], rayW.d))) return false;
 	}
 	Ray ray = transform_ray(rayW, in.Mi);
 	bool did = false;

@@ -477,7 +477,25 @@ int process_material(ne_b200_scene_file& S, const JValue& m) {
 		for (int k = 0; k < 3; k++) o.direction[k] = (0.0f - p[k]) / len;  // normalize(vec3(0) - position) :158
 	} else if (type == "infiniteAreaLight") {
 		o.type = NE_B200_MAT_INFINITE;
-		return bad("infiniteAreaLight is not covered by this build (SURVEY 8f rank 3)");
+		std::string path, data, perr;
+		if (!str_of(m.get("path"), path, "path", err)) return bad(err);
+		auto it = S.imageByPath.find(path);
+		if (it != S.imageByPath.end()) o.env_tex = it->second;
+		else {
+			if (!read_file(S.resources + path, data)) return bad("couldn't read the file at " + S.resources + path);
+			int w = 0, h = 0;
+			std::unique_ptr<std::vector<uint8_t>> px(new std::vector<uint8_t>());
+			if (!png_decode(data, w, h, *px, perr)) return bad(path + ": " + perr);
+			ne_b200_texture t{};
+			t.width = w; t.height = h;
+			t.format = NE_B200_TEX_RGBA8;
+			t.wrap_u = t.wrap_v = NE_B200_WRAP_MIRROR;
+			t.texels = px->data();
+			S.bytes.push_back(std::move(px));
+			S.textures.push_back(t);
+			o.env_tex = int(S.textures.size()) - 1;
+			S.imageByPath[path] = o.env_tex;
+		}
 	} else if (type == "volume") {
 		o.type = NE_B200_MAT_VOLUME;
 		std::string phase;

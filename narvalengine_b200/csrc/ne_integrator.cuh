@@ -100,7 +100,28 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	wo.o = isect.p;
 	float lightPdf;
 	V3 Li;
-	if (lm.directional) {
+	if (lm.infinite) {
+		// InfiniteAreaLight::sampleLi, lights/InfiniteAreaLight.h:58-91. vec2(random(), random()): right to left (A.9)
+		const DEnvDist& env = s.env[lm.env];
+		float u1 = rng.next(), u0 = rng.next();
+		float d0, d1, mapPdf;
+		env_sample_continuous(env, u0, u1, d0, d1, mapPdf);
+		wo.d = V3(0.0f);
+		lightPdf = 0;
+		Li = V3(0.0f);
+		if (mapPdf != 0) {
+			float theta = float(double(d1) * NE_PI), phi = float(double(d0) * 2.0 * NE_PI);
+			float cosTheta = cosf(theta), sinTheta = sinf(theta), sinPhi = sinf(phi), cosPhi = cosf(phi);
+			V3 polar(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+			V3 up(0.0f, 1.0f, 0.0f), ss, ts;
+			onb(up, ss, ts);
+			wo.d = to_lcs(polar, up, ss, ts);
+			lightPdf = float(double(mapPdf) / (2.0 * NE_PI * NE_PI * double(sinTheta)));
+			if (sinTheta == 0) lightPdf = 0;
+			V4 t = tex_sample(s.tex[env.tex], d0, d1);
+			Li = V3(t.x, t.y, t.z);
+		}
+	} else if (lm.directional) {
 		// DirectionalLight::sampleLi, lights/DirectionalLight.cpp:13-20: no draws, pdf 1, returns Light::li = 0 (Q23: the
 		// light half is dead; wo.d still feeds the medium's phase evaluation of the BSDF half, Q18)
 		wo.d = -V3(lm.direction[0], lm.direction[1], lm.direction[2]);
@@ -192,10 +213,11 @@ NE_D int classify_hit(const DScene& s, bool did, const Hit& isect, const PathSta
 	}
 	// else at bounce 0 (:249-256): the sum of Light::Le over every light model - 0 for DiffuseLight (lights/Light.h:20-22),
 	// le for DirectionalLight (lights/DirectionalLight.cpp:4-6)
-	else if (ps.bounce == 0 && s.n_directional) {
+	else if (ps.bounce == 0 && (s.n_directional | s.n_infinite)) {
 		for (int i = s.n_models; i < s.n_inst; i++) {
 			const DMaterial& lm = s.mat[s.inst[i].material];
 			if (lm.directional) sink.emit(ps.T * V3(lm.li[0], lm.li[1], lm.li[2]));
+			if (lm.infinite) sink.emit(ps.T * env_le(s, s.env[lm.env], s.inst[i].Mi, ps.ray.d));  // InfiniteAreaLight::Le :47-56
 		}
 	}
 	if (!did || mi < 0 || !s.mat[mi].has_bsdf) return HIT_TERMINATE;

@@ -41,6 +41,8 @@ struct DMaterial {
 	int has_bsdf;     // Material::bsdf != nullptr
 	int transmissive; // bsdf->hasType(BxDF_TRANSMISSION)
 	int has_light, has_medium;
+	int infinite;      // InfiniteAreaLight (lights/InfiniteAreaLight.h): Le / sampleLi from the lat-long map `env`, Li() = 0
+	int env;           // index into DScene::env
 	int directional;   // DirectionalLight (lights/DirectionalLight.cpp): Le = Li() = li, sampleLi returns 0 (Q23); never hit
 	float direction[3];
 	int light_owner;  // fold index of the instance whose primitive Light::primitive points at (Q7: last one built)
@@ -75,6 +77,19 @@ struct DInstance {
 	int desc_index;       // index in the caller's primitive array
 };
 
+// InfiniteAreaLight's Distribution2D (utils/Sampling.h:69-112) over map.g * sin(theta): h conditional distributions of
+// nc = h entries each (Q27: built with n = height, whatever the width) + the marginal over the h rows.
+struct DEnvDist {
+	int tex;              // the lat-long map (DScene::tex)
+	int w, h, nc;
+	const float* cFunc;   // [h][nc]
+	const float* cCdf;    // [h][nc + 1]
+	const float* cInt;    // [h] funcInt of each conditional
+	const float* mFunc;   // [h]
+	const float* mCdf;    // [h + 1]
+	float mInt;
+};
+
 struct DScene {
 	int n_inst;    // fold order: instancedModels..., lights...
 	int n_models;  // first n_models entries are Scene::instancedModels
@@ -85,6 +100,8 @@ struct DScene {
 	const DTexture* tex;
 	const DVolume* vol;
 	const DMesh* mesh;
+	const DEnvDist* env;
+	int n_infinite;  // light instances with an InfiniteAreaLight material
 	int n_directional;  // light instances with a DirectionalLight material (their Le is added to camera rays)
 	int has_medium;  // any instance with a medium material (intersectTr can only return true then, Q12)
 };

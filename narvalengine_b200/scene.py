@@ -102,6 +102,17 @@ class SceneBuilder:
         m.env_tex = -1
         return self._mat(name, m)
 
+    def add_infinite_area_light(self, name, env_image):
+        """infiniteAreaLight material (SceneReader.cpp:169-186): a lat-long RGBA8 map loaded like any image texture
+        (mirror wrap, nearest texel)."""
+        img = np.asarray(env_image, dtype=np.uint8)
+        m = abi.Material()
+        m.type = abi.MAT_INFINITE
+        m.env_tex = self.add_texture(img, abi.TEX_RGBA8, img.shape[1], img.shape[0], abi.WRAP_MIRROR)
+        m.albedo_tex = m.roughness_tex = m.metallic_tex = m.normal_tex = -1
+        m.volume = -1
+        return self._mat(name, m)
+
     def add_directional(self, name, le, position):
         """directionalLight material (SceneReader.cpp:156-168): le = albedo, direction = normalize(-position)."""
         m = abi.Material()

@@ -47,6 +47,7 @@
 #include "primitives/Model.h"
 #include "primitives/InstancedModel.h"
 #include "materials/HomogeneousMedia.h"
+#include "lights/InfiniteAreaLight.h"  // uses Sphere without including it
 
 #include "ne_b200.h"
 
@@ -171,6 +172,13 @@ Material* buildMaterial(RefScene& rs, const ne_b200_material& m, const std::stri
 		DiffuseLight* l = new DiffuseLight();
 		l->li = v3(m.li);
 		mat->light = l;
+	} else if (m.type == NE_B200_MAT_INFINITE) {
+		// SceneReader.cpp:169-186
+		Texture* tex = rs.textures[m.env_tex];
+		tex->textureName = TEX_1;
+		InfiniteAreaLight* l = new InfiniteAreaLight(tex);
+		mat->light = l;
+		mat->addTexture(TEX_1, tex);
 	} else if (m.type == NE_B200_MAT_DIRECTIONAL) {
 		// SceneReader.cpp:156-168: only `le` and `direction` are set (li stays 0, Q23)
 		DirectionalLight* l = new DirectionalLight();

@@ -239,3 +239,24 @@ def directional_scene(transform_fn=None, res=(20, 16, 24)):
 
 
 DIRECTIONAL_CAMERA = CameraParams((0, 2, -5), (0, 1, 0), 45.0)
+
+
+def environment_scene(transform_fn=None, res=(16, 12, 20)):
+    """An `infiniteAreaLight` lat-long map carried by a big sphere (the reference casts its primitive to Sphere,
+    InfiniteAreaLight.h:95) over a floor, a cloud and a small area light."""
+    b = SceneBuilder(transform_fn)
+    rng = np.random.default_rng(17)
+    env = rng.integers(40, 256, (8, 16, 4), dtype=np.uint8)  # no black texel: Le never is, so the sphere is never hit
+    vol = b.add_volume_dense(cloud_density(res, seed=9))
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 15.0, vol, "hg", 0.0)
+    b.add_microfacet("floor", (.8, .8, .8), 0.95, 0.0)
+    b.add_infinite_area_light("sky", env)
+    b.add_emitter("light", (150, 150, 140))
+    b.add_volume("cloud", (0.5, 1.2, 0), (0, 10, 0), (1.8, 1.4, 1.8))
+    b.add_rectangle("floor", (0, 0, 0), (90, 0, 0), (8, 8, 1))
+    b.add_sphere("sky", (0, 0, 0), 40.0)
+    b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
+    return b
+
+
+ENVIRONMENT_CAMERA = CameraParams((0, 2, -5), (0, 1, 0), 45.0)

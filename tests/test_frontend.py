@@ -176,6 +176,22 @@ def test_directional_light_material(lib):
     sf.close()
 
 
+def test_infinite_area_light_material(lib, resources):
+    """SceneReader.cpp:169-186: the map is loaded like any image texture (RGBA8, mirror)."""
+    root, img, _ = resources
+    s = {"version": "1", "materials": [{"name": "sky", "type": "infiniteAreaLight", "path": "imgs/check.png"}],
+         "primitives": [{"name": "s", "type": "sphere", "radius": 30, "materialName": "sky", "transform": {"position": [0, 0, 0]}}],
+         "camera": SCENE["camera"], "renderer": SCENE["renderer"]}
+    sf = SceneFile(text=json.dumps(s), resources_dir=str(root))
+    d = sf.desc()
+    m = d.materials[0]
+    assert m.type == abi.MAT_INFINITE and m.env_tex == 0
+    a, wrap = tex_value(d, m.env_tex)
+    assert np.array_equal(a, img) and wrap == (abi.WRAP_MIRROR, abi.WRAP_MIRROR)
+    assert d.primitives[0].type == abi.PRIM_SPHERE and d.primitives[0].radius == 30
+    sf.close()
+
+
 def test_vol_reader_follows_the_reference_token_rules(lib, tmp_path):
     """ResourceManager.cpp:222-286: only space-terminated tokens count; line 2 is discarded; a value glued to a newline
     is dropped (std::stof stops at the newline); a last token without a trailing space is not captured."""

@@ -442,3 +442,18 @@ def test_li_tape_directional_light(ctx, oracle):
     assert same.mean() > 0.97, f"Li(directional) draw-count agreement {same.mean()}"
     assert_close(L[same], rL[same], what="Li directional", rtol=2e-4, atol=1e-5, frac=0.99)
     assert (rL.min(axis=1) >= 0.4 - 1e-6).mean() > 0.9  # nearly every camera ray carries the sun's Le
+
+
+def test_li_tape_infinite_area_light(ctx, oracle):
+    """InfiniteAreaLight + Distribution1D/2D (lights/InfiniteAreaLight.h, utils/Sampling.h incl. Q27): Le on camera rays,
+    importance-sampled light half, never-hit carrier sphere - whole Li paths draw for draw against the reference."""
+    b = scenes.environment_scene()
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    cam_o, cam_d = oracle.camera_rays(scenes.ENVIRONMENT_CAMERA, 1.0, 7, np.random.default_rng(4).uniform(0, 1, (2000, 2)))
+    seeds = np.arange(len(cam_o), dtype=np.uint32) + 90000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, cam_o, cam_d, 6, seeds, stride=16384)
+    same = used == rused
+    assert same.mean() > 0.97, f"Li(environment) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li environment", rtol=2e-4, atol=1e-5, frac=0.99)
+    assert (rused > 0).mean() > 0.3 and rL.mean() > 0.5

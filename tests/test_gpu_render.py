@@ -37,6 +37,7 @@ CASES = {
     "mixed": (scenes.mixed_scene, scenes.MIXED_CAMERA),
     "mesh": (lambda: scenes.mesh_scene(n=64), scenes.MESH_CAMERA),
     "directional": (scenes.directional_scene, scenes.DIRECTIONAL_CAMERA),
+    "environment": (scenes.environment_scene, scenes.ENVIRONMENT_CAMERA),
 }
 
 
