@@ -437,7 +437,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 		case NE_B200_MAT_EMITTER: o.has_light = 1; break;
 		case NE_B200_MAT_VOLUME:
 			o.has_bsdf = 1; o.transmissive = 1; o.has_medium = 1;
-			if (m.volume < 0) { set_error("HomogeneousMedia (volume material without a grid) is not covered yet (SURVEY 8f rank 3)"); return NE_B200_ERR_UNSUPPORTED; }
+			// volume < 0: HomogeneousMedia (SceneReader.cpp:208-210, materials/HomogeneousMedia.cpp)
 			if (m.volume >= d->n_volumes) { set_error("material volume index out of range"); return NE_B200_ERR_INVALID; }
 			break;
 		case NE_B200_MAT_DIRECTIONAL:  // SceneReader.cpp:156-168: le = albedo (in `li` here), direction = normalize(-position)

@@ -351,7 +351,7 @@ NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float t
 			hit.prim = tri;
 			did = true;
 		}
-	} else if (in.type == PRIM_VOLUME && !in_lights) {
+	} else if (in.type == PRIM_VOLUME && !in_lights && s.mat[in.material].volume >= 0) {
 		// GridMedia special case, Model.cpp:394-413: ignores tMin/tMax (Q4)
 		float tn, tf; V3 nn, hp;
 		aabb_intersect(V3(-0.5f, -0.5f, -0.5f), V3(0.5f, 0.5f, 0.5f), ray, tn, tf, nn, hp);
@@ -366,9 +366,17 @@ NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float t
 			tMax = a;
 			did = true;
 		}
-	} else if (in.type == PRIM_RECTANGLE || in.type == PRIM_SPHERE) {
+	} else if (in.type == PRIM_RECTANGLE || in.type == PRIM_SPHERE || (in.type == PRIM_VOLUME && !in_lights)) {
 		Hit tmp;
-		bool local = in.type == PRIM_RECTANGLE ? rect_intersect(ray, tmp) : sphere_intersect(ray, in.radius, tmp);
+		bool local;
+		if (in.type == PRIM_VOLUME) {
+			// the proxy AABB of a HomogeneousMedia is an ordinary primitive (the dynamic_cast<GridMedia*> at Model.cpp:395 fails)
+			local = aabb_intersect(V3(-0.5f, -0.5f, -0.5f), V3(0.5f, 0.5f, 0.5f), ray, tmp.tNear, tmp.tFar, tmp.n, tmp.p);
+			tmp.u = tmp.v = 0;
+			tmp.prim = 0;
+		} else {
+			local = in.type == PRIM_RECTANGLE ? rect_intersect(ray, tmp) : sphere_intersect(ray, in.radius, tmp);
+		}
 		if (local && !in_lights && tmp.tNear != tmp.tFar && tmp.tNear < 0 && tmp.tFar > 0) {
 			// "inside" case, Model.cpp:418-424 (Q14): hit at t=0, normal left as computed at the negative root
 			tmp.tNear = 0;

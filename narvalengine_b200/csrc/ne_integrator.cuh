@@ -36,9 +36,16 @@ NE_D float visibility_tr(const DScene& s, V3 p, V3 lightPoint, R& rng, Stats& st
 }
 
 // intersectTr :10-32 — marches THROUGH non-medium surfaces until a medium (true, Tr) or nothing (false) (Q12).
+// HomogeneousMedia::Tr(ray, hit) = Tr(tFar - tNear) = exp(-extinction * distance * density), materials/HomogeneousMedia.cpp:15-22
+NE_D V3 homog_tr(const DMaterial& m, float distance) {
+	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+	V3 v = ext * distance * m.density_mult;
+	return V3(expf(-v.x), expf(-v.y), expf(-v.z));
+}
+
 template <class R, bool FAITHFUL, bool BRICKMAJ>
-NE_D bool intersect_tr(const DScene& s, Ray ray, float& Tr, R& rng, Stats& st) {
-	Tr = 1.0f;
+NE_D bool intersect_tr(const DScene& s, Ray ray, V3& Tr, R& rng, Stats& st) {
+	Tr = V3(1.0f);
 	if (!FAITHFUL && !s.has_medium) return false;  // can only return true through a medium
 	for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
 		Hit h;
@@ -52,7 +59,11 @@ NE_D bool intersect_tr(const DScene& s, Ray ray, float& Tr, R& rng, Stats& st) {
 				h.tFar -= h.tNear;
 				h.tNear = 0;
 			}
-			Tr *= grid_tr<R, BRICKMAJ>(s.inst[h.inst], s.mat[mi], s.vol[s.mat[mi].volume], ray, h.tNear, h.tFar, rng, st);
+			Tr = Tr * V3(grid_tr<R, BRICKMAJ>(s.inst[h.inst], s.mat[mi], s.vol[s.mat[mi].volume], ray, h.tNear, h.tFar, rng, st));
+			return true;
+		}
+		if (mi >= 0 && s.mat[mi].has_medium) {  // HomogeneousMedia
+			Tr = Tr * homog_tr(s.mat[mi], h.tFar - h.tNear);
 			return true;
 		}
 		ray.o = h.p;
@@ -76,11 +87,11 @@ struct ImmediateSink {
 	}
 	// BSDF half :132-153: Ld += f * Li * Tr * weight / scatteringPdf when intersectTr finds a medium
 	NE_D void bsdf_term(const DScene& s, Ray ray, V3 f, V3 Li, float weight, float pdf, R& rng, uint32_t stream, Stats& st) {
-		float Tr;
+		V3 Tr;
 		Fork<R> fork(rng, stream);
 		bool found = intersect_tr<R, FAITHFUL, BRICKMAJ>(s, ray, Tr, fork.get(), st);
 		V3 Li2 = found ? Li : V3(0.0f);
-		if (!is_black(Li2)) Ld = Ld + f * Li2 * V3(Tr) * weight / pdf;
+		if (!is_black(Li2)) Ld = Ld + f * Li2 * Tr * weight / pdf;
 	}
 	// uniformSampleOneLight's return value (Ld / lightSelectionPdf), added by the caller as L += T * value
 	NE_D V3 end(float selPdf) { return Ld / selPdf; }
@@ -237,6 +248,8 @@ NE_D int volume_escape(PathState& ps, const Hit& isect) {
 	if (++ps.guard > NE_MAX_NULL_SEGMENTS) return PATH_DONE;
 	return PATH_SAME_BOUNCE;
 }
+template <class R, class SINK>
+NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray scattered, V3 a, R& rng, SINK& sink, Stats& st);
 // (2b) :215-236 real collision at parameter t of the OCS ray `rayO`.
 template <class R, class SINK>
 NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const Ray& rayO, float t, R& rng, SINK& sink, Stats& st) {
@@ -246,7 +259,13 @@ NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const 
 	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
 	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
 	V3 a = sc / ext;
-	if (all_one(a)) return volume_escape(ps, isect);  // Q1b: albedo exactly 1 is mistaken for an escape
+	return volume_collision(s, ps, isect, scattered, a, rng, sink, st);
+}
+// Li :209-236 once the medium has answered with `a` and `scattered`.
+template <class R, class SINK>
+NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray scattered, V3 a, R& rng, SINK& sink, Stats& st) {
+	const DMaterial& m = s.mat[s.inst[isect.inst].material];
+	if (all_one(a)) return volume_escape(ps, isect);  // Q1 / Q1b: an escape is recognised by the value (1,1,1)
 	ps.T = ps.T * a;
 	V3 phaseFr = bsdf_eval(s, m, ps.ray.d, scattered.d, isect);
 	float phasePdf = bsdf_pdf(s, m, ps.ray.d, scattered.d, isect.n, isect);
@@ -259,11 +278,42 @@ NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const 
 	ps.ray = scattered;
 	return PATH_NEXT_BOUNCE;
 }
+// The volume branch for a HomogeneousMedia (materials/HomogeneousMedia.cpp:24-51): closed-form free flight in WCS
+// (no OCS transform), `t` divided by the segment length (sic), phase sample about the proxy box's hit normal; the
+// escape value Tr / avg(Tr) is (1,1,1) only when the rounding of (x+x+x)/3 allows it - otherwise Li treats the
+// escape as a collision that keeps its direction.
+template <class R, class SINK>
+NE_D int shade_volume_homog(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& sink, Stats& st) {
+	const DMaterial& m = s.mat[s.inst[isect.inst].material];
+	volume_enter(ps, isect);
+	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
+	float t = -logf(1 - rng.next()) / avg(ext);
+	float dist = isect.tFar - isect.tNear;
+	t = t / dist;
+	bool sampled = t < dist;
+	Ray scattered;
+	if (sampled) {
+		st.scatter_events++;
+		scattered.o = ps.ray.at(t);
+		scattered.d = bsdf_sample(s, m, ps.ray.d, isect.n, isect, rng);
+	} else {
+		scattered.o = ps.ray.at(dist + 0.001f);
+		scattered.d = ps.ray.d;
+	}
+	V3 Tr = homog_tr(m, t);
+	V3 density = sampled ? (ext * Tr) : Tr;
+	float pdf = avg(density);
+	if (pdf == 0) pdf = 1;
+	V3 a = sampled ? (Tr * sc / pdf) : Tr / pdf;
+	return volume_collision(s, ps, isect, scattered, a, rng, sink, st);
+}
 // The whole volume branch in one go (one thread per path).
 template <class R, bool BRICKMAJ, class SINK>
 NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& sink, Stats& st) {
 	const DInstance& in = s.inst[isect.inst];
 	const DMaterial& m = s.mat[in.material];
+	if (m.volume < 0) return shade_volume_homog(s, ps, isect, rng, sink, st);
 	const DVolume& v = s.vol[m.volume];
 	volume_enter(ps, isect);
 	Ray rayO = transform_ray(ps.ray, in.Mi);

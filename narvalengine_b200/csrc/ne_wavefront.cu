@@ -311,8 +311,11 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
 		} else {
 			store_hit(b, slot, h);
-			if (kind == HIT_VOLUME) b.qVol[warp_push(&b.c->vol)] = slot;
-			else b.qSurf[warp_push(&b.c->surf)] = slot;
+			if (kind == HIT_VOLUME) {
+				// a grid medium is walked by k_wf_track; a HomogeneousMedia needs no walk and goes straight to k_wf_scatter
+				if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[warp_push(&b.c->vol)] = slot;
+				else b.qScat[warp_push(&b.c->scat)] = slot;
+			} else b.qSurf[warp_push(&b.c->surf)] = slot;
 		}
 	}
 	flush_stats_wf(st, P.counters);
@@ -472,8 +475,13 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 		sink.accum = P.accum;
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
-		Ray rayO = transform_ray(r.ps.ray, S.inst[h.inst].Mi);
-		int next = volume_scatter(S, r.ps, h, rayO, r.tHit, rng, sink, st);
+		int next;
+		if (S.mat[S.inst[h.inst].material].volume < 0) {
+			next = shade_volume_homog(S, r.ps, h, rng, sink, st);
+		} else {
+			Ray rayO = transform_ray(r.ps.ray, S.inst[h.inst].Mi);
+			next = volume_scatter(S, r.ps, h, rayO, r.tHit, rng, sink, st);
+		}
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
 		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
@@ -556,6 +564,11 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 				ray.o = ray.at(hh.tNear);
 				tRemain = hh.tFar - hh.tNear;
 				break;
+			}
+			if (mi >= 0 && S.mat[mi].has_medium) {  // HomogeneousMedia: closed-form transmittance, nothing to walk
+				float4 C = b.tC[i];
+				splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * homog_tr(S.mat[mi], hh.tFar - hh.tNear));
+				break;  // inst stays -2: the request is done
 			}
 			ray.o = hh.p;
 		}

@@ -260,3 +260,20 @@ def environment_scene(transform_fn=None, res=(16, 12, 20)):
 
 
 ENVIRONMENT_CAMERA = CameraParams((0, 2, -5), (0, 1, 0), 45.0)
+
+
+def homogeneous_scene(transform_fn=None, grey=True):
+    """A HomogeneousMedia box (volume material without a grid, materials/HomogeneousMedia.cpp) over a floor with an area
+    light. (The reference's own SceneReader cannot build this - DESIGN.md §8 - but its integrator handles it.)"""
+    b = SceneBuilder(transform_fn)
+    sc = (1.1, 1.1, 1.1) if grey else (1.2, 0.9, 0.6)
+    b.add_volume_material("fog", sc, (.01, .01, .01), 1.5, -1, "hg", 0.3)
+    b.add_microfacet("floor", (.8, .8, .8), 0.95, 0.0)
+    b.add_emitter("light", (200, 200, 180))
+    b.add_volume("fog", (0.2, 1.1, 0.3), (0, 25, 0), (1.6, 1.2, 1.4))
+    b.add_rectangle("floor", (0, 0, 0), (90, 0, 0), (8, 8, 1))
+    b.add_rectangle("light", (0, 3.9, 0), (-89, 0, 0), (1, 1, 1))
+    return b
+
+
+HOMOGENEOUS_CAMERA = CameraParams((0, 2, -5), (0, 1, 0), 45.0)

@@ -457,3 +457,19 @@ def test_li_tape_infinite_area_light(ctx, oracle):
     assert same.mean() > 0.97, f"Li(environment) draw-count agreement {same.mean()}"
     assert_close(L[same], rL[same], what="Li environment", rtol=2e-4, atol=1e-5, frac=0.99)
     assert (rused > 0).mean() > 0.3 and rL.mean() > 0.5
+
+
+@pytest.mark.parametrize("grey", [True, False])
+def test_li_tape_homogeneous_media(ctx, oracle, grey):
+    """HomogeneousMedia (materials/HomogeneousMedia.cpp:15-51): closed-form sample with its t / distance quirk, the
+    rounding-dependent escape detection, vec3 transmittance through intersectTr - whole Li paths draw for draw."""
+    b = scenes.homogeneous_scene(grey=grey)
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    cam_o, cam_d = oracle.camera_rays(scenes.HOMOGENEOUS_CAMERA, 1.0, 7, np.random.default_rng(6).uniform(0, 1, (2000, 2)))
+    seeds = np.arange(len(cam_o), dtype=np.uint32) + 110000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, cam_o, cam_d, 6, seeds, stride=16384)
+    same = used == rused
+    assert same.mean() > 0.97, f"Li(homogeneous) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li homogeneous", rtol=2e-4, atol=1e-5, frac=0.99)
+    assert (rused > 0).mean() > 0.2

@@ -38,6 +38,7 @@ CASES = {
     "mesh": (lambda: scenes.mesh_scene(n=64), scenes.MESH_CAMERA),
     "directional": (scenes.directional_scene, scenes.DIRECTIONAL_CAMERA),
     "environment": (scenes.environment_scene, scenes.ENVIRONMENT_CAMERA),
+    "homogeneous": (scenes.homogeneous_scene, scenes.HOMOGENEOUS_CAMERA),
 }
 
 
