@@ -198,7 +198,9 @@ typedef struct ne_b200_render_settings {
  * processCameraAndRenderer :650-675, ResourceManager::loadVolasTexture (.vol, ResourceManager.cpp:222-286) and
  * loadTexture (PNG -> RGBA8, mirror wrap, :288-315). `resources_dir` is the reference's RESOURCES_DIR: asset paths in
  * the JSON are relative to it. The object owns every array its descriptor points to.
- * Not covered: .vdb (needs OpenVDB: pass leaf bricks through ne_b200_volume) and gltf -> error. */
+ * `gltf` primitives: glTF 2.0 .gltf (external or base64 buffers) and .glb, triangle primitives of the node tree in
+ * depth-first order without node transforms (what Model::processNode keeps, Model.cpp:323-335).
+ * Not covered: .vdb (needs OpenVDB: pass leaf bricks through ne_b200_volume) -> error. */
 typedef struct ne_b200_scene_file ne_b200_scene_file;
 int ne_b200_scene_file_load(const char* json_path, const char* resources_dir, ne_b200_scene_file** out);
 int ne_b200_scene_file_parse(const char* json_text, const char* resources_dir, ne_b200_scene_file** out);

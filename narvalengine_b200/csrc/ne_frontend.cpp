@@ -2,7 +2,7 @@
 // core/ResourceManager.cpp:165-315 do for the reference, producing the POD ne_b200_scene_desc the backend uploads.
 // Pure host code with no third-party dependency except zlib (PNG): its own JSON reader (the reference uses rapidjson),
 // `.vol` reader/writer (ResourceManager::loadVolasTexture :222-286, incl. its space-terminated-token parser), OBJ reader
-// (the reference goes through assimp with Triangulate | FlipUVs and NO vertex joining, ResourceManager.cpp:59: one
+// and glTF 2.0 / .glb reader (the reference goes through assimp with Triangulate | FlipUVs and NO vertex joining, ResourceManager.cpp:59: one
 // vertex per face corner, so a triangle's three vertices are consecutive - which is what Triangle::samplePointOnTexture
 // assumes, Q30), PNG reader (stbi_load(..., STBI_rgb_alpha), ResourceManager.cpp:288-315) and the framebuffer
 // consumers (§8f rank 2): PNG / EXR as materials/Texture.h:44-75 saveImage writes them, and OfflineEngine::coreLoop's
@@ -360,6 +360,160 @@ int obj_parse(const std::string& text, std::vector<float>& pos, std::vector<floa
 	return NE_B200_OK;
 }
 
+// glTF 2.0 (.gltf with external / base64 buffers, or .glb): what the reference gets from assimp for a `gltf` primitive and
+// Model::processNode keeps of it (primitives/Model.cpp:323-335): the meshes of the node tree in depth-first order, one
+// after the other, WITHOUT the nodes' transforms; triangles only; indexed vertices as stored; V flipped (aiProcess_FlipUVs).
+bool base64_decode(const std::string& in, std::string& out) {
+	static int8_t T[256];
+	static bool init = false;
+	if (!init) {
+		for (int i = 0; i < 256; i++) T[i] = -1;
+		const char* a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+		for (int i = 0; i < 64; i++) T[uint8_t(a[i])] = int8_t(i);
+		init = true;
+	}
+	uint32_t acc = 0;
+	int bits = 0;
+	for (char c : in) {
+		if (c == '=' || c == '\n' || c == '\r') continue;
+		int v = T[uint8_t(c)];
+		if (v < 0) return false;
+		acc = (acc << 6) | uint32_t(v);
+		bits += 6;
+		if (bits >= 8) { bits -= 8; out += char((acc >> bits) & 0xFF); }
+	}
+	return true;
+}
+
+int gltf_parse(const std::string& file, const std::string& dir, std::vector<float>& pos, std::vector<float>& uv, std::vector<uint32_t>& idx, bool& hasUv) {
+	auto bad = [&](const std::string& e) { set_error("gltf: " + e); return NE_B200_ERR_INVALID; };
+	std::string json = file, glbBin;
+	if (file.size() >= 20 && !memcmp(file.data(), "glTF", 4)) {  // .glb: 12-byte header, JSON chunk, optional BIN chunk
+		auto le32 = [&](size_t o) { uint32_t v; memcpy(&v, file.data() + o, 4); return v; };
+		size_t o = 12;
+		json.clear();
+		while (o + 8 <= file.size()) {
+			uint32_t len = le32(o), type = le32(o + 4);
+			if (o + 8 + size_t(len) > file.size()) return bad("truncated glb chunk");
+			if (type == 0x4E4F534A) json.assign(file.data() + o + 8, len);
+			else if (type == 0x004E4942) glbBin.assign(file.data() + o + 8, len);
+			o += 8 + size_t(len);
+		}
+	}
+	JParser jp{json.c_str(), json.c_str() + json.size(), ""};
+	JValue doc;
+	if (!jp.parse(doc) || doc.kind != JValue::Object) return bad("malformatted json: " + jp.err);
+	auto arr = [&](const char* k) -> const std::vector<JValue>* { const JValue* v = doc.get(k); return (v && v->kind == JValue::Array) ? &v->arr : nullptr; };
+	const auto* buffers = arr("buffers");
+	const auto* views = arr("bufferViews");
+	const auto* accessors = arr("accessors");
+	const auto* meshes = arr("meshes");
+	const auto* nodes = arr("nodes");
+	if (!buffers || !views || !accessors || !meshes) return bad("missing buffers / bufferViews / accessors / meshes");
+	std::vector<std::string> data(buffers->size());
+	for (size_t i = 0; i < buffers->size(); i++) {
+		const JValue* uri = (*buffers)[i].get("uri");
+		if (!uri) { data[i] = glbBin; continue; }
+		if (uri->str.compare(0, 5, "data:") == 0) {
+			size_t c = uri->str.find("base64,");
+			if (c == std::string::npos || !base64_decode(uri->str.substr(c + 7), data[i])) return bad("bad data: URI");
+		} else if (!read_file(dir + uri->str, data[i])) return bad("couldn't read the file at " + dir + uri->str);
+	}
+	auto num = [](const JValue& o, const char* k, double dflt) { const JValue* v = o.get(k); return (v && v->kind == JValue::Number) ? v->num : dflt; };
+	struct View { const uint8_t* p; size_t stride, count; int comp, n; bool normalized; };
+	auto view_of = [&](int ai, View& out) -> bool {
+		if (ai < 0 || size_t(ai) >= accessors->size()) return false;
+		const JValue& a = (*accessors)[ai];
+		int bv = int(num(a, "bufferView", -1));
+		if (bv < 0 || size_t(bv) >= views->size()) return false;
+		const JValue& v = (*views)[bv];
+		int buf = int(num(v, "buffer", -1));
+		if (buf < 0 || size_t(buf) >= data.size()) return false;
+		const JValue* type = a.get("type");
+		if (!type) return false;
+		out.n = type->str == "SCALAR" ? 1 : type->str == "VEC2" ? 2 : type->str == "VEC3" ? 3 : type->str == "VEC4" ? 4 : 0;
+		out.comp = int(num(a, "componentType", 0));
+		size_t cs = out.comp == 5126 || out.comp == 5125 ? 4 : (out.comp == 5123 || out.comp == 5122) ? 2 : (out.comp == 5121 || out.comp == 5120) ? 1 : 0;
+		if (!out.n || !cs) return false;
+		out.count = size_t(num(a, "count", 0));
+		out.stride = size_t(num(v, "byteStride", 0));
+		if (!out.stride) out.stride = cs * out.n;
+		const JValue* nz = a.get("normalized");
+		out.normalized = nz && nz->kind == JValue::Bool && nz->b;
+		size_t off = size_t(num(v, "byteOffset", 0)) + size_t(num(a, "byteOffset", 0));
+		if (out.count && off + (out.count - 1) * out.stride + cs * out.n > data[buf].size()) return false;
+		out.p = reinterpret_cast<const uint8_t*>(data[buf].data()) + off;
+		return true;
+	};
+	auto fetch = [](const View& v, size_t i, int c) -> double {
+		const uint8_t* q = v.p + i * v.stride;
+		switch (v.comp) {
+		case 5126: { float f; memcpy(&f, q + 4 * c, 4); return f; }
+		case 5125: { uint32_t u; memcpy(&u, q + 4 * c, 4); return u; }
+		case 5123: { uint16_t u; memcpy(&u, q + 2 * c, 2); return v.normalized ? u / 65535.0 : u; }
+		case 5121: return v.normalized ? q[c] / 255.0 : q[c];
+		default: return 0;
+		}
+	};
+	hasUv = false;
+	auto add_mesh = [&](int mi) -> int {
+		if (mi < 0 || size_t(mi) >= meshes->size()) return bad("mesh index out of range");
+		const JValue* prims = (*meshes)[mi].get("primitives");
+		if (!prims || prims->kind != JValue::Array) return NE_B200_OK;
+		for (const JValue& pr : prims->arr) {
+			if (int(num(pr, "mode", 4)) != 4) continue;  // triangles only
+			const JValue* at = pr.get("attributes");
+			if (!at) continue;
+			View vp, vt, vi;
+			if (!view_of(int(num(*at, "POSITION", -1)), vp) || vp.n != 3 || vp.comp != 5126) return bad("bad POSITION accessor");
+			bool uvOk = at->has("TEXCOORD_0") && view_of(int(num(*at, "TEXCOORD_0", -1)), vt) && vt.n == 2;
+			const uint32_t base = uint32_t(pos.size() / 3);
+			for (size_t i = 0; i < vp.count; i++) {
+				for (int c = 0; c < 3; c++) pos.push_back(float(fetch(vp, i, c)));
+				if (uvOk && i < vt.count) { uv.push_back(float(fetch(vt, i, 0))); uv.push_back(1.0f - float(fetch(vt, i, 1))); hasUv = true; }
+				else { uv.push_back(0.0f); uv.push_back(0.0f); }
+			}
+			if (pr.has("indices")) {
+				if (!view_of(int(num(pr, "indices", -1)), vi) || vi.n != 1) return bad("bad indices accessor");
+				for (size_t i = 0; i + 2 < vi.count; i += 3)
+					for (int k = 0; k < 3; k++) {
+						uint32_t ix = uint32_t(fetch(vi, i + k, 0));
+						if (ix >= vp.count) return bad("index out of range");
+						idx.push_back(base + ix);
+					}
+			} else {
+				for (size_t i = 0; i + 2 < vp.count; i += 3)
+					for (int k = 0; k < 3; k++) idx.push_back(base + uint32_t(i + k));
+			}
+		}
+		return NE_B200_OK;
+	};
+	// depth-first over the scene's node tree, like Model::processNode
+	std::vector<int> stack;
+	const auto* scenesArr = arr("scenes");
+	if (nodes && scenesArr && !scenesArr->empty()) {
+		size_t si = size_t(num(doc, "scene", 0));
+		if (si >= scenesArr->size()) si = 0;
+		const JValue* roots = (*scenesArr)[si].get("nodes");
+		if (roots && roots->kind == JValue::Array)
+			for (size_t i = roots->arr.size(); i-- > 0;) stack.push_back(int(roots->arr[i].num));
+	} else if (!nodes) {
+		for (size_t m = 0; m < meshes->size(); m++) { int rc = add_mesh(int(m)); if (rc) return rc; }
+	}
+	size_t visited = 0;
+	while (!stack.empty()) {
+		int ni = stack.back();
+		stack.pop_back();
+		if (ni < 0 || size_t(ni) >= nodes->size() || ++visited > 100000) return bad("bad node graph");
+		const JValue& n = (*nodes)[ni];
+		if (n.has("mesh")) { int rc = add_mesh(int(num(n, "mesh", -1))); if (rc) return rc; }
+		const JValue* ch = n.get("children");
+		if (ch && ch->kind == JValue::Array)
+			for (size_t i = ch->arr.size(); i-- > 0;) stack.push_back(int(ch->arr[i].num));
+	}
+	return NE_B200_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -566,7 +720,6 @@ int process_primitive(ne_b200_scene_file& S, const JValue& p) {
 	bool needRS = type != "sphere";
 	if (needRS && (!vec3_of(tr->get("scale"), scale, "transform.scale", err) || !vec3_of(tr->get("rotation"), rot, "transform.rotation", err))) return bad(err);
 	if (type == "obj" || type == "gltf") {
-		if (type == "gltf") { set_error("primitive " + name + ": gltf import is not covered by this build (use obj)"); return NE_B200_ERR_UNSUPPORTED; }
 		o.type = NE_B200_PRIM_MESH;
 		o.material = material(false);
 		if (o.material == -2) return bad("unknown materialName");
@@ -576,7 +729,10 @@ int process_primitive(ne_b200_scene_file& S, const JValue& p) {
 		std::vector<float> vp, vuv;
 		std::unique_ptr<std::vector<uint32_t>> idx(new std::vector<uint32_t>());
 		bool hasUv = false;
-		int rc = obj_parse(text, vp, vuv, *idx, hasUv);
+		bool gltf = type == "gltf" || (text.size() >= 4 && !memcmp(text.data(), "glTF", 4));
+		size_t slash = path.find_last_of('/');
+		int rc = gltf ? gltf_parse(text, S.resources + (slash == std::string::npos ? "" : path.substr(0, slash + 1)), vp, vuv, *idx, hasUv)
+		              : obj_parse(text, vp, vuv, *idx, hasUv);
 		if (rc) return rc;
 		o.n_vertices = int32_t(vp.size() / 3);
 		o.n_triangles = int32_t(idx->size() / 3);

@@ -1,5 +1,5 @@
 """Generates the committed golden fixtures from the ORACLE (the reference's own code, oracle/_ref). Run where
-/root/reference exists:  python tests/golden/make_golden.py [images]
+/root/reference exists:  python tests/golden/make_golden.py [case ...]
   image_<case>.npz : two independent converged oracle renders (different mt seeds per thread) of the test_gpu_render
                      cases at equal spp -> parity target + oracle-vs-oracle noise floor.
 """
@@ -15,14 +15,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import scenes  # noqa: E402
 from refclient import RefOracle  # noqa: E402
 
-SIZES = {"cornell": (24, 16, 65536), "volume": (24, 16, 65536), "mixed": (16, 12, 131072), "mesh": (24, 16, 32768)}
+SIZES = {"cornell": (24, 16, 65536), "volume": (24, 16, 65536), "mixed": (16, 12, 131072), "mesh": (24, 16, 32768),
+         "directional": (24, 16, 32768), "environment": (24, 16, 32768), "homogeneous": (24, 16, 32768)}
 
 
 def main():
     from test_gpu_render import CASES
     o = RefOracle()
     nthreads = os.cpu_count() or 1
+    only = [a for a in sys.argv[1:] if a in CASES]
     for name, (mk, cam) in CASES.items():
+        if only and name not in only:
+            continue
         W, H, spp = SIZES[name]
         sc = o.scene(mk(o.transform_fn()) if name in ("cornell", "mixed") and False else mk())
         t = time.time()

@@ -222,12 +222,12 @@ def cornell_c1(transform_fn=None):
     return b
 
 
-def directional_scene(transform_fn=None, res=(20, 16, 24)):
+def directional_scene(transform_fn=None, res=(20, 16, 24), g=0.2):
     """A `directionalLight` sun (carried by a point primitive) over a cloud and a floor, plus a small area light: the sun
     reaches the image only through Light::Le on camera rays and through the BSDF half of estimateDirect (Q23, Q12)."""
     b = SceneBuilder(transform_fn)
     vol = b.add_volume_dense(cloud_density(res, seed=5))
-    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 20.0, vol, "hg", 0.2)
+    b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 20.0, vol, "hg", g)
     b.add_microfacet("floor", (.8, .8, .8), 0.95, 0.0)
     b.add_directional("sun", (0.6, 0.5, 0.4), (3, 5, -2))
     b.add_emitter("light", (200, 200, 180))
@@ -262,12 +262,12 @@ def environment_scene(transform_fn=None, res=(16, 12, 20)):
 ENVIRONMENT_CAMERA = CameraParams((0, 2, -5), (0, 1, 0), 45.0)
 
 
-def homogeneous_scene(transform_fn=None, grey=True):
+def homogeneous_scene(transform_fn=None, grey=True, g=0.3):
     """A HomogeneousMedia box (volume material without a grid, materials/HomogeneousMedia.cpp) over a floor with an area
     light. (The reference's own SceneReader cannot build this - DESIGN.md §8 - but its integrator handles it.)"""
     b = SceneBuilder(transform_fn)
     sc = (1.1, 1.1, 1.1) if grey else (1.2, 0.9, 0.6)
-    b.add_volume_material("fog", sc, (.01, .01, .01), 1.5, -1, "hg", 0.3)
+    b.add_volume_material("fog", sc, (.01, .01, .01), 1.5, -1, "hg", g)
     b.add_microfacet("floor", (.8, .8, .8), 0.95, 0.0)
     b.add_emitter("light", (200, 200, 180))
     b.add_volume("fog", (0.2, 1.1, 0.3), (0, 25, 0), (1.6, 1.2, 1.4))

@@ -192,6 +192,60 @@ def test_infinite_area_light_material(lib, resources):
     sf.close()
 
 
+def _gltf_doc(uri, nbytes):
+    # two meshes under a small node tree (child before sibling: depth-first), the second without indices or uvs
+    return {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 2]}],
+            "nodes": [{"children": [1], "translation": [5, 5, 5]}, {"mesh": 0}, {"mesh": 1}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2}]},
+                       {"primitives": [{"attributes": {"POSITION": 3}, "mode": 4}, {"attributes": {"POSITION": 3}, "mode": 1}]}],
+            "buffers": [{"byteLength": nbytes, **({"uri": uri} if uri else {})}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 48}, {"buffer": 0, "byteOffset": 48, "byteLength": 32},
+                            {"buffer": 0, "byteOffset": 80, "byteLength": 12}, {"buffer": 0, "byteOffset": 92, "byteLength": 36}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+                          {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC2"},
+                          {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"},
+                          {"bufferView": 3, "componentType": 5126, "count": 3, "type": "VEC3"}]}
+
+
+@pytest.mark.parametrize("container", ["base64", "bin", "glb"])
+def test_gltf_reader(lib, tmp_path, container):
+    """`gltf` primitives (SceneReader.cpp:245-267 -> assimp -> Model::processNode, Model.cpp:323-335): meshes of the node
+    tree depth-first, no node transforms, indexed vertices kept, V flipped, non-triangle primitives skipped."""
+    import base64
+    P0 = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    UV = np.array([[0, 0], [1, 0], [1, .25], [0, 1]], np.float32)
+    I0 = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    P1 = np.array([[2, 0, 0], [3, 0, 1], [2, 1, 0]], np.float32)
+    blob = P0.tobytes() + UV.tobytes() + I0.tobytes() + P1.tobytes()
+    (tmp_path / "models").mkdir()
+    if container == "base64":
+        doc = _gltf_doc("data:application/octet-stream;base64," + base64.b64encode(blob).decode(), len(blob))
+        (tmp_path / "models" / "m.gltf").write_text(json.dumps(doc))
+        path = "models/m.gltf"
+    elif container == "bin":
+        (tmp_path / "models" / "m.bin").write_bytes(blob)
+        (tmp_path / "models" / "m.gltf").write_text(json.dumps(_gltf_doc("m.bin", len(blob))))
+        path = "models/m.gltf"
+    else:
+        js = json.dumps(_gltf_doc(None, len(blob))).encode()
+        js += b" " * (-len(js) % 4)
+        body = struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+        (tmp_path / "models" / "m.glb").write_bytes(b"glTF" + struct.pack("<II", 2, 12 + len(body)) + body)
+        path = "models/m.glb"
+    s = {"version": "1", "materials": [{"name": "m", "type": "microfacet", "roughness": 0.5, "metallic": 0.0, "albedo": [1, 1, 1]}],
+         "primitives": [{"name": "g", "type": "gltf", "path": path, "materialName": "m",
+                         "transform": {"position": [0, 0, 0], "scale": [1, 1, 1], "rotation": [0, 0, 0]}}],
+         "camera": SCENE["camera"], "renderer": SCENE["renderer"]}
+    sf = SceneFile(text=json.dumps(s), resources_dir=str(tmp_path))
+    p = sf.desc().primitives[0]
+    assert (p.type, p.n_vertices, p.n_triangles) == (abi.PRIM_MESH, 7, 3)
+    assert np.array_equal(np.ctypeslib.as_array(p.positions, (7, 3)), np.concatenate([P0, P1]))
+    assert np.array_equal(np.ctypeslib.as_array(p.indices, (9,)), [0, 1, 2, 0, 2, 3, 4, 5, 6])
+    uv = np.ctypeslib.as_array(p.uvs, (7, 2))
+    assert np.array_equal(uv[:4], np.stack([UV[:, 0], 1 - UV[:, 1]], 1)) and not uv[4:].any()
+    sf.close()
+
+
 def test_vol_reader_follows_the_reference_token_rules(lib, tmp_path):
     """ResourceManager.cpp:222-286: only space-terminated tokens count; line 2 is discarded; a value glued to a newline
     is dropped (std::stof stops at the newline); a last token without a trailing space is not captured."""

@@ -36,9 +36,11 @@ CASES = {
                scenes.CameraParams((0, 1, -6), (0, 1, 0), 45.0)),
     "mixed": (scenes.mixed_scene, scenes.MIXED_CAMERA),
     "mesh": (lambda: scenes.mesh_scene(n=64), scenes.MESH_CAMERA),
-    "directional": (scenes.directional_scene, scenes.DIRECTIONAL_CAMERA),
+    # g = 0 in the image cases: HG::sample with g != 0 (Medium.h:96-114) yields sqrt(1 - cos^2) of a cos a hair beyond 1 about
+    # once in 1e7 draws, a NaN direction that trips the reference's own assert (Medium.h:126) in a converged render
+    "directional": (lambda: scenes.directional_scene(g=0.0), scenes.DIRECTIONAL_CAMERA),
     "environment": (scenes.environment_scene, scenes.ENVIRONMENT_CAMERA),
-    "homogeneous": (scenes.homogeneous_scene, scenes.HOMOGENEOUS_CAMERA),
+    "homogeneous": (lambda: scenes.homogeneous_scene(g=0.0), scenes.HOMOGENEOUS_CAMERA),
 }
 
 
@@ -131,7 +133,7 @@ def test_global_and_brick_majorants_agree_statistically(ctx):
     assert c0.delta_steps > 0
 
 
-@pytest.mark.parametrize("name", ["cornell", "volume", "mixed", "mesh"])
+@pytest.mark.parametrize("name", ["cornell", "volume", "mixed", "mesh", "directional", "environment", "homogeneous"])
 def test_image_parity_with_oracle_golden(ctx, name):
     """Converged-image parity against the committed oracle render (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, f"image_{name}.npz"))
