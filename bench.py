@@ -137,14 +137,16 @@ def run_reference(args, rank):
     if rank != 0:
         return
     b, cam, _, _ = build_scene()
-    vals, sample, cores = [], "", 0
+    vals, ms, sample, cores = [], [], "", 0
     for i in range(args.warmup + args.steps):
+        t0 = time.time()
         v, sample, cores = cpu_reference_run(b, cam, budget_s=args.ref_seconds)
         if i >= args.warmup:
             vals.append(v)
+            ms.append((time.time() - t0) * 1e3)
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
