@@ -29,7 +29,7 @@ using namespace ne;
 namespace {
 
 struct WfCounts {
-	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, done;
+	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, genTaken, done;
 	unsigned long long workNext, workTotal;
 };
 
@@ -251,15 +251,20 @@ __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 	if (hostDone) *hostDone = c.done;
 }
 
-// OfflineEngine.cpp:64-67 — sample jitter + Camera::getRayPassingThrough for `gen` new paths into free slots.
-__global__ void __launch_bounds__(256) k_wf_generate(WfBuf b, WfParams P) {
+// OfflineEngine.cpp:64-67 + Li's first intersectScene (:187-193, :244-260) fused: sample jitter,
+// Camera::getRayPassingThrough, trace and classify `gen` new camera paths. A camera path that ends right there (it
+// misses everything, or sees an emitter) never touches the pool - no slot, no record, no queue entry; only survivors
+// take a slot (from the `gen` the plan set aside; commit returns the rest) and are written ONCE, path and hit
+// together, straight into the volume / surface queue. In the C2 frame 5 of 6 camera paths miss the medium's box.
+__global__ void __launch_bounds__(256, 2) k_wf_generate(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
 	const uint32_t gen = b.c->gen;
 	const uint32_t freeN = b.c->freeN;
-	const uint32_t extendBase = b.c->extend;
 	const unsigned long long workBase = b.c->workNext;
 	const uint32_t npix = uint32_t(P.W) * uint32_t(P.H);
+	Stats st;
+	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < gen; i += gridDim.x * blockDim.x) {
-		uint32_t slot = b.qFree[freeN + gen - 1 - i];
 		unsigned long long w = workBase + i;
 		uint32_t pixel = uint32_t(w % npix);
 		uint32_t sample = uint32_t(P.sppBegin) + uint32_t(w / npix);
@@ -278,17 +283,32 @@ __global__ void __launch_bounds__(256) k_wf_generate(WfBuf b, WfParams P) {
 		r.sample = sample;
 		r.dim = rng.dim;
 		r.tHit = 0;
+		Hit h;
+		st.extend_rays++;
+		bool did = intersect_scene(S, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
+		QueueSink sink;
+		sink.accum = P.accum;
+		sink.pixel = pixel;
+		int kind = classify_hit(S, did, h, r.ps, sink);
+		if (kind == HIT_TERMINATE) continue;
+		uint32_t slot = b.qFree[freeN + gen - 1 - warp_push(&b.c->genTaken)];
 		store_path(b, slot, r);
-		b.qExtend[extendBase + i] = slot;
+		store_hit(b, slot, h);
+		if (kind == HIT_VOLUME) {
+			if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[warp_push(&b.c->vol)] = slot;
+			else b.qScat[warp_push(&b.c->scat)] = slot;
+		} else b.qSurf[warp_push(&b.c->surf)] = slot;
 	}
+	flush_stats_wf(st, P.counters);
 }
-// One thread: publish the refill (after generate has read the old counts).
+// One thread: publish the refill (after generate has read the old counts); unused reserved slots go back to the free list.
 __global__ void k_wf_commit(WfBuf b, DCounters* counters) {
 	WfCounts& c = *b.c;
-	c.extend += c.gen;
+	c.freeN += c.gen - c.genTaken;
 	c.workNext += c.gen;
 	atomicAdd(&counters->paths, (unsigned long long)c.gen);
 	c.gen = 0;
+	c.genTaken = 0;
 }
 
 // Scene::intersectScene for every path of the extend queue + classify (Li :187-193, :244-260).
