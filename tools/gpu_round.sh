@@ -22,11 +22,11 @@ if [[ " $WHAT " == *" bench "* ]]; then
   cat gpurun_out/bench.json
 fi
 if [[ " $WHAT " == *" ncu "* ]]; then
-  ARGS="--steps 1 --warmup 1 --no-cpu-baseline --no-e2e --spp 8"
+  ARGS="--steps 1 --warmup 0 --no-cpu-baseline --no-e2e"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
       python bench.py $ARGS > gpurun_out/launches_bench.log 2>&1
-  for K in k_wf_track k_wf_tr k_wf_extend; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -s 12 -c 1 -f -o gpurun_out/prof_$K \
+  for K in k_wf_track k_wf_tr k_wf_extend k_wf_scatter k_wf_generate; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -s 6 -c 1 -f -o gpurun_out/prof_$K \
         python bench.py $ARGS > gpurun_out/prof_$K.log 2>&1
   done
 fi
