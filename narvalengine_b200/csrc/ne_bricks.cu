@@ -5,6 +5,9 @@
 // The result is bit-identical to the host builder ne_b200_host_build_bricks (ne_host.cpp), which stays the
 // inspectable definition and serves leaf (.vdb) input; tests/test_gpu_parity.py compares the two.
 #include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
 #include <vector>
 
 #include "ne_ctx.h"
@@ -114,6 +117,56 @@ int scratch_reserve(ne_b200_ctx* ctx, size_t bytes) {
 	return NE_B200_OK;
 }
 
+// Host -> device copy of a large PAGEABLE caller buffer. cudaMemcpy from pageable memory is staged by the driver on one
+// thread (~7 GB/s measured for the 64 MiB C2 grid = 9 ms of a 49 ms end-to-end frame). Here a few host threads copy
+// 4 MiB chunks into the context's pinned staging buffer while the calling thread issues one async DMA per chunk as it
+// becomes ready, so the memcpy runs at several threads' worth of memory bandwidth and overlaps the PCIe transfer.
+// Buffers larger than the staging cap go in rounds.
+int h2d_staged(ne_b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+	const size_t CH = size_t(4) << 20, CAP = size_t(256) << 20;
+	if (bytes < 2 * CH) {
+		NE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		return NE_B200_OK;
+	}
+	const size_t want = std::min(bytes, CAP);
+	if (ctx->pinnedBytes < want) {
+		if (ctx->pinned) { NE_CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinnedBytes = 0; }
+		NE_CUDA_OK(cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault));
+		ctx->pinnedBytes = want;
+	}
+	const unsigned hw = std::thread::hardware_concurrency();
+	const int nThreads = int(std::max(1u, std::min(8u, hw ? hw / 2 : 4u)));
+	for (size_t roundOff = 0; roundOff < bytes; roundOff += ctx->pinnedBytes) {
+		const size_t roundBytes = std::min(ctx->pinnedBytes, bytes - roundOff);
+		const size_t nChunks = (roundBytes + CH - 1) / CH;
+		std::vector<std::atomic<int>> ready(nChunks);
+		for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+		std::atomic<size_t> next{0};
+		const char* s8 = static_cast<const char*>(src) + roundOff;
+		char* pin = static_cast<char*>(ctx->pinned);
+		auto worker = [&]() {
+			for (size_t c = next++; c < nChunks; c = next++) {
+				size_t off = c * CH, len = std::min(CH, roundBytes - off);
+				memcpy(pin + off, s8 + off, len);
+				ready[c].store(1, std::memory_order_release);
+			}
+		};
+		std::vector<std::thread> pool;
+		for (int t = 0; t < nThreads; t++) pool.emplace_back(worker);
+		cudaError_t err = cudaSuccess;
+		for (size_t c = 0; c < nChunks; c++) {
+			while (!ready[c].load(std::memory_order_acquire)) std::this_thread::yield();
+			size_t off = c * CH, len = std::min(CH, roundBytes - off);
+			if (err == cudaSuccess) err = cudaMemcpyAsync(static_cast<char*>(dst) + roundOff + off, pin + off, len, cudaMemcpyHostToDevice, ctx->stream);
+		}
+		for (auto& t : pool) t.join();
+		NE_CUDA_OK(err);
+		// the staging buffer is reused by the next round / the next upload
+		NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	}
+	return NE_B200_OK;
+}
+
 // dense (host) -> DVolume in HBM. Allocations that belong to the scene are pushed to ctx->sceneAllocs.
 int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out) {
 	const size_t nvox = size_t(v.width) * v.height * v.depth;
@@ -133,7 +186,7 @@ int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out)
 	int* dTot = reinterpret_cast<int*>(base + oTot);
 	cudaStream_t st = ctx->stream;
 	NE_CUDA_OK(cudaMemsetAsync(dTot, 0, 8, st));
-	NE_CUDA_OK(cudaMemcpyAsync(dDense, v.dense, nvox * 4, cudaMemcpyHostToDevice, st));
+	if ((rc = h2d_staged(ctx, dDense, v.dense, nvox * 4))) return rc;
 	k_brick_scan<<<unsigned((nb * 32 + 255) / 256), 256, 0, st>>>(dDense, v.width, v.height, v.depth, nbx, nby, nbz, dNeed, dMaj,
 	                                                             reinterpret_cast<unsigned int*>(dTot + 1));
 	k_brick_slots<<<1, 1024, 0, st>>>(dNeed, int(nb), dSlot, dTot);
@@ -143,9 +196,9 @@ int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out)
 	NE_CUDA_OK(cudaStreamSynchronize(st));
 	int2* dCells = nullptr;
 	float* dPool = nullptr;
-	NE_CUDA_OK(cudaMalloc(&dCells, nb * sizeof(int2)));
+	NE_CUDA_OK(cudaMallocAsync(&dCells, nb * sizeof(int2), st));
 	ctx->sceneAllocs.push_back(dCells);
-	NE_CUDA_OK(cudaMalloc(&dPool, std::max<size_t>(1, size_t(tot[0]) * BRICK_VOX) * sizeof(float)));
+	NE_CUDA_OK(cudaMallocAsync(&dPool, std::max<size_t>(1, size_t(tot[0]) * BRICK_VOX) * sizeof(float), st));
 	ctx->sceneAllocs.push_back(dPool);
 	k_brick_fill<<<unsigned(nb), 256, 0, st>>>(dDense, v.width, v.height, v.depth, nbx, nby, dSlot, dMaj, dCells, dPool);
 	ctx->kernelLaunches++;

@@ -44,6 +44,8 @@ struct ne_b200_ctx {
 	ne_wavefront_state* wf = nullptr;
 	void* scratch = nullptr;  // reusable device scratch (dense grid staging of the brick builder, resolve buffers)
 	size_t scratchBytes = 0;
+	void* pinned = nullptr;  // pinned host staging for large uploads from pageable caller memory (ne_bricks.cu h2d_staged)
+	size_t pinnedBytes = 0;
 };
 
 namespace ne {
