@@ -486,13 +486,16 @@ NE_D V3 phase_sample(const DMaterial& m, R& rng) {
 	return sample_unit_sphere(e1, e2);
 }
 
-template <class R>
+// KIND: -1 = look the material's kind up at run time; 0 = known surface (GGX); 1 = known medium (phase function). A
+// kernel that only ever sees one kind (k_wf_scatter: media, k_wf_surface: surfaces) compiles the other half out.
+template <int KIND = -1, class R>
 NE_D V3 bsdf_sample(const DScene& s, const DMaterial& m, V3 incoming, V3 normal, const Hit& ri, R& rng) {
 	V3 ss, ts;
 	onb(normal, ss, ts);
 	V3 wo = to_lcs(-normalize(incoming), normal, ss, ts);
 	V3 sc;
-	if (m.transmissive)
+	const bool transmissive = KIND < 0 ? bool(m.transmissive) : KIND == 1;
+	if (transmissive)
 		sc = phase_sample(m, rng);
 	else {
 		float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
@@ -502,22 +505,26 @@ NE_D V3 bsdf_sample(const DScene& s, const DMaterial& m, V3 incoming, V3 normal,
 	}
 	return to_world(sc, normal, ss, ts);
 }
+template <int KIND = -1>
 NE_D float bsdf_pdf(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered, V3 normal, const Hit& ri) {
-	if (!m.transmissive && (!(dot(-incoming, normal) > 0) || !(dot(scattered, normal) > 0))) return 0;
+	const bool transmissive = KIND < 0 ? bool(m.transmissive) : KIND == 1;
+	if (!transmissive && (!(dot(-incoming, normal) > 0) || !(dot(scattered, normal) > 0))) return 0;
 	V3 ss, ts;
 	onb(normal, ss, ts);
 	V3 wo = to_lcs(-normalize(incoming), normal, ss, ts), wi = to_lcs(scattered, normal, ss, ts);
-	if (m.transmissive) return phase_eval(m, wo, wi);
+	if (transmissive) return phase_eval(m, wo, wi);
 	V3 h = normalize(wo + wi);
 	float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
 	return ggx_pdf(rough * rough, wi, h);
 }
+template <int KIND = -1>
 NE_D V3 bsdf_eval(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered, const Hit& ri) {
-	if (!m.transmissive && (!(dot(-incoming, ri.n) > 0) || !(dot(scattered, ri.n) > 0))) return V3(0.0f);
+	const bool transmissive = KIND < 0 ? bool(m.transmissive) : KIND == 1;
+	if (!transmissive && (!(dot(-incoming, ri.n) > 0) || !(dot(scattered, ri.n) > 0))) return V3(0.0f);
 	V3 ss, ts;
 	onb(ri.n, ss, ts);
 	V3 wo = to_lcs(-normalize(incoming), ri.n, ss, ts), wi = to_lcs(scattered, ri.n, ss, ts);
-	if (m.transmissive) return V3(phase_eval(m, wo, wi));
+	if (transmissive) return V3(phase_eval(m, wo, wi));
 	float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
 	float alpha = rough * rough;
 	V3 H = normalize(wo + wi);

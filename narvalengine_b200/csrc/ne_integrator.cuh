@@ -99,7 +99,7 @@ struct ImmediateSink {
 
 // estimateDirect :74-157. `lightIdx` = fold index of the chosen light instance; `stream` names the side stream of
 // the BSDF-half transmittance walk.
-template <class R, class SINK>
+template <int KIND = -1, class R, class SINK>
 NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int lightIdx, R& rng, SINK& sink, uint32_t stream, Stats& st) {
 	const DInstance& li = s.inst[lightIdx];
 	const DMaterial& lm = s.mat[li.material];
@@ -147,14 +147,14 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	}
 	V3 f(0.0f);
 	float scatteringPdf = 0;
-	bool isSurface = !m.has_medium;
+	const bool isSurface = KIND < 0 ? !m.has_medium : KIND == 0;
 
 	if (lightPdf > 0 && !is_black(Li)) {
 		if (isSurface) {
-			f = bsdf_eval(s, m, incoming.d, wo.d, isect) * fabsf(dot(wo.d, isect.n));
-			scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
+			f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect) * fabsf(dot(wo.d, isect.n));
+			scatteringPdf = bsdf_pdf<KIND>(s, m, incoming.d, wo.d, isect.n, isect);
 		} else {
-			f = bsdf_eval(s, m, incoming.d, wo.d, isect);
+			f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect);
 			scatteringPdf = f.x;
 		}
 		if (!is_black(f)) {
@@ -164,13 +164,13 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	}
 
 	if (isSurface) {
-		wo.d = bsdf_sample(s, m, incoming.d, isect.n, isect, rng);
-		f = bsdf_eval(s, m, incoming.d, wo.d, isect);
+		wo.d = bsdf_sample<KIND>(s, m, incoming.d, isect.n, isect, rng);
+		f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect);
 		f = f * fabsf(dot(wo.d, isect.n));
-		scatteringPdf = bsdf_pdf(s, m, incoming.d, wo.d, isect.n, isect);
+		scatteringPdf = bsdf_pdf<KIND>(s, m, incoming.d, wo.d, isect.n, isect);
 	} else {
-		f = bsdf_eval(s, m, incoming.d, wo.d, isect);                            // Q18: f for the light-half direction ...
-		wo.d = bsdf_sample(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
+		f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect);                            // Q18: f for the light-half direction ...
+		wo.d = bsdf_sample<KIND>(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
 		scatteringPdf = f.x;
 	}
 
@@ -187,7 +187,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 
 // uniformSampleOneLight :159-174. Returns what the caller must add as L += T * value (zero for queueing sinks,
 // which splat T * value later themselves).
-template <class R, class SINK>
+template <int KIND = -1, class R, class SINK>
 NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng, SINK& sink, uint32_t stream, Stats& st) {
 	float r = rng.next();
 	if (s.n_lights == 0) return V3(0.0f);  // the reference throws std::out_of_range here
@@ -197,7 +197,7 @@ NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng
 	(void)rng.next();  // second getRandomLightPrimitive call
 	sink.begin();
 	sink.sel_pdf = lightPdf;
-	estimate_direct(s, incoming, isect, s.n_models + i, rng, sink, stream, st);
+	estimate_direct<KIND>(s, incoming, isect, s.n_models + i, rng, sink, stream, st);
 	return sink.end(lightPdf);
 }
 
@@ -267,12 +267,12 @@ NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray 
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	if (all_one(a)) return volume_escape(ps, isect);  // Q1 / Q1b: an escape is recognised by the value (1,1,1)
 	ps.T = ps.T * a;
-	V3 phaseFr = bsdf_eval(s, m, ps.ray.d, scattered.d, isect);
-	float phasePdf = bsdf_pdf(s, m, ps.ray.d, scattered.d, isect.n, isect);
+	V3 phaseFr = bsdf_eval<1>(s, m, ps.ray.d, scattered.d, isect);
+	float phasePdf = bsdf_pdf<1>(s, m, ps.ray.d, scattered.d, isect.n, isect);
 	if (is_black(phaseFr) || phasePdf == 0.f) return PATH_DONE;
 	V3 Tnew = ps.T * (phaseFr / phasePdf);
 	sink.scale = Tnew;  // L += T * lightSample happens AFTER the throughput update (:228-232)
-	V3 lightSample = sample_one_light(s, scattered, isect, rng, sink, 1u + ps.nee++, st);  // Q2
+	V3 lightSample = sample_one_light<1>(s, scattered, isect, rng, sink, 1u + ps.nee++, st);  // Q2
 	ps.T = Tnew;
 	sink.emit(ps.T * lightSample);
 	ps.ray = scattered;
@@ -296,7 +296,7 @@ NE_D int shade_volume_homog(const DScene& s, PathState& ps, Hit& isect, R& rng, 
 	if (sampled) {
 		st.scatter_events++;
 		scattered.o = ps.ray.at(t);
-		scattered.d = bsdf_sample(s, m, ps.ray.d, isect.n, isect, rng);
+		scattered.d = bsdf_sample<1>(s, m, ps.ray.d, isect.n, isect, rng);
 	} else {
 		scattered.o = ps.ray.at(dist + 0.001f);
 		scattered.d = ps.ray.d;
@@ -331,13 +331,13 @@ NE_D int shade_surface(const DScene& s, PathState& ps, const Hit& isect, R& rng,
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	st.surface_events++;
 	sink.scale = ps.T;
-	V3 ls = sample_one_light(s, ps.ray, isect, rng, sink, 1u + ps.nee++, st);
+	V3 ls = sample_one_light<0>(s, ps.ray, isect, rng, sink, 1u + ps.nee++, st);
 	sink.emit(ps.T * ls);
 	Ray scattered;
 	scattered.o = isect.p;
-	scattered.d = bsdf_sample(s, m, ps.ray.d, isect.n, isect, rng);
-	float bsdfPdf = bsdf_pdf(s, m, ps.ray.d, scattered.d, isect.n, isect);
-	V3 fr = bsdf_eval(s, m, ps.ray.d, scattered.d, isect);
+	scattered.d = bsdf_sample<0>(s, m, ps.ray.d, isect.n, isect, rng);
+	float bsdfPdf = bsdf_pdf<0>(s, m, ps.ray.d, scattered.d, isect.n, isect);
+	V3 fr = bsdf_eval<0>(s, m, ps.ray.d, scattered.d, isect);
 	if (is_black(fr) || bsdfPdf == 0.f) return PATH_DONE;
 	ps.T = ps.T * (fr * fabsf(dot(ps.ray.d, isect.n)) / bsdfPdf);  // Q5
 	ps.ray = scattered;

@@ -211,7 +211,7 @@ NE_D Ray grid_scatter(const DScene& s, const DInstance& in, const DMaterial& m, 
 	st.scatter_events++;
 	Ray so;
 	so.o = rayOCS.at(t);
-	so.d = bsdf_sample(s, m, rayOCS.d, V3(0.0f, 1.0f, 0.0f), isect, rng);
+	so.d = bsdf_sample<1>(s, m, rayOCS.d, V3(0.0f, 1.0f, 0.0f), isect, rng);
 	return transform_ray(so, in.M);
 }
 
