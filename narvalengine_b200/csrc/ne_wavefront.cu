@@ -341,6 +341,9 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 	flush_stats_wf(st, P.counters);
 }
 
+#ifndef NE_TRACK_EARLY_BREAK
+#define NE_TRACK_EARLY_BREAK 0  // leave the move loop as soon as no lane of the warp is moving (a vote per crossing: measured slower)
+#endif
 #ifndef NE_TRACK_THREADS
 #define NE_TRACK_THREADS 256
 #endif
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 				else if (trk.wants_candidate(wr)) state = L_CAND;
 				else if (trk.move(st) == TRACK_END) state = L_FIN_END;
 			}
-			if (!__any_sync(0xffffffffu, state == L_MOVING)) break;
+			if (NE_TRACK_EARLY_BREAK && !__any_sync(0xffffffffu, state == L_MOVING)) break;
 		}
 		// ---- candidate
 		if (state == L_CAND) {
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 				else if (trk.wants_candidate(wr)) state = L_CAND;
 				else if (trk.move(st) == TRACK_END) state = L_FIN_END;
 			}
-			if (!__any_sync(0xffffffffu, state == L_MOVING)) break;
+			if (NE_TRACK_EARLY_BREAK && !__any_sync(0xffffffffu, state == L_MOVING)) break;
 		}
 		// ---- candidate
 		if (state == L_CAND) {
