@@ -770,7 +770,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	P.bounces = bounces;
 	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
 	P.moves = int(std::max(1u, env_u32("NE_B200_TRACK_MOVES", 4)));  // brick crossings per lane between two candidate phases
-	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 12))));  // refill a warp once this many lanes are idle
+	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 20))));  // refill a warp once this many lanes are idle
 	P.seed = seed;
 	P.counters = ctx->dCounters;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
