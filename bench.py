@@ -300,7 +300,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [DEBUG spp={spp}]", "resolution": [W, H], "spp_per_gpu": spp,
                            "bounces": BOUNCES, "grid": [GRID] * 3, "partition": f"sample-index x{world} + NCCL reduce" if world > 1 else "single GPU",
-                           "l2": "flushed between timed steps (256 MiB write)", "majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 25))},
+                           "l2": "flushed between timed steps (256 MiB write)", "majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 26))},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "counters": {k: int(getattr(c, k)) for k in ("paths", "extend_rays", "shadow_rays", "delta_steps", "ratio_steps", "brick_visits",
                                                               "scatter_events", "wavefront_iterations")},

@@ -2,8 +2,8 @@
 // (core/OfflineEngine.cpp:61-71) over the whole frame as a WAVEFRONT of SoA path records.
 //
 //   pool      N path slots (one 128-byte record each: 64 B path state + 48 B hit) that are refilled with new camera
-//             samples as paths terminate, so the wavefront stays full until the work runs out. 32 Mi slots by default
-//             (10.4 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
+//             samples as paths terminate, so the wavefront stays full until the work runs out. 64 Mi slots by default
+//             (21 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
 //   queues    arrays of slot indices: extend -> {volume, surface}; volume -> {scatter, volume (walk not finished),
 //             next extend}; free slots. All pushes are warp-aggregated (one atomicAdd per warp per queue)
 //   kernels   plan (1 thread: queue bookkeeping) · generate (camera rays) · extend (Scene::intersectScene fold, BVH)
@@ -754,7 +754,7 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
 	const unsigned long long work = (unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin);
 	if (work == 0 || bounces == 0) return NE_B200_OK;
-	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 25));
+	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 26));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
 	int rc = wavefront_ensure(ctx, nSlots);
 	if (rc) return rc;
