@@ -1,22 +1,26 @@
 // ne_wavefront.cu — the production renderer: OfflineEngine::renderTile's pixel x sample loops
-// (core/OfflineEngine.cpp:61-71) over the whole frame as a WAVEFRONT of SoA path records.
+// (core/OfflineEngine.cpp:61-71) over the whole frame as a WAVEFRONT of path records.
 //
 //   pool      N path slots (one 128-byte record each: 64 B path state + 48 B hit) that are refilled with new camera
 //             samples as paths terminate, so the wavefront stays full until the work runs out. 64 Mi slots by default
 //             (21 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
-//   queues    arrays of slot indices: extend -> {volume, surface}; volume -> {scatter, volume (walk not finished),
-//             next extend}; free slots. All pushes are warp-aggregated (one atomicAdd per warp per queue)
-//   kernels   plan (1 thread: queue bookkeeping) · generate (camera rays) · extend (Scene::intersectScene fold, BVH)
-//             · track (delta tracking, bounded events per pass) · scatter (phase function + next-event setup)
-//             · surface (GGX shading + next-event setup) · shadow (visibilityTr requests)
-//             · tr (intersectTr requests: walk to the first medium + ratio tracking, bounded events per pass)
+//   queues    arrays of slot indices: {generate, extend} -> {volume, scatter (homogeneous media), surface};
+//             volume -> {scatter, volume (walk not finished), next extend}; free slots. Pushes are warp-aggregated
+//             (one atomicAdd per warp per queue; the persistent tracking kernels batch theirs per phase)
+//   kernels   plan / commit (1 thread: queue bookkeeping)
+//             · generate (camera ray + the path's first Scene::intersectScene: paths that end at once never enter the pool)
+//             · extend (Scene::intersectScene fold, BVH, for continuing paths)
+//             · track (delta tracking: persistent warps in finish+refill / move / candidate phases, bounded events per pass)
+//             · scatter (phase function + next-event setup) · surface (GGX shading + next-event setup)
+//             · shadow (visibilityTr requests) · trfind (intersectTr: walk through surfaces to the first medium)
+//             · tr (ratio tracking through that medium, persistent warps like track)
 //   output    fp32 atomicAdd splats into the context's linear accumulation buffer
 //
-// The two tracking kernels stop a walk after `budget` events (brick moves + density look-ups), move the origin to the
-// point reached and queue the remainder for the next pass: exponential free flights are memoryless, so the estimate is
-// unchanged, and a warp is never held hostage by its longest walk. Every kernel is a grid-stride loop over a
-// device-side count with a fixed grid of (SM count x resident blocks): no host round trip sizes a launch; the host
-// only polls a mapped "done" word every few iterations.
+// The two tracking kernels stop a walk after `budget` events (brick crossings + density look-ups) and queue the
+// remainder for the next pass: exponential free flights are memoryless, so the estimate is unchanged, and a warp is
+// never held hostage by its longest walk. Every kernel runs over a device-side count with a fixed grid of (SM count x
+// resident blocks): no host round trip sizes a launch; the host only polls a mapped "done" word every few iterations.
+// Every block stages the scene's instance / material / volume tables in shared memory first (stage_scene).
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
