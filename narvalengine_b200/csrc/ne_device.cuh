@@ -9,6 +9,8 @@
 //   BRICKMAJ  track with per-brick majorants over a brick DDA instead of the reference's single global majorant
 //             (same expectation, far fewer null collisions; SURVEY.md A.5 last bullet).
 #pragma once
+#include <climits>
+
 #include "ne_math.cuh"
 #include "ne_rng.cuh"
 #include "ne_scene.cuh"
@@ -240,57 +242,59 @@ NE_D bool bvh_closest(const DMesh& m, Ray r, float& tBest, int& slotBest, Stats&
 	// keeps the slab test inclusive there (the reference's one-triangle unit test hits at a vertex, tests.cpp:300-347).
 	const V3 inv(1.0f / (fabsf(r.d.x) > 1e-20f ? r.d.x : copysignf(1e-20f, r.d.x)), 1.0f / (fabsf(r.d.y) > 1e-20f ? r.d.y : copysignf(1e-20f, r.d.y)),
 	             1.0f / (fabsf(r.d.z) > 1e-20f ? r.d.z : copysignf(1e-20f, r.d.z)));
+	// "while-while" traversal (Aila & Laine 2009): every lane first descends inner nodes until it stands on a leaf (or
+	// has nothing left), and only then do the lanes of the warp test their leaves' triangles together. With the two kinds
+	// of work interleaved per lane ("if-if"), ncu showed 3 of 32 lanes active in the triangle code on the 2 M-triangle
+	// scene. The order in which a ray visits nodes and triangles - hence the result - is unchanged.
+	const int DONE = INT_MIN;  // bottom of the stack
 	int stack[48];
 	int sp = 0;
+	stack[sp++] = DONE;
 	int node = 0;
 	tBest = INFINITY;
 	slotBest = -1;
 	bool any = false;
 	while (true) {
-		if (node < 0) {
-			int enc = ~node;
-			int first = enc >> 3, cnt = enc & 7;
-			for (int i = 0; i < cnt; i++) {
-				const float4* tp = m.tri + 3 * size_t(first + i);
-				float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-				float t;
-				st.tri_tests++;
-				if (tri_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), r, t)) {
-					any = true;
-					if (t < tBest) { tBest = t; slotBest = first + i; }
-				}
+		while (node >= 0) {
+			st.bvh_nodes++;
+			const float4* np = reinterpret_cast<const float4*>(m.nodes + node);
+			float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+			// n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = child0 child1 - -
+			float ax = (n0.x - r.o.x) * inv.x, bx = (n0.w - r.o.x) * inv.x;
+			float ay = (n0.y - r.o.y) * inv.y, by = (n1.x - r.o.y) * inv.y;
+			float az = (n0.z - r.o.z) * inv.z, bz = (n1.y - r.o.z) * inv.z;
+			float tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+			float tf0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+			ax = (n1.z - r.o.x) * inv.x; bx = (n2.y - r.o.x) * inv.x;
+			ay = (n1.w - r.o.y) * inv.y; by = (n2.z - r.o.y) * inv.y;
+			az = (n2.x - r.o.z) * inv.z; bz = (n2.w - r.o.z) * inv.z;
+			float tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+			float tf1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+			bool h0 = tn0 <= tf0 && tn0 <= tBest;
+			bool h1 = tn1 <= tf1 && tn1 <= tBest;
+			int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+			if (h0 && h1) {
+				if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
+				if (sp < 48) stack[sp++] = c1;
+				node = c0;
+			} else if (h0) node = c0;
+			else if (h1) node = c1;
+			else node = stack[--sp];
+		}
+		if (node == DONE) break;
+		int enc = ~node;
+		int first = enc >> 3, cnt = enc & 7;
+		for (int i = 0; i < cnt; i++) {
+			const float4* tp = m.tri + 3 * size_t(first + i);
+			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			float t;
+			st.tri_tests++;
+			if (tri_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), r, t)) {
+				any = true;
+				if (t < tBest) { tBest = t; slotBest = first + i; }
 			}
-			if (sp == 0) break;
-			node = stack[--sp];
-			continue;
 		}
-		st.bvh_nodes++;
-		const float4* np = reinterpret_cast<const float4*>(m.nodes + node);
-		float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-		// n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = child0 child1 - -
-		float ax = (n0.x - r.o.x) * inv.x, bx = (n0.w - r.o.x) * inv.x;
-		float ay = (n0.y - r.o.y) * inv.y, by = (n1.x - r.o.y) * inv.y;
-		float az = (n0.z - r.o.z) * inv.z, bz = (n1.y - r.o.z) * inv.z;
-		float tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-		float tf0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-		ax = (n1.z - r.o.x) * inv.x; bx = (n2.y - r.o.x) * inv.x;
-		ay = (n1.w - r.o.y) * inv.y; by = (n2.z - r.o.y) * inv.y;
-		az = (n2.x - r.o.z) * inv.z; bz = (n2.w - r.o.z) * inv.z;
-		float tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-		float tf1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-		bool h0 = tn0 <= tf0 && tn0 <= tBest;
-		bool h1 = tn1 <= tf1 && tn1 <= tBest;
-		int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-		if (h0 && h1) {
-			if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
-			if (sp < 48) stack[sp++] = c1;
-			node = c0;
-		} else if (h0) node = c0;
-		else if (h1) node = c1;
-		else {
-			if (sp == 0) break;
-			node = stack[--sp];
-		}
+		node = stack[--sp];
 	}
 	return any;
 }
