@@ -641,6 +641,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	if ((rc = push_alloc(ctx, envDists.data(), envDists.size(), &s.env))) return rc;
 	ctx->scene = s;
 	ctx->nVolumes = d->n_volumes;
+	ctx->nMeshes = int(meshes.size());
 	ctx->haveScene = true;
 	ctx->msUpload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	return NE_B200_OK;

@@ -32,6 +32,7 @@ struct ne_b200_ctx {
 	ne::DScene scene{};
 	bool haveScene = false;
 	int nVolumes = 0;
+	int nMeshes = 0;  // triangle meshes with a BVH: the wavefront then runs its persistent trace kernels
 	ne::DCamera cam{};
 	bool haveCamera = false;
 	float* accum = nullptr;  // W*H*3 fp32 radiance sums

@@ -237,19 +237,65 @@ NE_D V3 normal_from_map(V3 texNormal, V3 worldNormal) {
 // Closest triangle with t >= 0 (BVH::intersect semantics, primitives/BVH.cpp:108-194: no tMin/tMax inside, strict
 // `<` keeps the first of equal hits) over OUR binned-SAH 2-wide BVH. Node boxes are tested with a conservative
 // slab test; every triangle test uses the reference arithmetic above.
-NE_D bool bvh_closest(const DMesh& m, Ray r, float& tBest, int& slotBest, Stats& st) {
+NE_D V3 bvh_inv_dir(const Ray& r) {
 	// A zero direction component would give 0*inf = NaN for rays lying exactly in a box face; a huge finite reciprocal
 	// keeps the slab test inclusive there (the reference's one-triangle unit test hits at a vertex, tests.cpp:300-347).
-	const V3 inv(1.0f / (fabsf(r.d.x) > 1e-20f ? r.d.x : copysignf(1e-20f, r.d.x)), 1.0f / (fabsf(r.d.y) > 1e-20f ? r.d.y : copysignf(1e-20f, r.d.y)),
-	             1.0f / (fabsf(r.d.z) > 1e-20f ? r.d.z : copysignf(1e-20f, r.d.z)));
+	return V3(1.0f / (fabsf(r.d.x) > 1e-20f ? r.d.x : copysignf(1e-20f, r.d.x)), 1.0f / (fabsf(r.d.y) > 1e-20f ? r.d.y : copysignf(1e-20f, r.d.y)),
+	          1.0f / (fabsf(r.d.z) > 1e-20f ? r.d.z : copysignf(1e-20f, r.d.z)));
+}
+#define NE_BVH_DONE INT_MIN  // bottom of the traversal stack
+#define NE_BVH_STACK 48
+// One inner-node visit: both child boxes against the ray, near child first, far child pushed.
+NE_D int bvh_node_step(const DMesh& m, const Ray& r, const V3& inv, int node, int* stack, int& sp, float tBest) {
+	const float4* np = reinterpret_cast<const float4*>(m.nodes + node);
+	float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+	// n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = child0 child1 - -
+	float ax = (n0.x - r.o.x) * inv.x, bx = (n0.w - r.o.x) * inv.x;
+	float ay = (n0.y - r.o.y) * inv.y, by = (n1.x - r.o.y) * inv.y;
+	float az = (n0.z - r.o.z) * inv.z, bz = (n1.y - r.o.z) * inv.z;
+	float tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+	float tf0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+	ax = (n1.z - r.o.x) * inv.x; bx = (n2.y - r.o.x) * inv.x;
+	ay = (n1.w - r.o.y) * inv.y; by = (n2.z - r.o.y) * inv.y;
+	az = (n2.x - r.o.z) * inv.z; bz = (n2.w - r.o.z) * inv.z;
+	float tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+	float tf1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+	bool h0 = tn0 <= tf0 && tn0 <= tBest;
+	bool h1 = tn1 <= tf1 && tn1 <= tBest;
+	int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+	if (h0 && h1) {
+		if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
+		if (sp < NE_BVH_STACK) stack[sp++] = c1;
+		return c0;
+	}
+	if (h0) return c0;
+	if (h1) return c1;
+	return stack[--sp];
+}
+// One leaf (node < 0, not NE_BVH_DONE): its triangles with the reference arithmetic, strict `<` keeps the first of equals.
+NE_D void bvh_leaf(const DMesh& m, const Ray& r, int node, float& tBest, int& slotBest, bool& any, Stats& st) {
+	int enc = ~node;
+	int first = enc >> 3, cnt = enc & 7;
+	for (int i = 0; i < cnt; i++) {
+		const float4* tp = m.tri + 3 * size_t(first + i);
+		float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+		float t;
+		st.tri_tests++;
+		if (tri_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), r, t)) {
+			any = true;
+			if (t < tBest) { tBest = t; slotBest = first + i; }
+		}
+	}
+}
+NE_D bool bvh_closest(const DMesh& m, Ray r, float& tBest, int& slotBest, Stats& st) {
+	const V3 inv = bvh_inv_dir(r);
 	// "while-while" traversal (Aila & Laine 2009): every lane first descends inner nodes until it stands on a leaf (or
 	// has nothing left), and only then do the lanes of the warp test their leaves' triangles together. With the two kinds
 	// of work interleaved per lane ("if-if"), ncu showed 3 of 32 lanes active in the triangle code on the 2 M-triangle
 	// scene. The order in which a ray visits nodes and triangles - hence the result - is unchanged.
-	const int DONE = INT_MIN;  // bottom of the stack
-	int stack[48];
+	int stack[NE_BVH_STACK];
 	int sp = 0;
-	stack[sp++] = DONE;
+	stack[sp++] = NE_BVH_DONE;
 	int node = 0;
 	tBest = INFINITY;
 	slotBest = -1;
@@ -257,43 +303,10 @@ NE_D bool bvh_closest(const DMesh& m, Ray r, float& tBest, int& slotBest, Stats&
 	while (true) {
 		while (node >= 0) {
 			st.bvh_nodes++;
-			const float4* np = reinterpret_cast<const float4*>(m.nodes + node);
-			float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-			// n0 = lo0.xyz hi0.x ; n1 = hi0.yz lo1.xy ; n2 = lo1.z hi1.xyz ; n3 = child0 child1 - -
-			float ax = (n0.x - r.o.x) * inv.x, bx = (n0.w - r.o.x) * inv.x;
-			float ay = (n0.y - r.o.y) * inv.y, by = (n1.x - r.o.y) * inv.y;
-			float az = (n0.z - r.o.z) * inv.z, bz = (n1.y - r.o.z) * inv.z;
-			float tn0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-			float tf0 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-			ax = (n1.z - r.o.x) * inv.x; bx = (n2.y - r.o.x) * inv.x;
-			ay = (n1.w - r.o.y) * inv.y; by = (n2.z - r.o.y) * inv.y;
-			az = (n2.x - r.o.z) * inv.z; bz = (n2.w - r.o.z) * inv.z;
-			float tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-			float tf1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-			bool h0 = tn0 <= tf0 && tn0 <= tBest;
-			bool h1 = tn1 <= tf1 && tn1 <= tBest;
-			int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-			if (h0 && h1) {
-				if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
-				if (sp < 48) stack[sp++] = c1;
-				node = c0;
-			} else if (h0) node = c0;
-			else if (h1) node = c1;
-			else node = stack[--sp];
+			node = bvh_node_step(m, r, inv, node, stack, sp, tBest);
 		}
-		if (node == DONE) break;
-		int enc = ~node;
-		int first = enc >> 3, cnt = enc & 7;
-		for (int i = 0; i < cnt; i++) {
-			const float4* tp = m.tri + 3 * size_t(first + i);
-			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-			float t;
-			st.tri_tests++;
-			if (tri_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), r, t)) {
-				any = true;
-				if (t < tBest) { tBest = t; slotBest = first + i; }
-			}
-		}
+		if (node == NE_BVH_DONE) break;
+		bvh_leaf(m, r, node, tBest, slotBest, any, st);
 		node = stack[--sp];
 	}
 	return any;
@@ -320,7 +333,39 @@ NE_D void tri_uv(const DMesh& m, int tri, V3 p, float& u, float& v) {
 // for the one-primitive models SceneReader builds. `in_lights`: the instance sits in Scene::lights, i.e. its
 // primitive is in Model::lights (tested by the lights loop :432-444: no "inside" case).
 // ---------------------------------------------------------------------------------------------------------------
-NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st) {
+// The mesh branch after the BVH has answered (Model.cpp:381-392 + InstancedModel.cpp:30-36): accept the closest triangle
+// if it lies in (tMin, tMax), fill the hit record in OCS. `ray` is the OCS ray.
+NE_D bool mesh_accept(const DScene& s, const DInstance& in, const DMesh& m, const Ray& ray, bool local, float t, int slot, Hit& hit, float tMin, float& tMax) {
+	if (!(local && t > tMin && t < tMax)) return false;
+	tMax = t;
+	const float4* tp = m.tri + 3 * size_t(slot);
+	float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+	V3 v0(a.x, a.y, a.z), v1(b.x, b.y, b.z), v2(c.x, c.y, c.z);
+	int tri = __float_as_int(a.w);
+	hit.tNear = hit.tFar = t;
+	hit.p = ray.at(t);
+	tri_uv(m, tri, hit.p, hit.u, hit.v);
+	V3 n = normalize(cross(v1 - v0, v2 - v0));
+	if (in.material >= 0 && s.mat[in.material].has_normal_flag) {
+		V4 tn4 = material_sample(s, s.mat[in.material].normal_tex, hit.u, hit.v);
+		n = normal_from_map(V3(tn4.x, tn4.y, tn4.z), n);
+	}
+	hit.n = n;
+	hit.prim = tri;
+	return true;
+}
+// InstancedModel.cpp:33-36: the accepted hit goes back to WCS.
+NE_D void hit_to_wcs(const DInstance& in, int i, Hit& hit) {
+	hit.p = xform_point(in.M, hit.p);
+	hit.n = normalize(xform_dir(in.M, hit.n));
+	hit.inst = i;
+}
+
+// DEFER = true (the persistent trace kernels, SceneTrace below): a mesh whose bounding box the ray enters is NOT
+// traversed here; the call returns false with `deferred` set and the OCS ray in `rayO`, the caller walks the BVH at its
+// own pace and completes the instance with mesh_accept + hit_to_wcs.
+template <bool DEFER>
+NE_D bool instance_intersect_t(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st, bool& deferred, Ray& rayO) {
 	const DInstance& in = s.inst[i];
 	if (!in.collision) return false;
 	if (in_lights) {  // Model.cpp:429-432: a light whose Le(ray, identity) is not black (directional, environment) is never intersected
@@ -335,26 +380,14 @@ NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float t
 		const DMesh& m = s.mesh[in.mesh];
 		float tn, tf; V3 nn, hp;
 		if (!aabb_intersect(V3(m.bbmin[0], m.bbmin[1], m.bbmin[2]), V3(m.bbmax[0], m.bbmax[1], m.bbmax[2]), ray, tn, tf, nn, hp)) return false;
+		if (DEFER) {
+			deferred = true;
+			rayO = ray;
+			return false;
+		}
 		float t; int slot;
 		bool local = bvh_closest(m, ray, t, slot, st);
-		if (local && t > tMin && t < tMax) {
-			tMax = t;
-			const float4* tp = m.tri + 3 * size_t(slot);
-			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-			V3 v0(a.x, a.y, a.z), v1(b.x, b.y, b.z), v2(c.x, c.y, c.z);
-			int tri = __float_as_int(a.w);
-			hit.tNear = hit.tFar = t;
-			hit.p = ray.at(t);
-			tri_uv(m, tri, hit.p, hit.u, hit.v);
-			V3 n = normalize(cross(v1 - v0, v2 - v0));
-			if (in.material >= 0 && s.mat[in.material].has_normal_flag) {
-				V4 tn4 = material_sample(s, s.mat[in.material].normal_tex, hit.u, hit.v);
-				n = normal_from_map(V3(tn4.x, tn4.y, tn4.z), n);
-			}
-			hit.n = n;
-			hit.prim = tri;
-			did = true;
-		}
+		did = mesh_accept(s, in, m, ray, local, t, slot, hit, tMin, tMax);
 	} else if (in.type == PRIM_VOLUME && !in_lights && s.mat[in.material].volume >= 0) {
 		// GridMedia special case, Model.cpp:394-413: ignores tMin/tMax (Q4)
 		float tn, tf; V3 nn, hp;
@@ -396,12 +429,13 @@ NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float t
 		}
 	}
 	// PRIM_POINT: Point::intersect never hits (primitives/Point.cpp:10-12)
-	if (did) {
-		hit.p = xform_point(in.M, hit.p);
-		hit.n = normalize(xform_dir(in.M, hit.n));
-		hit.inst = i;
-	}
+	if (did) hit_to_wcs(in, i, hit);
 	return did;
+}
+NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st) {
+	bool deferred;
+	Ray rayO;
+	return instance_intersect_t<false>(s, i, rayW, hit, tMin, tMax, in_lights, st, deferred, rayO);
 }
 
 // Scene::intersectScene, core/Scene.cpp:30-56: sequential fold, instancedModels then lights, tMax shrinks on
@@ -415,6 +449,74 @@ NE_D bool intersect_scene(const DScene& s, Ray ray, Hit& hit, float tMin, float 
 	}
 	return did;
 }
+
+// Scene::intersectScene as a RESUMABLE computation, for the persistent trace kernels (ne_wavefront.cu, k_wf_trace): the
+// fold over instances runs until a mesh needs its BVH (fold() returns true), the BVH is walked in bounded slices
+// (walk()), the mesh is completed (mesh_done()) and the fold goes on. Same functions, same order of operations and
+// same results as intersect_scene; what changes is that the lanes of a warp can stand at different rays.
+struct SceneTrace {
+	Ray rayW, rayO;
+	Hit hit;
+	float tMin, tMax;
+	int i;  // instance the fold stands at
+	bool did;
+	// BVH walk of instance i
+	V3 inv;
+	int sp, node, slotBest;
+	float tBest;
+	bool any;
+	// the traversal stack (int[NE_BVH_STACK], dynamically indexed, hence in local memory) is the caller's and is passed to
+	// fold / walk: as a member it would drag the whole struct into local memory
+
+	NE_D void begin(Ray r, float tMin_, float tMax_) {
+		rayW = r;
+		tMin = tMin_;
+		tMax = tMax_;
+		i = 0;
+		did = false;
+		hit.inst = -1;
+	}
+	// true: instance i is a mesh waiting for walk(); false: the fold is complete (did / hit hold the answer)
+	NE_D bool fold(const DScene& s, int* stack, Stats& st) {
+		while (i < s.n_inst) {
+			bool deferred = false;
+			bool th = instance_intersect_t<true>(s, i, rayW, hit, tMin, tMax, i >= s.n_models, st, deferred, rayO);
+			if (deferred) {
+				inv = bvh_inv_dir(rayO);
+				sp = 0;
+				stack[sp++] = NE_BVH_DONE;
+				node = 0;
+				tBest = INFINITY;
+				slotBest = -1;
+				any = false;
+				return true;
+			}
+			did = did || th;
+			i++;
+		}
+		return false;
+	}
+	// At most `budget` inner-node visits of the while-while traversal; true when the walk is complete.
+	NE_D bool walk(const DMesh& m, int* stack, int budget, Stats& st) {
+		while (true) {
+			while (node >= 0) {
+				if (budget-- <= 0) return false;
+				st.bvh_nodes++;
+				node = bvh_node_step(m, rayO, inv, node, stack, sp, tBest);
+			}
+			if (node == NE_BVH_DONE) return true;
+			bvh_leaf(m, rayO, node, tBest, slotBest, any, st);
+			node = stack[--sp];
+		}
+	}
+	NE_D void mesh_done(const DScene& s) {
+		const DInstance& in = s.inst[i];
+		bool th = mesh_accept(s, in, s.mesh[in.mesh], rayO, any, tBest, slotBest, hit, tMin, tMax);
+		if (th) hit_to_wcs(in, i, hit);
+		did = did || th;
+		i++;
+	}
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // BSDFs: BSDF wrapper core/BSDF.h:100-142; GlossyBSDF core/GlossyBSDF.cpp:10-48; GGX core/Microfacet.cpp:5-65;

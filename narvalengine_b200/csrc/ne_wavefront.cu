@@ -33,7 +33,7 @@ using namespace ne;
 namespace {
 
 struct WfCounts {
-	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, genTaken, done;
+	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, genTaken, done, extHead, shHead, trfHead, pad_;
 	unsigned long long workNext, workTotal;
 };
 
@@ -65,7 +65,7 @@ struct WfParams {
 	DScene s;
 	DCamera cam;
 	float* accum;
-	int W, H, sppBegin, bounces, budget, refill, moves;
+	int W, H, sppBegin, bounces, budget, refill, moves, walkBudget, walkRefill;
 	uint64_t seed;
 	DCounters* counters;
 };
@@ -246,7 +246,7 @@ __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 	c.trNew0 = c.trNext;  // requests pushed from here on are new: k_wf_trfind locates their medium
 	c.trNext = 0;
 	c.scat = c.surf = c.shadow = 0;
-	c.volHead = c.trHead = 0;
+	c.volHead = c.trHead = c.extHead = c.shHead = c.trfHead = 0;
 	unsigned long long remaining = c.workTotal - c.workNext;
 	uint32_t gen = uint32_t(remaining < c.freeN ? remaining : c.freeN);
 	c.gen = gen;
@@ -605,6 +605,187 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 	flush_stats_wf(st, P.counters);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Scenes WITH triangle meshes: the three ray-casting stages (extend, shadow, trfind) as PERSISTENT warps over the
+// resumable SceneTrace. Traversal lengths of incoherent rays are heavy-tailed; in the grid-stride kernels above a warp
+// lasts as long as its longest ray (ncu on C4: 7 of 32 lanes active). Here a warp alternates two warp-wide phases:
+//   refill   (when P.walkRefill lanes are not walking) lanes whose BVH walk ended complete their mesh instance and go
+//            on with the instance fold; lanes whose fold ended hand the answer to the job (classify / splat / locate
+//            the medium) and fetch the next ray (one atomicAdd per warp); new rays fold up to their first mesh
+//   walk     every walking lane spends at most P.walkBudget inner-node visits of the while-while traversal
+// Each ray still sees intersect_scene's exact sequence of operations. Scenes without meshes keep the kernels above
+// (their fold is a handful of analytic tests: nothing to balance).
+// ---------------------------------------------------------------------------------------------------------------
+enum { T_IDLE = 0, T_FOLD = 1, T_WALK = 2, T_WALKED = 3, T_FOLDED = 4 };
+
+// k_wf_extend's job: Scene::intersectScene for the extend queue + classify (Li :187-193, :244-260).
+struct ExtendJob {
+	uint32_t slot, pixel;
+	V3 T;
+	int bounce;
+	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->extHead; }
+	__device__ __forceinline__ static uint32_t first(const WfBuf&) { return 0; }
+	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->extend; }
+	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
+		slot = b.qExtend[i];
+		float4 A = b.rec[slot].pA, B = b.rec[slot].pB, C = b.rec[slot].pC;
+		bounce = int(b.rec[slot].pD.x & 0xff);
+		Ray ray;
+		ray.o = V3(A.x, A.y, A.z);
+		ray.d = V3(A.w, B.x, B.y);
+		T = V3(B.z, B.w, C.x);
+		pixel = __float_as_uint(C.y);
+		st.extend_rays++;
+		tr.begin(ray, float(NE_EPSILON12), INFINITY);
+	}
+	__device__ __forceinline__ bool consume(const DScene& S, const WfBuf& b, const WfParams& P, SceneTrace& tr, Stats&) {
+		PathState ps;
+		ps.ray = tr.rayW;
+		ps.T = T;
+		ps.bounce = bounce;
+		QueueSink sink;
+		sink.accum = P.accum;
+		sink.pixel = pixel;
+		int kind = classify_hit(S, tr.did, tr.hit, ps, sink);
+		if (kind == HIT_TERMINATE) {
+			b.qFree[warp_push(&b.c->freeN)] = slot;
+		} else {
+			store_hit(b, slot, tr.hit);
+			if (kind == HIT_VOLUME) {
+				if (S.mat[S.inst[tr.hit.inst].material].volume >= 0) b.qVol[warp_push(&b.c->vol)] = slot;
+				else b.qScat[warp_push(&b.c->scat)] = slot;
+			} else b.qSurf[warp_push(&b.c->surf)] = slot;
+		}
+		return false;
+	}
+};
+
+// k_wf_shadow's job: visibilityTr :34-72 for the shadow requests.
+struct ShadowJob {
+	uint32_t req;
+	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->shHead; }
+	__device__ __forceinline__ static uint32_t first(const WfBuf&) { return 0; }
+	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->shadow; }
+	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
+		req = i;
+		float4 A = b.sA[i], B = b.sB[i];
+		Ray ray;
+		ray.o = V3(A.x, A.y, A.z);
+		ray.d = V3(A.w, B.x, B.y) - ray.o;
+		st.shadow_rays++;
+		tr.begin(ray, float(NE_EPSILON3), INFINITY);
+	}
+	__device__ __forceinline__ bool consume(const DScene& S, const WfBuf& b, const WfParams& P, SceneTrace& tr, Stats&) {
+		bool vis = true;
+		if (tr.did) {
+			int mi = S.inst[tr.hit.inst].material;
+			vis = mi >= 0 && S.mat[mi].has_light;
+		}
+		if (vis) {
+			float4 B = b.sB[req];
+			float2 C = b.sC[req];
+			splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x));
+		}
+		return false;
+	}
+};
+
+// k_wf_trfind's job: intersectTr :13-31 for the requests pushed in this iteration.
+struct TrFindJob {
+	uint32_t req;
+	int seg;
+	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->trfHead; }
+	__device__ __forceinline__ static uint32_t first(const WfBuf& b) { return b.c->trNew0; }
+	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->tr - b.c->trNew0; }
+	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
+		req = i;
+		seg = 0;
+		float4 A = b.tA[i], B = b.tB[i];
+		Ray ray;
+		ray.o = V3(A.x, A.y, A.z);
+		ray.d = V3(A.w, B.x, B.y);
+		st.shadow_rays++;
+		tr.begin(ray, float(NE_EPSILON3), INFINITY);
+	}
+	__device__ __forceinline__ bool consume(const DScene& S, const WfBuf& b, const WfParams& P, SceneTrace& tr, Stats& st) {
+		Ray ray = tr.rayW;
+		int inst = -2;
+		float tRemain = 0;
+		if (tr.did) {
+			const Hit& hh = tr.hit;
+			int mi = S.inst[hh.inst].material;
+			if (mi >= 0 && S.mat[mi].has_medium && S.mat[mi].volume >= 0) {
+				inst = hh.inst;
+				ray.o = ray.at(hh.tNear);
+				tRemain = hh.tFar - hh.tNear;
+			} else if (mi >= 0 && S.mat[mi].has_medium) {  // HomogeneousMedia: closed-form transmittance, nothing to walk
+				float4 B = b.tB[req], C = b.tC[req];
+				splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * homog_tr(S.mat[mi], hh.tFar - hh.tNear));
+			} else {
+				ray.o = hh.p;
+				if (++seg < NE_MAX_TR_SEGMENTS) {  // through the surface: next segment of the same request
+					st.shadow_rays++;
+					tr.begin(ray, float(NE_EPSILON3), INFINITY);
+					return true;
+				}
+			}
+		}
+		b.tA[req] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+		b.tD[req] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
+		return false;
+	}
+};
+
+#ifndef NE_TRACE_BLOCKS
+#define NE_TRACE_BLOCKS 4  // resident 256-thread blocks per SM the trace kernels are compiled for (64 registers: the walk is bound by
+                           // the latency of dependent node loads, so warps in flight count; measured 2: 43.5, 3: 33.9, 4: 31.0, 5: 33.3 ms on C4)
+#endif
+template <class JOB>
+__global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfParams P) {
+	NE_STAGE_SCENE();
+	const uint32_t first = JOB::first(b), n = JOB::count(b);
+	Stats st;
+	st.clear();
+	JOB job;
+	SceneTrace tr;
+	int stack[NE_BVH_STACK];
+	int state = T_IDLE;
+	bool exhausted = false;
+	while (true) {
+		const unsigned walking = __ballot_sync(0xffffffffu, state == T_WALK);
+		const bool pending = !exhausted || __any_sync(0xffffffffu, state == T_WALKED);  // something a refill phase could do
+		if (walking == 0 || (pending && 32 - __popc(walking) >= P.walkRefill)) {
+			// ---- refill: runs until every lane either walks a BVH or has nothing left to do
+			while (true) {
+				if (state == T_WALKED) {
+					tr.mesh_done(S);
+					state = T_FOLD;
+				}
+				if (state == T_FOLDED) state = job.consume(S, b, P, tr, st) ? T_FOLD : T_IDLE;
+				if (!exhausted) {
+					WarpReserve rf;
+					rf.issue(JOB::head(b), state == T_IDLE);
+					const uint32_t i = rf.get();
+					if (state == T_IDLE && i < n) {
+						job.fetch(b, first + i, tr, st);
+						state = T_FOLD;
+					}
+					if (__ballot_sync(0xffffffffu, state == T_IDLE)) exhausted = true;  // a lane came back empty-handed
+				}
+				if (state == T_FOLD) state = tr.fold(S, stack, st) ? T_WALK : T_FOLDED;
+				if (!__any_sync(0xffffffffu, state == T_FOLDED)) break;  // T_FOLD / T_WALKED cannot be pending here
+			}
+			if (__ballot_sync(0xffffffffu, state != T_IDLE) == 0) break;
+		}
+		// ---- walk
+		if (state == T_WALK) {
+			const DMesh& m = S.mesh[S.inst[tr.i].mesh];
+			if (tr.walk(m, stack, P.walkBudget, st)) state = T_WALKED;
+		}
+	}
+	flush_stats_wf(st, P.counters);
+}
+
 // Transmittance requests whose medium is known: ratio tracking through it (at most P.budget events per pass), splat
 // weight * Tr. Persistent warps and phases like k_wf_track; the weight and pixel are re-read from the request when the
 // walk ends.
@@ -775,8 +956,13 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
 	P.moves = int(std::max(1u, env_u32("NE_B200_TRACK_MOVES", 4)));  // brick crossings per lane between two candidate phases
 	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 20))));  // refill a warp once this many lanes are idle
+	P.walkBudget = int(std::max(1u, env_u32("NE_B200_WALK_BUDGET", 24)));  // inner-node visits per walking lane between two votes
+	P.walkRefill = int(std::min(32u, std::max(1u, env_u32("NE_B200_WALK_REFILL", 12))));  // refill a trace warp once this many lanes are not walking
 	P.seed = seed;
 	P.counters = ctx->dCounters;
+	// persistent trace kernels when there are BVHs to walk (NE_B200_TRACE=0/1 overrides)
+	const bool trace = env_u32("NE_B200_TRACE", ctx->nMeshes > 0 ? 1 : 0) != 0;
+	const int GR = w->smCount * NE_TRACE_BLOCKS;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
 	cudaStream_t st = ctx->stream;
 	const int G = w->gridBlocks, B = 256;
@@ -816,10 +1002,11 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 				std::swap(b.tD, b.uD);
 			}
 			k_wf_plan<<<1, 1, 0, st>>>(b, w->devDone);
-			k_wf_generate<<<G, B, 0, st>>>(b, P);
+			k_wf_generate<<<G, B, 0, st>>>(b, P);  // camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
 			k_wf_commit<<<1, 1, 0, st>>>(b, ctx->dCounters);
 			cudaEvent_t e0 = timeStages ? ev() : nullptr;
-			k_wf_extend<<<G, B, 0, st>>>(b, P);
+			if (trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
+			else k_wf_extend<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e1 = timeStages ? ev() : nullptr;
 			if (brick) k_wf_track<true><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 			else k_wf_track<false><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
@@ -827,8 +1014,13 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 			k_wf_scatter<<<G, B, 0, st>>>(b, P);
 			k_wf_surface<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e3 = timeStages ? ev() : nullptr;
-			k_wf_shadow<<<G, B, 0, st>>>(b, P);
-			k_wf_trfind<<<G, B, 0, st>>>(b, P);
+			if (trace) {
+				k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
+				k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
+			} else {
+				k_wf_shadow<<<G, B, 0, st>>>(b, P);
+				k_wf_trfind<<<G, B, 0, st>>>(b, P);
+			}
 			cudaEvent_t e4 = timeStages ? ev() : nullptr;
 			if (brick) k_wf_tr<true><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 			else k_wf_tr<false><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
