@@ -260,7 +260,8 @@ __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 // misses everything, or sees an emitter) never touches the pool - no slot, no record, no queue entry; only survivors
 // take a slot (from the `gen` the plan set aside; commit returns the rest) and are written ONCE, path and hit
 // together, straight into the volume / surface queue. In the C2 frame 5 of 6 camera paths miss the medium's box.
-__global__ void __launch_bounds__(256, 2) k_wf_generate(WfBuf b, WfParams P) {
+template <int MINB>  // resident blocks per SM: 2 without meshes (no spills), 4 with (the BVH walk is latency-bound: warps in flight count)
+__global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
 	const uint32_t gen = b.c->gen;
 	const uint32_t freeN = b.c->freeN;
@@ -1002,7 +1003,9 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 				std::swap(b.tD, b.uD);
 			}
 			k_wf_plan<<<1, 1, 0, st>>>(b, w->devDone);
-			k_wf_generate<<<G, B, 0, st>>>(b, P);  // camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
+			// camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
+			if (trace) k_wf_generate<NE_TRACE_BLOCKS><<<G, B, 0, st>>>(b, P);
+			else k_wf_generate<2><<<G, B, 0, st>>>(b, P);
 			k_wf_commit<<<1, 1, 0, st>>>(b, ctx->dCounters);
 			cudaEvent_t e0 = timeStages ? ev() : nullptr;
 			if (trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
