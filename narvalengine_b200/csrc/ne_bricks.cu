@@ -213,4 +213,38 @@ int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out)
 	return NE_B200_OK;
 }
 
+// The 2-byte majorant table the tracking walks read at every brick crossing: q = the brick's majorant as a multiple of
+// maj_scale, rounded UP, 0 for bricks without a record. The walk's majorant is q * maj_scale >= the brick's maximum.
+static __global__ void k_brick_maj16(const int2* __restrict__ cells, int n, float scale, unsigned short* __restrict__ out) {
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n) return;
+	float inv = __int_as_float(cells[b].y);
+	unsigned q = 0;
+	if (cells[b].x >= 0 && inv > 0) {
+		float m = 1.0f / inv;
+		q = (unsigned)ceilf(m / scale);
+		if (q < 1) q = 1;
+		while (q < 65535u && float(q) * scale < m) q++;
+		if (q > 65535u) q = 65535u;
+	}
+	out[b] = (unsigned short)q;
+}
+
+int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol) {
+	const int nb = vol.bx * vol.by * vol.bz;
+	cudaStream_t st = ctx->stream;
+	unsigned short* d = nullptr;
+	NE_CUDA_OK(cudaMallocAsync(&d, std::max(1, nb) * sizeof(unsigned short), st));
+	ctx->sceneAllocs.push_back(d);
+	// 65535 * scale exceeds the global maximum by a few ulps, so the largest brick majorant is still bounded from above
+	vol.maj_scale = vol.max_density > 0 ? vol.max_density * (1.0f / 65535.0f) * 1.000001f : 1.0f;
+	if (nb > 0) {
+		k_brick_maj16<<<(nb + 255) / 256, 256, 0, st>>>(vol.cells, nb, vol.maj_scale, d);
+		ctx->kernelLaunches++;
+		NE_CUDA_OK(cudaGetLastError());
+	}
+	vol.maj16 = d;
+	return NE_B200_OK;
+}
+
 }  // namespace ne

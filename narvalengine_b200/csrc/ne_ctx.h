@@ -56,4 +56,5 @@ void wavefront_free(ne_b200_ctx* ctx);
 // ne_bricks.cu
 int scratch_reserve(ne_b200_ctx* ctx, size_t bytes);
 int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out);
+int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol);  // DVolume::maj16 / maj_scale from the cells
 }  // namespace ne

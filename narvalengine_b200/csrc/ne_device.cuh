@@ -364,7 +364,8 @@ NE_D void hit_to_wcs(const DInstance& in, int i, Hit& hit) {
 // DEFER = true (the persistent trace kernels, SceneTrace below): a mesh whose bounding box the ray enters is NOT
 // traversed here; the call returns false with `deferred` set and the OCS ray in `rayO`, the caller walks the BVH at its
 // own pace and completes the instance with mesh_accept + hit_to_wcs.
-template <bool DEFER>
+enum { ISECT_FULL = 0, ISECT_DEFER = 1, ISECT_NOMESH = 2 };  // ISECT_NOMESH: the scene has no mesh (the host checked): no BVH code is compiled in
+template <int DEFER>
 NE_D bool instance_intersect_t(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st, bool& deferred, Ray& rayO) {
 	const DInstance& in = s.inst[i];
 	if (!in.collision) return false;
@@ -380,7 +381,8 @@ NE_D bool instance_intersect_t(const DScene& s, int i, Ray rayW, Hit& hit, float
 		const DMesh& m = s.mesh[in.mesh];
 		float tn, tf; V3 nn, hp;
 		if (!aabb_intersect(V3(m.bbmin[0], m.bbmin[1], m.bbmin[2]), V3(m.bbmax[0], m.bbmax[1], m.bbmax[2]), ray, tn, tf, nn, hp)) return false;
-		if (DEFER) {
+		if (DEFER == ISECT_NOMESH) return false;
+		if (DEFER == ISECT_DEFER) {
 			deferred = true;
 			rayO = ray;
 			return false;
@@ -435,7 +437,7 @@ NE_D bool instance_intersect_t(const DScene& s, int i, Ray rayW, Hit& hit, float
 NE_D bool instance_intersect(const DScene& s, int i, Ray rayW, Hit& hit, float tMin, float& tMax, bool in_lights, Stats& st) {
 	bool deferred;
 	Ray rayO;
-	return instance_intersect_t<false>(s, i, rayW, hit, tMin, tMax, in_lights, st, deferred, rayO);
+	return instance_intersect_t<ISECT_FULL>(s, i, rayW, hit, tMin, tMax, in_lights, st, deferred, rayO);
 }
 
 // Scene::intersectScene, core/Scene.cpp:30-56: sequential fold, instancedModels then lights, tMax shrinks on
@@ -445,6 +447,18 @@ NE_D bool intersect_scene(const DScene& s, Ray ray, Hit& hit, float tMin, float 
 	hit.inst = -1;
 	for (int i = 0; i < s.n_inst; i++) {
 		bool th = instance_intersect(s, i, ray, hit, tMin, tMax, i >= s.n_models, st);
+		did = did || th;
+	}
+	return did;
+}
+// intersect_scene for a scene the host knows to hold no triangle mesh.
+NE_D bool intersect_scene_nomesh(const DScene& s, Ray ray, Hit& hit, float tMin, float tMax, Stats& st) {
+	bool did = false;
+	hit.inst = -1;
+	for (int i = 0; i < s.n_inst; i++) {
+		bool deferred;
+		Ray rayO;
+		bool th = instance_intersect_t<ISECT_NOMESH>(s, i, ray, hit, tMin, tMax, i >= s.n_models, st, deferred, rayO);
 		did = did || th;
 	}
 	return did;
@@ -480,7 +494,7 @@ struct SceneTrace {
 	NE_D bool fold(const DScene& s, int* stack, Stats& st) {
 		while (i < s.n_inst) {
 			bool deferred = false;
-			bool th = instance_intersect_t<true>(s, i, rayW, hit, tMin, tMax, i >= s.n_models, st, deferred, rayO);
+			bool th = instance_intersect_t<ISECT_DEFER>(s, i, rayW, hit, tMin, tMax, i >= s.n_models, st, deferred, rayO);
 			if (deferred) {
 				inv = bvh_inv_dir(rayO);
 				sp = 0;

@@ -26,6 +26,10 @@ struct DVolume {
 	int n_slots;
 	const int2* cells;
 	const float* pool;
+	// per-brick majorant as a 16-bit multiple of maj_scale, rounded UP (any bound >= the brick's maximum keeps tracking
+	// unbiased): 2 bytes per brick, so the table a walk consults at every brick crossing stays in L1 (64 KB for 256^3)
+	const unsigned short* maj16;
+	float maj_scale;
 	float max_density, inv_max_density;  // GridMedia::invMaxDensity, GridMedia.cpp:12
 };
 

@@ -60,23 +60,27 @@ template <>
 struct Tracker<true> {
 	const int2* __restrict__ cells;
 	const float* __restrict__ pool;
+	const unsigned short* __restrict__ maj16;
+	float majScale;
 	int nbx, nby, nbz;
 	V3 g0, gd;      // grid-space ray g(t) = g0 + t * gd
 	float t, tFar;
 	float tExit;    // where the ray leaves the current brick (clipped to tFar)
 	float sig;      // sigma_bar per unit density per unit t
 	float invSig;
-	float invMaj;   // 1 / majorant of the current brick, 0 = nothing to collide with
+	float majQ;     // majorant of the current brick (the 16-bit upper bound), 0 = nothing to collide with
+	float invMaj;   // 1 / majQ, set when a candidate is proposed
 	float sigMaj;   // sigma_bar x majorant of the current brick: optical depth per unit t (0 in an empty brick)
 	float tau;      // optical depth left before the next candidate
 	float cap;      // scratch of wants_candidate(): optical depth of the rest of the current brick
-	int slot;       // record of the current brick
 	BrickDDA dda;
 
 	template <class W>
 	NE_D void init(const DVolume& v, const DMaterial& m, Ray rayOCS, float tStart, float tEnd, W& wr, Stats& st) {
 		cells = v.cells;
 		pool = v.pool;
+		maj16 = v.maj16;
+		majScale = v.maj_scale;
 		nbx = v.bx; nby = v.by; nbz = v.bz;
 		V3 res(float(v.W), float(v.H), float(v.D));
 		g0 = (rayOCS.o + V3(0.5f)) * res;
@@ -92,12 +96,12 @@ struct Tracker<true> {
 		tau = exp_variate(wr);
 	}
 	NE_D V3 point(float tt) const { return V3(fmaf(gd.x, tt, g0.x), fmaf(gd.y, tt, g0.y), fmaf(gd.z, tt, g0.z)); }
+	// A brick crossing reads TWO BYTES: the brick's majorant from the compact table (L1-resident; the 8-byte
+	// {slot, 1/majorant} cells it replaced on this path were an L2 round trip per crossing, the walk's critical path).
 	NE_D void enter_brick(Stats& st) {
 		st.brick_visits++;
-		int2 c = __ldg(cells + (dda.bz * nby + dda.by) * nbx + dda.bx);
-		slot = c.x;
-		invMaj = __int_as_float(c.y);
-		sigMaj = invMaj > 0 ? sig * __fdividef(1.0f, invMaj) : 0.0f;
+		majQ = float(__ldg(maj16 + (dda.bz * nby + dda.by) * nbx + dda.bx)) * majScale;
+		sigMaj = sig * majQ;
 		tExit = fminf(dda.exit_t(), tFar);
 	}
 	template <class W>
@@ -113,8 +117,11 @@ struct Tracker<true> {
 		enter_brick(st);
 		return TRACK_MOVED;
 	}
+	// Only a candidate needs the brick's record: its slot is looked up here (majQ > 0, so the brick has one).
 	NE_D float candidate_density(const DVolume&) {
+		invMaj = __fdividef(1.0f, majQ);
 		t = fmaf(tau * invSig, invMaj, t);
+		int slot = __ldg(&cells[(dda.bz * nby + dda.by) * nbx + dda.bx].x);
 		return brick_density(pool, slot, point(t), dda.bx, dda.by, dda.bz);
 	}
 	template <class W>
