@@ -124,7 +124,12 @@ int scratch_reserve(ne_b200_ctx* ctx, size_t bytes) {
 // Buffers larger than the staging cap go in rounds.
 int h2d_staged(ne_b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
 	const size_t CH = size_t(4) << 20, CAP = size_t(256) << 20;
-	if (bytes < 2 * CH) {
+	// a caller that already holds the data in page-locked memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch
+	// tensor) gets one direct DMA: no staging copy at all
+	cudaPointerAttributes attr{};
+	const bool srcPinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();  // an unregistered host pointer is not an error here
+	if (bytes < 2 * CH || srcPinned) {
 		NE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 		return NE_B200_OK;
 	}
