@@ -522,11 +522,13 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 			r.dim = rng.dim;
 			if (FUSE) {
 				Hit h2;
+				const uint32_t prims0 = st.prim_tests;
 				bool did = intersect_scene_nomesh(S, r.ps.ray, h2, float(NE_EPSILON12), INFINITY, st);
 				int kind = classify_hit(S, did, h2, r.ps, sink);
 				const bool grid = kind == HIT_VOLUME && S.mat[S.inst[h2.inst].material].volume >= 0;
 				if (kind == HIT_VOLUME && !grid) {
 					// a HomogeneousMedia hit belongs in the scatter queue, which this kernel is draining: leave it to k_wf_extend
+					st.prim_tests = prims0;  // k_wf_extend will count the query
 					store_path(b, slot, r);
 					b.qNext[warp_push(&b.c->next)] = slot;
 					continue;

@@ -59,6 +59,97 @@ def test_wavefront_equals_megakernel(ctx, name, monkeypatch):
     np.testing.assert_allclose(a, m, rtol=2e-4, atol=1e-5 * float(m.mean()))
 
 
+COUNTED = ("paths", "extend_rays", "shadow_rays", "bvh_nodes", "tri_tests", "prim_tests", "delta_steps", "ratio_steps", "brick_visits",
+           "scatter_events", "surface_events")
+
+
+def render_counted(ctx, b, cam, W, H, spp, **kw):
+    ctx.upload(b)  # counters_reset needs a scene on some paths; upload first, then reset
+    ctx.counters_reset()
+    img = render(ctx, b, cam, W, H, spp, **kw)
+    c = ctx.counters()
+    return img, {k: int(getattr(c, k)) for k in COUNTED}
+
+
+@pytest.mark.parametrize("name", ["mesh", "mixed"])
+def test_persistent_trace_kernels_equal_grid_stride_kernels(ctx, name, monkeypatch):
+    """k_wf_trace (extend / shadow / trfind as jobs over the resumable SceneTrace, the default with meshes) must trace
+    exactly the rays the grid-stride kernels trace, node for node and triangle for triangle: equal counters, images
+    equal up to the order of fp32 splats. A tiny walk budget and refill threshold force many cut-and-resumed walks."""
+    mk, cam = CASES[name]
+    b = mk()
+    W, H, spp = 96, 64, 8
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    monkeypatch.setenv("NE_B200_TRACE", "0")
+    ref, cref = render_counted(ctx, b, cam, W, H, spp)
+    assert cref["bvh_nodes"] > 0 and cref["tri_tests"] > 0
+    for budget, refill in (("24", "12"), ("1", "1"), ("3", "31")):
+        monkeypatch.setenv("NE_B200_TRACE", "1")
+        monkeypatch.setenv("NE_B200_WALK_BUDGET", budget)
+        monkeypatch.setenv("NE_B200_WALK_REFILL", refill)
+        img, c = render_counted(ctx, b, cam, W, H, spp)
+        assert c == cref, (budget, refill)
+        np.testing.assert_allclose(img, ref, rtol=2e-4, atol=1e-5 * float(ref.mean()))
+
+
+@pytest.mark.parametrize("name", ["volume", "cornell", "homogeneous", "directional"])
+def test_fused_scatter_equals_separate_extend(ctx, name, monkeypatch):
+    """In mesh-free scenes k_wf_scatter traces and classifies its own continuation ray (NE_B200_FUSE, default on):
+    same rays, same events, same image as the trip through k_wf_extend."""
+    mk, cam = CASES[name]
+    b = mk()
+    W, H, spp = 96, 64, 8
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    monkeypatch.setenv("NE_B200_FUSE", "0")
+    ref, cref = render_counted(ctx, b, cam, W, H, spp)
+    monkeypatch.setenv("NE_B200_FUSE", "1")
+    img, c = render_counted(ctx, b, cam, W, H, spp)
+    assert c == cref
+    np.testing.assert_allclose(img, ref, rtol=2e-4, atol=1e-5 * float(ref.mean()))
+
+
+def test_trace_kernels_on_a_mesh_free_scene(ctx, monkeypatch):
+    """NE_B200_TRACE=1 forced where there is no BVH: the jobs' folds finish without ever walking."""
+    mk, cam = CASES["volume"]
+    b = mk()
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    monkeypatch.setenv("NE_B200_FUSE", "0")
+    monkeypatch.setenv("NE_B200_TRACE", "0")
+    ref, cref = render_counted(ctx, b, cam, 64, 48, 8)
+    monkeypatch.setenv("NE_B200_TRACE", "1")
+    img, c = render_counted(ctx, b, cam, 64, 48, 8)
+    assert c == cref
+    np.testing.assert_allclose(img, ref, rtol=2e-4, atol=1e-5 * float(ref.mean()))
+
+
+def test_upload_from_pinned_memory_equals_pageable(ctx):
+    """ne_b200_scene_upload takes a page-locked grid by one direct DMA and a pageable one through its staging buffer:
+    same bricks either way (grid large enough for the staged path, >= 8 MiB)."""
+    import torch
+    grid = scenes.cloud_density((160, 128, 128), seed=3)  # 10 MiB
+    assert grid.nbytes >= 8 << 20
+    pinned_t = torch.from_numpy(grid.copy()).pin_memory()
+    import ctypes as C
+
+    def read_bricks():
+        dims, mx = (C.c_int32 * 4)(), C.c_float()
+        assert ctx.lib.ne_b200_test_read_bricks(ctx.h, 0, dims, None, None, None, C.byref(mx)) == 0
+        bx, by, bz, slots = list(dims)
+        t, inv, pool = np.zeros((bz, by, bx), np.int32), np.zeros((bz, by, bx), np.float32), np.zeros((max(slots, 1), 729), np.float32)
+        assert ctx.lib.ne_b200_test_read_bricks(ctx.h, 0, dims, t.ctypes.data_as(abi.pi32), inv.ctypes.data_as(abi.pf32),
+                                                pool.ctypes.data_as(abi.pf32), None) == 0
+        return [list(dims), np.float32(mx.value), t, inv.view(np.uint32), pool.view(np.uint32)]
+
+    out = []
+    for g in (grid, pinned_t.numpy()):
+        b = scenes.noise_volume_scene(res=(160, 128, 128), density=40.0, light="rect", grid=g)
+        ctx.upload(b)
+        out.append(read_bricks())
+    assert out[0][0][3] > 0
+    for x, y in zip(out[0], out[1]):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+
+
 def test_sample_ranges_are_additive(ctx):
     """Philox keyed (seed, pixel, sample): rendering [0,4)+[4,8) equals [0,8) (sample-index partition across GPUs)."""
     b = scenes.cornell_c1()
