@@ -571,6 +571,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 		if ((rc = push_alloc(ctx, cells.data(), cells.size(), &o.cells))) return rc;
 		if ((rc = push_alloc(ctx, hb.pool.data(), hb.pool.size(), &o.pool))) return rc;
 	}
+	ctx->skipWorthwhile = false;
 	for (DVolume& o : vols)
 		if ((rc = device_build_majorants(ctx, o))) return rc;
 

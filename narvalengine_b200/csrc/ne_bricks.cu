@@ -5,6 +5,7 @@
 // The result is bit-identical to the host builder ne_b200_host_build_bricks (ne_host.cpp), which stays the
 // inspectable definition and serves leaf (.vdb) input; tests/test_gpu_parity.py compares the two.
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -218,35 +219,98 @@ int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out)
 	return NE_B200_OK;
 }
 
-// The 2-byte majorant table the tracking walks read at every brick crossing: q = the brick's majorant as a multiple of
-// maj_scale, rounded UP, 0 for bricks without a record. The walk's majorant is q * maj_scale >= the brick's maximum.
+// The 2-byte table the tracking walks read at every brick crossing.
+//   brick with a record:  q in [1, 32767] = its majorant as a multiple of maj_scale, rounded UP (the walk's majorant
+//                         q * maj_scale bounds the brick's maximum from above: tracking stays unbiased)
+//   empty brick:          0x8000 | d, d = Chebyshev distance (in bricks, capped at NE_SKIP_MAX) to the nearest brick with
+//                         a record OR to the outside of the table: every brick closer than d is empty and inside, so a
+//                         walk standing here may cross the whole (2d-1)^3 cube in one move (BrickDDA::jump)
+#define NE_SKIP_MAX 16
 static __global__ void k_brick_maj16(const int2* __restrict__ cells, int n, float scale, unsigned short* __restrict__ out) {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= n) return;
 	float inv = __int_as_float(cells[b].y);
-	unsigned q = 0;
+	unsigned q = 0x8001u;
 	if (cells[b].x >= 0 && inv > 0) {
 		float m = 1.0f / inv;
 		q = (unsigned)ceilf(m / scale);
 		if (q < 1) q = 1;
-		while (q < 65535u && float(q) * scale < m) q++;
-		if (q > 65535u) q = 65535u;
+		while (q < 32767u && float(q) * scale < m) q++;
+		if (q > 32767u) q = 32767u;
 	}
 	out[b] = (unsigned short)q;
+}
+// One relaxation of the distance field: d_i(c) = min(NE_SKIP_MAX, 1 + min over the 26 neighbours of d_{i-1}), with d = 0
+// for bricks with a record and for the outside. Started from d_0 = 1, i iterations give min(true distance, i + 1).
+static __global__ void k_brick_skip(const unsigned short* __restrict__ in, unsigned short* __restrict__ out, int nbx, int nby, int nbz) {
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nbx * nby * nbz) return;
+	unsigned short v = in[b];
+	if (!(v & 0x8000u)) { out[b] = v; return; }
+	int x = b % nbx, y = (b / nbx) % nby, z = b / (nbx * nby);
+	unsigned best = NE_SKIP_MAX;
+	for (int dz = -1; dz <= 1; dz++)
+		for (int dy = -1; dy <= 1; dy++)
+			for (int dx = -1; dx <= 1; dx++) {
+				int xx = x + dx, yy = y + dy, zz = z + dz;
+				unsigned d = 0;
+				if (unsigned(xx) < unsigned(nbx) && unsigned(yy) < unsigned(nby) && unsigned(zz) < unsigned(nbz)) {
+					unsigned short w = in[(zz * nby + yy) * nbx + xx];
+					d = (w & 0x8000u) ? (w & 0x7fffu) : 0u;
+				}
+				best = min(best, d);
+			}
+	out[b] = (unsigned short)(0x8000u | min(unsigned(NE_SKIP_MAX), best + 1));
+}
+
+// Short skips cost more than the bricks they save (the jump is ~40 instructions and the warp's other lanes wait for
+// it): distances below `minD` are stored as 1 = "no skip".
+static __global__ void k_brick_skip_floor(unsigned short* __restrict__ t, int n, unsigned minD, unsigned* __restrict__ nSkippable) {
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	bool far = false;
+	if (b < n) {
+		unsigned short v = t[b];
+		far = (v & 0x8000u) && (v & 0x7fffu) >= minD;
+		if ((v & 0x8000u) && !far) t[b] = (unsigned short)0x8001u;
+	}
+	unsigned m = __ballot_sync(0xffffffffu, far);
+	if ((threadIdx.x & 31) == 0 && m) atomicAdd(nSkippable, (unsigned)__popc(m));
 }
 
 int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol) {
 	const int nb = vol.bx * vol.by * vol.bz;
 	cudaStream_t st = ctx->stream;
-	unsigned short* d = nullptr;
+	unsigned short *d = nullptr, *tmp = nullptr;
 	NE_CUDA_OK(cudaMallocAsync(&d, std::max(1, nb) * sizeof(unsigned short), st));
 	ctx->sceneAllocs.push_back(d);
-	// 65535 * scale exceeds the global maximum by a few ulps, so the largest brick majorant is still bounded from above
-	vol.maj_scale = vol.max_density > 0 ? vol.max_density * (1.0f / 65535.0f) * 1.000001f : 1.0f;
+	// 32767 * scale exceeds the global maximum by a few ulps, so the largest brick majorant is still bounded from above
+	vol.maj_scale = vol.max_density > 0 ? vol.max_density * (1.0f / 32767.0f) * 1.000001f : 1.0f;
 	if (nb > 0) {
-		k_brick_maj16<<<(nb + 255) / 256, 256, 0, st>>>(vol.cells, nb, vol.maj_scale, d);
-		ctx->kernelLaunches++;
+		NE_CUDA_OK(cudaMallocAsync(&tmp, nb * sizeof(unsigned short), st));
+		const unsigned grid = unsigned((nb + 255) / 256);
+		// an odd number of relaxations, so the last one lands in `d`
+		k_brick_maj16<<<grid, 256, 0, st>>>(vol.cells, nb, vol.maj_scale, tmp);
+		unsigned short *src = tmp, *dst = d;
+		for (int i = 0; i < NE_SKIP_MAX - 1; i++) {
+			k_brick_skip<<<grid, 256, 0, st>>>(src, dst, vol.bx, vol.by, vol.bz);
+			std::swap(src, dst);
+		}
+		const char* e = getenv("NE_B200_SKIP_MIN");  // smallest cube radius worth a jump (>= NE_SKIP_MAX: no skipping at all)
+		const unsigned minR = e ? unsigned(strtoul(e, nullptr, 10)) : 2u;
+		unsigned* dCount = nullptr;
+		NE_CUDA_OK(cudaMallocAsync(&dCount, sizeof(unsigned), st));
+		NE_CUDA_OK(cudaMemsetAsync(dCount, 0, sizeof(unsigned), st));
+		k_brick_skip_floor<<<grid, 256, 0, st>>>(d, nb, minR + 1, dCount);
+		ctx->kernelLaunches += NE_SKIP_MAX + 1;
 		NE_CUDA_OK(cudaGetLastError());
+		unsigned nSkippable = 0;
+		NE_CUDA_OK(cudaMemcpyAsync(&nSkippable, dCount, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+		NE_CUDA_OK(cudaStreamSynchronize(st));
+		NE_CUDA_OK(cudaFreeAsync(dCount, st));
+		NE_CUDA_OK(cudaFreeAsync(tmp, st));
+		// the skipping variant of the tracking kernels costs ~4 % where there is little to skip (C2: 17.3 vs 16.6 ms) and
+		// saves 20-25 % on a WDAS-scale sparse cloud: use it when a third of the table is far from any density
+		if (double(nSkippable) >= 0.33 * double(nb)) ctx->skipWorthwhile = true;
 	}
 	vol.maj16 = d;
 	return NE_B200_OK;

@@ -32,6 +32,7 @@ struct ne_b200_ctx {
 	ne::DScene scene{};
 	bool haveScene = false;
 	int nVolumes = 0;
+	bool skipWorthwhile = false;  // some volume's brick table is mostly skippable empty space (ne_bricks.cu device_build_majorants)
 	int nMeshes = 0;  // triangle meshes with a BVH: the wavefront then runs its persistent trace kernels
 	ne::DCamera cam{};
 	bool haveCamera = false;

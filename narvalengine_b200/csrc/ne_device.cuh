@@ -739,6 +739,24 @@ struct BrickDDA {
 		nz += cz ? dz : 0.0f;
 		return (unsigned(bx) < unsigned(nbx)) & (unsigned(by) < unsigned(nby)) & (unsigned(bz) < unsigned(nbz));
 	}
+	// Empty-space skip: every brick within Chebyshev distance r of the current one is empty (and inside the table). Move
+	// the DDA, in one go, to the LAST brick the ray visits inside that cube, so that exit_t() is where it leaves the cube
+	// and the next step() crosses the cube's face. Per axis the ray crosses at most r boundaries before that moment:
+	// the exit axis exactly r (its (r+1)-th crossing IS the exit), the others as many as lie before the exit time.
+	NE_D void jump(int r, V3 gd) {
+		const float fr = float(r);
+		const float tx = fmaf(fr, dx, nx), ty = fmaf(fr, dy, ny), tz = fmaf(fr, dz, nz);  // inf for an axis-parallel ray
+		const float tc = fminf(tx, fminf(ty, tz));
+		int kx = nx <= tc ? min(r, int(__fdividef(tc - nx, dx)) + 1) : 0;
+		int ky = ny <= tc ? min(r, int(__fdividef(tc - ny, dy)) + 1) : 0;
+		int kz = nz <= tc ? min(r, int(__fdividef(tc - nz, dz)) + 1) : 0;
+		bx += gd.x > 0 ? kx : -kx;
+		by += gd.y > 0 ? ky : -ky;
+		bz += gd.z > 0 ? kz : -kz;
+		nx = kx ? fmaf(float(kx), dx, nx) : nx;
+		ny = ky ? fmaf(float(ky), dy, ny) : ny;
+		nz = kz ? fmaf(float(kz), dz, nz) : nz;
+	}
 };
 
 }  // namespace ne

@@ -23,11 +23,14 @@ enum { TRACK_END = 0, TRACK_CANDIDATE = 1, TRACK_BUDGET = 2, TRACK_MOVED = 3 };
 template <class W>
 NE_D float exp_variate(W& wr) { return -logf(1 - wr.next()); }
 
-template <bool BRICKMAJ>
+// MODE 0 (= false): the reference's global-majorant walk. 1 (= true): per-brick majorants. 2: per-brick majorants + empty-space
+// skipping (TRACK_SKIP; the wavefront's tracking kernels pick it for sparse tables, see wavefront_render).
+enum { TRACK_GLOBAL = 0, TRACK_BRICK = 1, TRACK_SKIP = 2 };
+template <int MODE>
 struct Tracker;
 
 template <>
-struct Tracker<false> {
+struct Tracker<TRACK_GLOBAL> {
 	Ray ray;  // OCS
 	float t, tFar;
 	float sig;     // sigma_bar per unit density = avg(extinction * densityMultiplier)
@@ -56,8 +59,8 @@ struct Tracker<false> {
 	NE_D void after_candidate(W&) {}
 };
 
-template <>
-struct Tracker<true> {
+template <int MODE>
+struct BrickTracker {
 	const int2* __restrict__ cells;
 	const float* __restrict__ pool;
 	const unsigned short* __restrict__ maj16;
@@ -98,10 +101,16 @@ struct Tracker<true> {
 	NE_D V3 point(float tt) const { return V3(fmaf(gd.x, tt, g0.x), fmaf(gd.y, tt, g0.y), fmaf(gd.z, tt, g0.z)); }
 	// A brick crossing reads TWO BYTES: the brick's majorant from the compact table (L1-resident; the 8-byte
 	// {slot, 1/majorant} cells it replaced on this path were an L2 round trip per crossing, the walk's critical path).
+	// An EMPTY brick's entry holds how far the emptiness reaches instead: the walk then crosses the whole cube of empty
+	// bricks around it in this one move (nothing happens to tau in empty space, so the walk's law is untouched).
 	NE_D void enter_brick(Stats& st) {
 		st.brick_visits++;
-		majQ = float(__ldg(maj16 + (dda.bz * nby + dda.by) * nbx + dda.bx)) * majScale;
+		const unsigned v = __ldg(maj16 + (dda.bz * nby + dda.by) * nbx + dda.bx);
+		const bool empty = (v & 0x8000u) != 0;
+		majQ = empty ? 0.0f : float(v) * majScale;
 		sigMaj = sig * majQ;
+		const int r = int(v & 0x7fffu) - 1;
+		if (MODE == TRACK_SKIP && empty && r > 0) dda.jump(r, gd);
 		tExit = fminf(dda.exit_t(), tFar);
 	}
 	template <class W>
@@ -127,9 +136,13 @@ struct Tracker<true> {
 	template <class W>
 	NE_D void after_candidate(W& wr) { tau = exp_variate(wr); }
 };
+template <>
+struct Tracker<TRACK_BRICK> : BrickTracker<TRACK_BRICK> {};
+template <>
+struct Tracker<TRACK_SKIP> : BrickTracker<TRACK_SKIP> {};
 
 // One event: TRACK_CANDIDATE (`dens` = density at the proposed collision point trk.t), TRACK_MOVED, or TRACK_END.
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int track_advance(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, float& dens, Stats& st) {
 	if (trk.wants_candidate(wr)) {
 		dens = trk.candidate_density(v);
@@ -142,7 +155,7 @@ NE_D int track_advance(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, float& d
 
 // What a candidate does to a ratio-tracking walk, with pbrt's Russian roulette (GridMedia.cpp:58-66). TRACK_END =
 // killed (Tr = 0), TRACK_MOVED = keep going.
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int ratio_candidate(Tracker<BRICKMAJ>& trk, float density, float& Tr, W& wr, Stats& st) {
 	st.ratio_steps++;
 	Tr *= 1 - fmaxf(0.0f, density * trk.invMaj);
@@ -156,7 +169,7 @@ NE_D int ratio_candidate(Tracker<BRICKMAJ>& trk, float density, float& Tr, W& wr
 	return TRACK_MOVED;
 }
 // What a candidate does to a delta-tracking walk (GridMedia.cpp:84-95). TRACK_CANDIDATE = REAL collision at trk.t.
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int delta_candidate(Tracker<BRICKMAJ>& trk, float density, W& wr, Stats& st) {
 	st.delta_steps++;
 	float ra = wr.next();
@@ -165,7 +178,7 @@ NE_D int delta_candidate(Tracker<BRICKMAJ>& trk, float density, W& wr, Stats& st
 	return TRACK_MOVED;
 }
 // One ratio-tracking event. Returns TRACK_END when the walk is over (Tr final, possibly 0 = killed), else TRACK_MOVED.
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr, Stats& st) {
 	float density;
 	int e = track_advance(v, trk, wr, density, st);
@@ -173,7 +186,7 @@ NE_D int ratio_event(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr,
 	return ratio_candidate(trk, density, Tr, wr, st);
 }
 // One delta-tracking event. TRACK_CANDIDATE = REAL collision at trk.t, TRACK_END = escaped, TRACK_MOVED = keep going.
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int delta_event(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st) {
 	float density;
 	int e = track_advance(v, trk, wr, density, st);
@@ -181,14 +194,14 @@ NE_D int delta_event(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st)
 	return delta_candidate(trk, density, wr, st);
 }
 
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int ratio_walk(const DVolume& v, Tracker<BRICKMAJ>& trk, float& Tr, W& wr, Stats& st, int budget) {
 	while (true) {
 		if (budget-- <= 0) return TRACK_BUDGET;
 		if (ratio_event<W, BRICKMAJ>(v, trk, Tr, wr, st) == TRACK_END) return TRACK_END;
 	}
 }
-template <class W, bool BRICKMAJ>
+template <class W, int BRICKMAJ>
 NE_D int delta_walk(const DVolume& v, Tracker<BRICKMAJ>& trk, W& wr, Stats& st, int budget) {
 	while (true) {
 		if (budget-- <= 0) return TRACK_BUDGET;
@@ -202,7 +215,7 @@ template <class R, bool BRICKMAJ>
 NE_D float grid_tr(const DInstance& in, const DMaterial& m, const DVolume& v, Ray rayW, float tNear, float tFar, R& rng, Stats& st) {
 	Ray ray = transform_ray(rayW, in.Mi);
 	ray.o = ray.at(tNear);
-	typename WalkRngOf<BRICKMAJ, R>::type wr;
+	typename WalkRngOf<(BRICKMAJ != 0), R>::type wr;
 	wr.start(rng);
 	Tracker<BRICKMAJ> trk;
 	trk.init(v, m, ray, 0.0f, tFar - tNear, wr, st);
@@ -229,7 +242,7 @@ NE_D V3 grid_sample(const DScene& s, const DInstance& in, const DMaterial& m, co
                     const Hit& isect, Ray& scattered, R& rng, Stats& st) {
 	scattered = incomingW;
 	Ray ray = transform_ray(incomingW, in.Mi);
-	typename WalkRngOf<BRICKMAJ, R>::type wr;
+	typename WalkRngOf<(BRICKMAJ != 0), R>::type wr;
 	wr.start(rng);
 	Tracker<BRICKMAJ> trk;
 	trk.init(v, m, ray, tNear, tFar, wr, st);  // GridMedia.cpp:79 starts at tNear; Li always passes 0

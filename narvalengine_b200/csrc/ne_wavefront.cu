@@ -386,10 +386,10 @@ struct WarpReserve {
 //                    record) and accepts or rejects it
 // A walk ends on a real collision, on leaving the medium, or after P.budget events (it then continues from the point
 // reached in the next pass), so a warp is never left with one lane grinding through a long walk while 31 idle.
-template <bool BRICKMAJ>
+template <int BRICKMAJ>  // TRACK_GLOBAL / TRACK_BRICK / TRACK_SKIP (ne_tracking.cuh)
 __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
-	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
+	typedef typename WalkRngOf<(BRICKMAJ != 0), PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->vol;
 	Stats st;
 	st.clear();
@@ -819,10 +819,10 @@ __global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfPa
 // Transmittance requests whose medium is known: ratio tracking through it (at most P.budget events per pass), splat
 // weight * Tr. Persistent warps and phases like k_wf_track; the weight and pixel are re-read from the request when the
 // walk ends.
-template <bool BRICKMAJ>
+template <int BRICKMAJ>
 __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
-	typedef typename WalkRngOf<BRICKMAJ, PhiloxRng>::type WalkRng;
+	typedef typename WalkRngOf<(BRICKMAJ != 0), PhiloxRng>::type WalkRng;
 	const uint32_t n = b.c->tr;
 	Stats st;
 	st.clear();
@@ -996,6 +996,9 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	// without meshes, k_wf_scatter traces its own continuation ray (NE_B200_FUSE=0/1 overrides)
 	const bool fuse = ctx->nMeshes == 0 && env_u32("NE_B200_FUSE", 1) != 0;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
+	// empty-space skipping in the tracking walks pays where a good part of a brick table is far from any density
+	// (ctx->skipWorthwhile, decided at upload; NE_B200_SKIP=0/1 overrides)
+	const bool skip = env_u32("NE_B200_SKIP", ctx->skipWorthwhile ? 1 : 0) != 0;
 	cudaStream_t st = ctx->stream;
 	const int G = w->gridBlocks, B = 256;
 	const int GT = w->smCount * NE_TRACK_BLOCKS;  // persistent tracking kernels: exactly the resident blocks
@@ -1042,8 +1045,9 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 			if (trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
 			else k_wf_extend<<<G, B, 0, st>>>(b, P);
 			cudaEvent_t e1 = timeStages ? ev() : nullptr;
-			if (brick) k_wf_track<true><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			else k_wf_track<false><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			if (!brick) k_wf_track<TRACK_GLOBAL><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			else if (skip) k_wf_track<TRACK_SKIP><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			else k_wf_track<TRACK_BRICK><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 			cudaEvent_t e2 = timeStages ? ev() : nullptr;
 			if (fuse) k_wf_scatter<true><<<G, B, 0, st>>>(b, P);
 			else k_wf_scatter<false><<<G, B, 0, st>>>(b, P);
@@ -1057,8 +1061,9 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 				k_wf_trfind<<<G, B, 0, st>>>(b, P);
 			}
 			cudaEvent_t e4 = timeStages ? ev() : nullptr;
-			if (brick) k_wf_tr<true><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			else k_wf_tr<false><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			if (!brick) k_wf_tr<TRACK_GLOBAL><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			else if (skip) k_wf_tr<TRACK_SKIP><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+			else k_wf_tr<TRACK_BRICK><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 			cudaEvent_t e5 = timeStages ? ev() : nullptr;
 			if (timeStages) {
 				spans.push_back({e0, e1, 0});  // extend

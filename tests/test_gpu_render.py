@@ -122,6 +122,28 @@ def test_trace_kernels_on_a_mesh_free_scene(ctx, monkeypatch):
     np.testing.assert_allclose(img, ref, rtol=2e-4, atol=1e-5 * float(ref.mean()))
 
 
+def test_empty_space_skipping_leaves_the_estimate_alone(ctx, monkeypatch):
+    """A sparse table (a small cloud in a 256^3 grid: most bricks are far from any density) switches the tracking kernels
+    to their skipping variant (TRACK_SKIP: an empty brick's table entry says how far the emptiness reaches and the walk
+    crosses that whole cube in one move). Nothing happens to a walk in empty space, so the estimate must not move: same
+    seed with and without skipping, far fewer brick visits with."""
+    grid = np.zeros((256, 256, 256), np.float32)
+    grid[96:160, 96:160, 96:160] = scenes.cloud_density((64, 64, 64), seed=5)
+    b = scenes.noise_volume_scene(res=(256, 256, 256), density=200.0, light="rect", li=(40000, 40000, 28000), grid=grid)
+    cam = scenes.CameraParams((0, 1, -6), (0, 1, 0), 45.0)
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    monkeypatch.setenv("NE_B200_SKIP", "0")
+    ref, cref = render_counted(ctx, b, cam, 48, 32, 512, seed=3)
+    monkeypatch.delenv("NE_B200_SKIP")  # the default: decided at upload from the table
+    img, c = render_counted(ctx, b, cam, 48, 32, 512, seed=3)
+    assert cref["delta_steps"] > 0 and ref.mean() > 0
+    assert c["brick_visits"] < 0.6 * cref["brick_visits"], (c["brick_visits"], cref["brick_visits"])
+    # the walks are the same up to the rounding of brick-crossing parameters: a handful of paths may decide differently
+    assert abs(luminance(img).mean() - luminance(ref).mean()) / luminance(ref).mean() < 0.005
+    assert rel_mse(img, ref) < 1e-3
+    assert abs(c["delta_steps"] - cref["delta_steps"]) < 0.01 * cref["delta_steps"]
+
+
 def test_upload_from_pinned_memory_equals_pageable(ctx):
     """ne_b200_scene_upload takes a page-locked grid by one direct DMA and a pageable one through its staging buffer:
     same bricks either way (grid large enough for the staged path, >= 8 MiB)."""
