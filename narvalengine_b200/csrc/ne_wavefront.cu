@@ -260,7 +260,7 @@ __global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
 // misses everything, or sees an emitter) never touches the pool - no slot, no record, no queue entry; only survivors
 // take a slot (from the `gen` the plan set aside; commit returns the rest) and are written ONCE, path and hit
 // together, straight into the volume / surface queue. In the C2 frame 5 of 6 camera paths miss the medium's box.
-template <int MINB>  // resident blocks per SM: 2 without meshes (no spills), 4 with (the BVH walk is latency-bound: warps in flight count)
+template <int MINB>  // resident blocks per SM: 3 without meshes, 4 with (the BVH walk is latency-bound: warps in flight count)
 __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
 	const uint32_t gen = b.c->gen;
@@ -996,6 +996,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	// without meshes, k_wf_scatter traces its own continuation ray (NE_B200_FUSE=0/1 overrides)
 	const bool fuse = ctx->nMeshes == 0 && env_u32("NE_B200_FUSE", 1) != 0;
 	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
+	const int genBlocks = int(env_u32("NE_B200_GEN_BLOCKS", trace ? 4 : 3));  // resident blocks k_wf_generate is compiled for (C2: 2: 33.9, 3: 33.2, 4: 33.6 ms)
 	// empty-space skipping in the tracking walks pays where a good part of a brick table is far from any density
 	// (ctx->skipWorthwhile, decided at upload; NE_B200_SKIP=0/1 overrides)
 	const bool skip = env_u32("NE_B200_SKIP", ctx->skipWorthwhile ? 1 : 0) != 0;
@@ -1038,7 +1039,8 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 			}
 			k_wf_plan<<<1, 1, 0, st>>>(b, w->devDone);
 			// camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
-			if (trace) k_wf_generate<NE_TRACE_BLOCKS><<<G, B, 0, st>>>(b, P);
+			if (genBlocks >= 4) k_wf_generate<4><<<G, B, 0, st>>>(b, P);
+			else if (genBlocks == 3) k_wf_generate<3><<<G, B, 0, st>>>(b, P);
 			else k_wf_generate<2><<<G, B, 0, st>>>(b, P);
 			k_wf_commit<<<1, 1, 0, st>>>(b, ctx->dCounters);
 			cudaEvent_t e0 = timeStages ? ev() : nullptr;
