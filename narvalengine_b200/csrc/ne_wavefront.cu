@@ -14,6 +14,10 @@
 //             · scatter (phase function + next-event setup) · surface (GGX shading + next-event setup)
 //             · shadow (visibilityTr requests) · trfind (intersectTr: walk through surfaces to the first medium)
 //             · tr (ratio tracking through that medium, persistent warps like track)
+//             · trace<Extend|Shadow|TrFind job> (scenes with meshes: the three ray-casting stages as persistent warps over
+//               a resumable intersectScene, so a warp is not held by its longest BVH walk)
+//             variants chosen per scene by the host: scatter<FUSE> traces its own continuation ray in mesh-free scenes;
+//             track/tr<TRACK_SKIP> cross cubes of empty bricks in one move where the brick table is sparse
 //   output    fp32 atomicAdd splats into the context's linear accumulation buffer
 //
 // The two tracking kernels stop a walk after `budget` events (brick crossings + density look-ups) and queue the
@@ -381,7 +385,7 @@ struct WarpReserve {
 //   finish + refill  (when P.refill lanes are not walking) finished walks write back the fields they changed and are
 //                    queued for the next stage; idle lanes take the next queued walks. All queue atomics of the phase
 //                    (three pushes and the fetch) are issued back to back, one L2 round trip for the lot.
-//   move             up to P.moves brick crossings per walking lane (one 8-byte cell load each, no density)
+//   move             up to P.moves brick crossings per walking lane (one 2-byte majorant load each, no density)
 //   candidate        every lane that proposed a collision point looks the density up (eight loads from one brick
 //                    record) and accepts or rejects it
 // A walk ends on a real collision, on leaving the medium, or after P.budget events (it then continues from the point
