@@ -271,11 +271,16 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	const uint32_t freeN = b.c->freeN;
 	const unsigned long long workBase = b.c->workNext;
 	const uint32_t npix = uint32_t(P.W) * uint32_t(P.H);
+	const bool tiled = (P.W % 8 == 0) && (P.H % 4 == 0);  // else the frame is walked row by row (any bijection will do: Philox is keyed by pixel)
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < gen; i += gridDim.x * blockDim.x) {
 		unsigned long long w = workBase + i;
 		uint32_t pixel = uint32_t(w % npix);
+		if (tiled) {  // a warp's 32 consecutive work items cover an 8x4 pixel tile, not a 32x1 strip: coherent camera rays
+			const uint32_t t = pixel >> 5, l = pixel & 31u, tilesX = uint32_t(P.W) >> 3;
+			pixel = ((t / tilesX) * 4u + (l >> 3)) * uint32_t(P.W) + (t % tilesX) * 8u + (l & 7u);
+		}
 		uint32_t sample = uint32_t(P.sppBegin) + uint32_t(w / npix);
 		int x = int(pixel % uint32_t(P.W)), y = int(pixel / uint32_t(P.W));
 		PhiloxRng rng;
