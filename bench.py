@@ -4,11 +4,14 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one heterogeneous 256^3 density volume (synthetic fBm cloud),
-sigma_s 1.1, sigma_a 0.01, HG g=0, density multiplier 100, scale 5 at the origin, point emitter, camera (0,0,-12) ->
-origin, vfov 45, 1920x1080, 64 spp, 6 bounces. One STEP = one whole frame (132.7 M camera paths) through the wavefront
-renderer. With N GPUs every rank holds a scene replica and renders 64 samples/pixel of its own sample-index range
-(weak scaling); the per-GPU fp32 accumulation buffers are summed onto rank 0 with one NCCL reduce inside the step.
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one heterogeneous 256^3 density volume generated with the
+reference tree's vendored FastNoise exactly as SURVEY 8d specifies (SimplexFractal, seed 1337, frequency 4/256, 5 octaves,
+remap + radial falloff; workload/c2_fastnoise_256.f32 written by tools/make_c2_density.py), sigma_s 1.1, sigma_a 0.01, HG
+g=0, density multiplier 100, scale 5 at the origin, point emitter, camera (0,0,-12) -> origin, vfov 45, 1920x1080, 64 spp,
+6 bounces. One STEP = one whole frame (132.7 M camera paths) through the wavefront renderer. With N GPUs every rank holds
+a scene replica and renders ITS SHARE of the frame's 64 samples per pixel (sample_range(rank, N, 64): STRONG scaling, the
+frame is the same at every N); the per-GPU fp32 accumulation buffers are summed onto rank 0 with one NCCL reduce inside
+the step. The weak-scaling figure (64 spp per GPU, frame of N*64) is reported beside it under "weak".
 
 Printed JSON (rank 0, one line): see README / the driver contract. `value` = device-timed render (scene resident in
 HBM); `e2e` = the same frame through ne_b200_scene_upload + ne_b200_render_frame with HOST buffers (scene H2D, frame
@@ -51,25 +54,46 @@ def pinned_like(a):
 v_keepalive = []
 
 
-def build_scene(grid_res=GRID, pin=False):
+DENSITY_FILE = os.path.join(ROOT, "workload", f"c2_fastnoise_{GRID}.f32")
+DENSITY_SOURCE = "FastNoise SimplexFractal seed 1337, 5 octaves, frequency 4/256 (SURVEY 8d C2; workload/c2_fastnoise_256.f32)"
+
+
+def load_density():
+    """The C2 density: a plain data file (git-ignored, travels with the snapshot; written by tools/make_c2_density.py from
+    the reference tree's FastNoise where that tree exists). No oracle code is loaded here."""
+    if not (os.path.exists(DENSITY_FILE) and os.path.getsize(DENSITY_FILE) == 4 * GRID ** 3):
+        raise SystemExit(f"bench.py: {DENSITY_FILE} is missing: run `python tools/make_c2_density.py` where /root/reference exists "
+                         "(__graft_entry__.build() does)")
+    return np.fromfile(DENSITY_FILE, np.float32).reshape(GRID, GRID, GRID)
+
+
+def build_scene(pin=False, transform_fn=None):
     import scenes
     t = time.time()
-    cache = os.path.join(ROOT, "build", f"bench_cloud_{grid_res}.npy")
-    if os.path.exists(cache):
-        grid = np.load(cache)
-    else:
-        grid = scenes.cloud_density((grid_res,) * 3, seed=1337)
-        try:
-            os.makedirs(os.path.dirname(cache), exist_ok=True)
-            np.save(cache, grid)
-        except OSError:
-            pass
+    grid = load_density()
     if pin:
         grid = pinned_like(grid)
-    b = scenes.noise_volume_scene(res=(grid_res,) * 3, density=100.0, light="point", scale=(5, 5, 5), pos=(0, 0, 0), li=(100, 100, 70),
-                                  grid=grid)
-    cam = scenes.CameraParams((0, 0, -12), (0, 0, 0), 45.0)
-    return b, cam, grid, time.time() - t
+    b = scenes.c2_scene(grid, transform_fn=transform_fn)
+    return b, scenes.C2_CAMERA, grid, time.time() - t
+
+
+def bench_config(world, spp):
+    """The `config` object both arms print (identical keys and values for the same N)."""
+    return {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [DEBUG spp={spp}]", "resolution": [W, H], "spp": spp, "bounces": BOUNCES,
+            "grid": [GRID] * 3, "density": DENSITY_SOURCE,
+            "partition": f"sample-index x{world} (each GPU renders its share of the {spp} spp of every pixel) + NCCL reduce" if world > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def csrc_sha16():
+    """Hash of the kernel sources: profiles carry it, so a traffic figure measured on other code is refused."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "narvalengine_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -151,11 +175,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-def cpu_reference_run(builder, cam, budget_s, threads=None):
+def cpu_reference_run(builder, cam, budget_s, threads=None, faithful=False):
     """The reference's own integrator on the host cores over a bounded, frame-covering sample of the workload:
-    every `row_step`-th row of the 1080p frame at `spp` samples. Returns (Mpaths/s, description, cores)."""
+    every `row_step`-th row of the 1080p frame at `spp` samples. Returns (Mpaths/s, description, cores).
+    faithful: the build with the reference's RNG exactly as shipped (one racy global mt19937) instead of the
+    thread-local patch (SURVEY 8d asks for both; speed-ups are quoted against the faster one)."""
     from refclient import RefOracle
-    oracle = RefOracle()
+    oracle = RefOracle(faithful=faithful)
     threads = threads or os.cpu_count() or 1
     sc = oracle.scene(builder)
     # pilot to size the sample: every 90th row (12 rows) x 1 spp
@@ -174,19 +200,23 @@ def cpu_reference_run(builder, cam, budget_s, threads=None):
 def run_reference(args, rank):
     if rank != 0:
         return
-    b, cam, _, _ = build_scene()
+    from refclient import RefOracle
+    # the scene's transforms come from the oracle itself (getTransform + glm::inverse): the product library is not loaded here
+    b, cam, _, _ = build_scene(transform_fn=RefOracle().transform_fn())
     vals, ms, sample, cores = [], [], "", 0
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        v, sample, cores = cpu_reference_run(b, cam, budget_s=args.ref_seconds)
+        v, sample, cores = cpu_reference_run(b, cam, budget_s=args.ref_seconds, faithful=args.cpu_faithful)
         if i >= args.warmup:
             vals.append(v)
             ms.append((time.time() - t0) * 1e3)
     value = float(np.mean(vals))
+    kind = "reference"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": bench_config(args.gpus, args.spp),
+            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample,
+                             "rng": "as shipped (one racy global mt19937)" if args.cpu_faithful else "thread_local patch of the global mt19937"},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -200,6 +230,8 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per reference step / cpu_baseline sample")
     ap.add_argument("--spp", type=int, default=SPP, help="debug only: a value other than 64 is not the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-faithful", action="store_true", help="CPU legs use the reference build with its RNG as shipped (racy global mt19937)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling measurement at N > 1")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -234,64 +266,108 @@ def main():
     frame = PartitionedFrame(ctx, alias_accum(ctx, local_rank), rank, world, dist if world > 1 else None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def step(i):
-        """One frame: this rank's 64 samples per pixel of the world*64 the frame holds (weak scaling), then the one
-        exchange step of the path: the sum of the per-GPU accumulation buffers onto rank 0 (NCCL reduce)."""
-        frame.render(W, H, world * spp, BOUNCES, seed=1 + i)
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    sync_all()
-    ctx.counters_reset()
+    def timed(step_fn, n_steps, n_warm):
+        """n_warm untimed steps, then exactly n_steps timed ones: L2 flushed and every rank synchronised (barrier +
+        cudaDeviceSynchronize) before each, CUDA events on the render stream around each, max over ranks of the sum."""
+        for i in range(n_warm):
+            step_fn(i)
+        sync_all()
+        ctx.counters_reset()
+        ms = []
+        for i in range(n_steps):
+            flush.fill_(i & 0xff)  # L2 flush between timed iterations (outside the timed bracket)
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn(n_warm + i)
+            e1.record(stream)
+            sync_all()
+            ms.append(e0.elapsed_time(e1))
+        total = float(sum(ms))
+        if world > 1:
+            t = torch.tensor([total], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, ctx.counters()
+
+    def step(i):
+        """One frame: this rank's share of the frame's 64 samples per pixel (strong scaling: the same frame at every N),
+        then the one exchange step of the path: the sum of the per-GPU accumulation buffers onto rank 0 (NCCL reduce)."""
+        frame.render(W, H, spp, BOUNCES, seed=1 + i)
+
+    def step_weak(i):
+        frame.render(W, H, world * spp, BOUNCES, seed=1 + i)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = []
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)  # L2 flush between timed iterations (outside the timed bracket)
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step(args.warmup + i)
-        e1.record(stream)
-        sync_all()
-        ms.append(e0.elapsed_time(e1))
+    total_ms, c = timed(step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    c = ctx.counters()
-    total_ms = float(sum(ms))
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    paths_per_step = W * H * spp * world
+    paths_per_step = W * H * spp
     value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    gpu_launches = int(c.kernel_launches)
+    stage_ms = {"volume": c.ms_volume_kernel, "extend_shadow": c.ms_extend_kernel, "shade": c.ms_shade_kernel, "generate_plan": c.ms_other_kernel,
+                "render": c.ms_render}
+    counters = {k: int(getattr(c, k)) for k in ("paths", "extend_rays", "shadow_rays", "delta_steps", "ratio_steps", "brick_visits",
+                                                  "scatter_events", "wavefront_iterations")}
 
-    # ---- roofline of the volume-tracking kernels (this rank), live CUDA-event time inside the library
-    steps_tracked = int(c.delta_steps + c.ratio_steps)
-    alg_bytes = steps_tracked * int(c.bytes_per_tracking_step)
+    weak = None
+    if world > 1 and not args.no_weak:
+        wk_ms, _ = timed(step_weak, args.steps, 1)
+        weak = {"value": W * H * spp * world * args.steps / (wk_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": wk_ms / args.steps,
+                "spp_per_gpu": spp, "note": "secondary: 64 spp per GPU, frame of N*64 spp"}
+
+    # ---- roofline of the volume-tracking kernels (this rank). The timed region above runs the production path (one CUDA graph
+    # per frame; its per-stage device times are %globaltimer stamps between the stages). The kernel time the roofline uses
+    # comes from CUDA EVENTS on the render stream: the same kernels launched by the host-driven loop (NE_B200_HOST_LOOP=1)
+    # over the same number of steps of the same workload; the graph's own figure is reported beside it.
+    os.environ["NE_B200_HOST_LOOP"] = "1"
+    ev_ms, ce = timed(step, args.steps, 1)
+    del os.environ["NE_B200_HOST_LOOP"]
+    steps_tracked = int(ce.delta_steps + ce.ratio_steps)
+    alg_bytes = steps_tracked * int(ce.bytes_per_tracking_step)
     peak, peak_src = measured_peak()
-    achieved = alg_bytes / (c.ms_volume_kernel * 1e-3) / 1e9 if c.ms_volume_kernel > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    achieved = alg_bytes / (ce.ms_volume_kernel * 1e-3) / 1e9 if ce.ms_volume_kernel > 0 else 0.0
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if tj.get("csrc_sha16") == csrc_sha16():
+                traffic = tj.get("dram_bytes_per_launch")
+            else:
+                traffic_note = f"profiles/r02_traffic.json was measured on other kernel sources ({tj.get('csrc_sha16')} != {csrc_sha16()}): not reported"
         except (OSError, ValueError):
             traffic = None
-    launches_volume = max(1, int(c.wavefront_iterations) * 2)
+    launches_volume = max(1, int(ce.wavefront_iterations) * 2)
+    frame_ms = ce.ms_volume_kernel + ce.ms_extend_kernel + ce.ms_shade_kernel + ce.ms_other_kernel + 1e-9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_wf_track (delta tracking) + k_wf_tr (ratio tracking)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / launches_volume, "tracking_steps_per_frame": steps_tracked / args.steps,
-                "kernel_ms_per_frame": c.ms_volume_kernel / args.steps,
-                "share_of_step": c.ms_volume_kernel / (c.ms_volume_kernel + c.ms_extend_kernel + c.ms_shade_kernel + 1e-9),
+                "kernel_ms_per_frame": ce.ms_volume_kernel / args.steps, "timer": "CUDA events on the render stream (host-driven loop over the same kernels)",
+                "kernel_ms_per_frame_in_graph": c.ms_volume_kernel / args.steps,
+                "share_of_step": ce.ms_volume_kernel / frame_ms,
+                "note": "these kernels are latency/occupancy-bound, not HBM-bound: see roofline_issue",
                 "Mrays_per_s": (c.extend_rays + c.shadow_rays) / (total_ms * 1e-3) / 1e6 * world}
-    gpu_launches = int(c.kernel_launches)
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
+    # second roofline block for the latency-bound kernels: issue-slot utilisation x lanes per instruction from the committed
+    # ncu capture of the same sources (None when the capture belongs to other code)
+    roofline_issue = None
+    ip = os.path.join(ROOT, "profiles", "r02_issue.json")
+    if os.path.exists(ip):
+        try:
+            ij = json.load(open(ip))
+            if ij.get("csrc_sha16") == csrc_sha16():
+                roofline_issue = ij.get("roofline_issue")
+        except (OSError, ValueError):
+            pass
 
     # ---- e2e: the reference-facing calls with HOST buffers (scene H2D + frame D2H inside the timed region)
     e2e = None
@@ -328,21 +404,19 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sample, cores = cpu_reference_run(b, cam_params, budget_s=args.ref_seconds)
+        v, sample, cores = cpu_reference_run(b, cam_params, budget_s=args.ref_seconds, faithful=args.cpu_faithful)
         cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample,
-               "note": "reference TUs compiled unmodified except a thread_local patch of the global mt19937 (oracle/Makefile)"}
+               "note": ("reference TUs compiled unmodified, RNG as shipped (one racy global mt19937)" if args.cpu_faithful else
+                        "reference TUs compiled unmodified except a thread_local patch of the global mt19937 (oracle/Makefile)")}
 
     if rank == 0:
+        cfg = bench_config(world, spp)
+        cfg.update({"majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 26)), "csrc_sha16": csrc_sha16()})
         line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [DEBUG spp={spp}]", "resolution": [W, H], "spp_per_gpu": spp,
-                           "bounces": BOUNCES, "grid": [GRID] * 3, "partition": f"sample-index x{world} + NCCL reduce" if world > 1 else "single GPU",
-                           "l2": "flushed between timed steps (256 MiB write)", "majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 26))},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-                "counters": {k: int(getattr(c, k)) for k in ("paths", "extend_rays", "shadow_rays", "delta_steps", "ratio_steps", "brick_visits",
-                                                              "scatter_events", "wavefront_iterations")},
-                "kernel_ms": {"volume": c.ms_volume_kernel, "extend_shadow": c.ms_extend_kernel, "surface": c.ms_shade_kernel, "render": c.ms_render}}
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfg,
+                "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+                "weak": weak, "counters": counters, "kernel_ms": stage_ms}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

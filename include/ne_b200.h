@@ -310,15 +310,18 @@ typedef struct ne_b200_counters {
 	uint64_t surface_events;      /* surface shading events */
 	uint64_t wavefront_iterations;
 	uint64_t kernel_launches;     /* CUDA kernels launched by the library */
-	double ms_render;             /* device time (CUDA events) of ne_b200_render calls */
-	double ms_volume_kernel;      /* device time of the volume tracking kernel(s) */
-	double ms_extend_kernel;
-	double ms_shade_kernel;
+	double ms_render;             /* device time of ne_b200_render calls: the sum of the stage accounts below (stamps of the
+	                                 GPU's %globaltimer between the stages of the render graph; CUDA events in the megakernel
+	                                 and with NE_B200_HOST_LOOP=1) */
+	double ms_volume_kernel;      /* device time of the volume tracking kernels (delta + ratio tracking) */
+	double ms_extend_kernel;      /* ray casting: extend, shadow, transmittance-search */
+	double ms_shade_kernel;       /* scatter + surface shading */
 	double ms_upload;             /* host wall time of the last ne_b200_scene_upload */
 	uint32_t bytes_per_tracking_step;  /* 32 B cell + 4 B brick-table entry + 4 B majorant */
 	uint32_t bytes_per_bvh_node;
 	uint32_t bytes_per_triangle;
-	uint32_t bytes_per_path_record;
+	uint32_t bytes_per_path_record;    /* sizeof the wavefront's path + hit record (one L2 line) */
+	double ms_other_kernel;       /* camera-ray generation (with the first intersectScene) + queue bookkeeping */
 } ne_b200_counters;
 int ne_b200_get_counters(ne_b200_ctx* ctx, ne_b200_counters* out);
 int ne_b200_counters_reset(ne_b200_ctx* ctx);

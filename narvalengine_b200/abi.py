@@ -78,7 +78,8 @@ class Counters(C.Structure):
                [(n, C.c_double) for n in ("ms_render", "ms_volume_kernel", "ms_extend_kernel", "ms_shade_kernel",
                                           "ms_upload")] + \
                [(n, u32) for n in ("bytes_per_tracking_step", "bytes_per_bvh_node", "bytes_per_triangle",
-                                   "bytes_per_path_record")]
+                                   "bytes_per_path_record")] + \
+               [("ms_other_kernel", C.c_double)]
 
 
 # Every symbol include/ne_b200.h declares: name -> (restype, argtypes). tests/test_abi.py checks the list

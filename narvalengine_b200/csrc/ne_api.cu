@@ -20,6 +20,9 @@ void set_error(const std::string& s) { g_err = s; }
 
 namespace {
 
+// The stream of the context a test hook runs on (set by check_ctx): hook uploads are ordered on it, like the hook's kernel.
+thread_local cudaStream_t g_hookStream = nullptr;
+
 template <class T>
 struct DevBuf {
 	T* p = nullptr;
@@ -29,12 +32,17 @@ struct DevBuf {
 		n = count;
 		return cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
 	}
+	// on the context's (non-blocking) stream: the legacy default stream the blocking cudaMemcpy uses does not order with it
 	cudaError_t upload(const T* h, size_t count) {
 		cudaError_t e = alloc(count);
 		if (e != cudaSuccess || !count) return e;
-		return cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice);
+		return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, g_hookStream);
 	}
-	cudaError_t download(T* h) const { return n ? cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost) : cudaSuccess; }
+	cudaError_t download(T* h) const {
+		if (!n) return cudaSuccess;
+		cudaError_t e = cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, g_hookStream);
+		return e != cudaSuccess ? e : cudaStreamSynchronize(g_hookStream);
+	}
 };
 
 __device__ __forceinline__ void flush_stats(const Stats& st, DCounters* c, unsigned paths) {
@@ -286,6 +294,7 @@ inline int blocks(size_t n, int bs) { return int((n + bs - 1) / bs); }
 int check_ctx(ne_b200_ctx* ctx, bool needScene) {
 	if (!ctx) { set_error("null context"); return NE_B200_ERR_INVALID; }
 	NE_CUDA_OK(cudaSetDevice(ctx->device));
+	g_hookStream = ctx->stream;
 	if (needScene && !ctx->haveScene) { set_error("no scene uploaded"); return NE_B200_ERR_STATE; }
 	return NE_B200_OK;
 }
@@ -646,6 +655,15 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	ctx->nVolumes = d->n_volumes;
 	ctx->nMeshes = int(meshes.size());
 	ctx->haveScene = true;
+	ctx->sceneGen++;
+	ctx->majTableBytes = 0;
+	ctx->l2Pool = nullptr;
+	ctx->l2PoolBytes = 0;
+	for (const DVolume& o : vols) {
+		ctx->majTableBytes += (size_t(o.bx) * o.by * o.bz * sizeof(unsigned short) + 15) & ~size_t(15);
+		const size_t pb = size_t(o.n_slots) * BRICK_VOX * sizeof(float);
+		if (pb > ctx->l2PoolBytes) { ctx->l2PoolBytes = pb; ctx->l2Pool = o.pool; }
+	}
 	ctx->msUpload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	return NE_B200_OK;
 }
@@ -677,6 +695,7 @@ int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int s
 	if (rc) return rc;
 	if (!ctx->haveCamera) { set_error("no camera set"); return NE_B200_ERR_STATE; }
 	if (width <= 0 || height <= 0 || spp_end < spp_begin || spp_begin < 0 || bounces < 0) { set_error("bad render arguments"); return NE_B200_ERR_INVALID; }
+	if (bounces > 65535) { set_error("more than 65535 bounces (the path record keeps the bounce count in 16 bits)"); return NE_B200_ERR_INVALID; }
 	if (!ctx->accum || width != ctx->W || height != ctx->H) {
 		NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->accum) cudaFree(ctx->accum);
@@ -688,8 +707,8 @@ int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int s
 		ctx->samples = 0;
 	}
 	if (spp_end == spp_begin) return NE_B200_OK;
-	NE_CUDA_OK(cudaEventRecord(ctx->evA, ctx->stream));
 	if (flags & NE_B200_RENDER_MEGAKERNEL) {
+		NE_CUDA_OK(cudaEventRecord(ctx->evA, ctx->stream));
 		int tilesX = (width + 7) / 8, tilesY = (height + 3) / 4;
 		size_t threads = size_t(tilesX) * tilesY * 32;
 		int bs = 128;
@@ -701,17 +720,17 @@ int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int s
 			                                                                  seed, ctx->dCounters);
 		ctx->kernelLaunches++;
 		NE_CUDA_OK(cudaGetLastError());
+		NE_CUDA_OK(cudaEventRecord(ctx->evB, ctx->stream));
+		NE_CUDA_OK(cudaEventSynchronize(ctx->evB));  // the debug path keeps its CUDA-event time
+		float ms = 0;
+		NE_CUDA_OK(cudaEventElapsedTime(&ms, ctx->evA, ctx->evB));
+		ctx->msRender += ms;
 	} else {
+		// asynchronous: the whole render is enqueued as one CUDA graph launch (ne_wavefront.cu); ne_b200_wait joins
 		rc = wavefront_render(ctx, spp_begin, spp_end, bounces, seed, flags);
 		if (rc) return rc;
 	}
-	NE_CUDA_OK(cudaEventRecord(ctx->evB, ctx->stream));
 	ctx->samples += spp_end - spp_begin;
-	// fold the device time of this render into the counters at the next wait
-	NE_CUDA_OK(cudaEventSynchronize(ctx->evB));
-	float ms = 0;
-	NE_CUDA_OK(cudaEventElapsedTime(&ms, ctx->evA, ctx->evB));
-	ctx->msRender += ms;
 	return NE_B200_OK;
 }
 
@@ -720,6 +739,16 @@ int ne_b200_wait(ne_b200_ctx* ctx) {
 	if (rc) return rc;
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	NE_CUDA_OK(cudaGetLastError());
+	if (ctx->renderPending) {
+		ctx->renderPending = false;
+		unsigned long long overflow = 0;
+		NE_CUDA_OK(cudaMemcpy(&overflow, &ctx->dCounters->overflow, sizeof(overflow), cudaMemcpyDeviceToHost));
+		if (overflow) {
+			cudaMemset(&ctx->dCounters->overflow, 0, sizeof(overflow));
+			set_error("wavefront request array overflow (internal capacity invariant violated); the frame is incomplete");
+			return NE_B200_ERR_STATE;
+		}
+	}
 	return NE_B200_OK;
 }
 
@@ -816,14 +845,22 @@ int ne_b200_get_counters(ne_b200_ctx* ctx, ne_b200_counters* out) {
 	out->paths = c.paths; out->extend_rays = c.extend_rays; out->shadow_rays = c.shadow_rays; out->delta_steps = c.delta_steps;
 	out->ratio_steps = c.ratio_steps; out->brick_visits = c.brick_visits; out->bvh_nodes = c.bvh_nodes; out->tri_tests = c.tri_tests;
 	out->prim_tests = c.prim_tests; out->scatter_events = c.scatter_events; out->surface_events = c.surface_events;
-	out->wavefront_iterations = ctx->wavefrontIterations;
-	out->kernel_launches = ctx->kernelLaunches;
-	out->ms_render = ctx->msRender; out->ms_volume_kernel = ctx->msVolume; out->ms_extend_kernel = ctx->msExtend; out->ms_shade_kernel = ctx->msShade;
+	out->wavefront_iterations = c.iterations;
+	out->kernel_launches = ctx->kernelLaunches + c.launches;
+	// host-side CUDA-event accounts (megakernel, host-driven loop) + the render graph's device-side stage accounts
+	const double ns = 1e-6;
+	out->ms_extend_kernel = ctx->msExtend + double(c.stage_ns[0]) * ns;
+	out->ms_volume_kernel = ctx->msVolume + double(c.stage_ns[1]) * ns;
+	out->ms_shade_kernel = ctx->msShade + double(c.stage_ns[2]) * ns;
+	out->ms_other_kernel = ctx->msOther + double(c.stage_ns[3]) * ns;
+	out->ms_render = ctx->msRender + double(c.stage_ns[0] + c.stage_ns[1] + c.stage_ns[2] + c.stage_ns[3]) * ns;
 	out->ms_upload = ctx->msUpload;
+	// SURVEY 8d's algorithmic figures: 8 voxels x 4 B + brick-table entry 4 B + majorant 4 B per tracking step (this
+	// layout reads 8 x 4 B + a 4-byte slot + a 2-byte majorant per brick crossing); 36 B of vertex data per triangle test
 	out->bytes_per_tracking_step = 40;
 	out->bytes_per_bvh_node = sizeof(BvhNode);
 	out->bytes_per_triangle = 36;
-	out->bytes_per_path_record = 64;
+	out->bytes_per_path_record = uint32_t(ne::wavefront_record_bytes());
 	return NE_B200_OK;
 }
 
@@ -833,7 +870,7 @@ int ne_b200_counters_reset(ne_b200_ctx* ctx) {
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	NE_CUDA_OK(cudaMemset(ctx->dCounters, 0, sizeof(DCounters)));
 	ctx->kernelLaunches = ctx->wavefrontIterations = 0;
-	ctx->msRender = ctx->msVolume = ctx->msExtend = ctx->msShade = 0;
+	ctx->msRender = ctx->msVolume = ctx->msExtend = ctx->msShade = ctx->msOther = 0;
 	return NE_B200_OK;
 }
 

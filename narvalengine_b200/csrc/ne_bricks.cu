@@ -281,7 +281,8 @@ int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol) {
 	const int nb = vol.bx * vol.by * vol.bz;
 	cudaStream_t st = ctx->stream;
 	unsigned short *d = nullptr, *tmp = nullptr;
-	NE_CUDA_OK(cudaMallocAsync(&d, std::max(1, nb) * sizeof(unsigned short), st));
+	// padded to 16 bytes: the tracking kernels copy the table to shared memory with bulk async copies (16-byte granules)
+	NE_CUDA_OK(cudaMallocAsync(&d, ((size_t(std::max(1, nb)) * sizeof(unsigned short) + 15) & ~size_t(15)) + 16, st));
 	ctx->sceneAllocs.push_back(d);
 	// 32767 * scale exceeds the global maximum by a few ulps, so the largest brick majorant is still bounded from above
 	vol.maj_scale = vol.max_density > 0 ? vol.max_density * (1.0f / 32767.0f) * 1.000001f : 1.0f;

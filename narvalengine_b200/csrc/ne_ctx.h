@@ -34,6 +34,11 @@ struct ne_b200_ctx {
 	int nVolumes = 0;
 	bool skipWorthwhile = false;  // some volume's brick table is mostly skippable empty space (ne_bricks.cu device_build_majorants)
 	int nMeshes = 0;  // triangle meshes with a BVH: the wavefront then runs its persistent trace kernels
+	unsigned long long sceneGen = 0;  // bumped by every upload: the wavefront's render graph is rebuilt when it changes
+	size_t majTableBytes = 0;  // sum of the volumes' 2-byte majorant tables, each padded to 16 bytes (shared-memory staging)
+	const void* l2Pool = nullptr;  // the largest brick pool (optional L2 persisting window, NE_B200_L2_PERSIST)
+	size_t l2PoolBytes = 0;
+	bool renderPending = false;  // an asynchronous ne_b200_render is in flight: ne_b200_wait checks its outcome
 	ne::DCamera cam{};
 	bool haveCamera = false;
 	float* accum = nullptr;  // W*H*3 fp32 radiance sums
@@ -41,7 +46,9 @@ struct ne_b200_ctx {
 	int samples = 0;
 	ne::DCounters* dCounters = nullptr;
 	unsigned long long kernelLaunches = 0, wavefrontIterations = 0;
-	double msRender = 0, msVolume = 0, msExtend = 0, msShade = 0, msUpload = 0;
+	// host-side accounts (CUDA events: megakernel, host-driven wavefront loop); the render graph's device-side accounts live
+	// in DCounters::stage_ns and are added by ne_b200_get_counters
+	double msRender = 0, msVolume = 0, msExtend = 0, msShade = 0, msOther = 0, msUpload = 0;
 	cudaEvent_t evA = nullptr, evB = nullptr;
 	ne_wavefront_state* wf = nullptr;
 	void* scratch = nullptr;  // reusable device scratch (dense grid staging of the brick builder, resolve buffers)
@@ -54,6 +61,7 @@ namespace ne {
 // ne_wavefront.cu
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags);
 void wavefront_free(ne_b200_ctx* ctx);
+size_t wavefront_record_bytes();  // sizeof the wavefront's path + hit record
 // ne_bricks.cu
 int scratch_reserve(ne_b200_ctx* ctx, size_t bytes);
 int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out);

@@ -186,10 +186,14 @@ int vol_parse(const std::string& text, int32_t dims[3], std::vector<float>* grid
 		start = endp + 1;
 		endp = first.find(' ', start);
 	}
-	if (count < 3 || res[0] < 1 || res[1] < 1 || res[2] < 1) { set_error(".vol: the first line must hold 'W H D ' (each number followed by a space)"); return NE_B200_ERR_INVALID; }
+	if (count < 3 || !(res[0] >= 1) || !(res[1] >= 1) || !(res[2] >= 1)) { set_error(".vol: the first line must hold 'W H D ' (each number followed by a space)"); return NE_B200_ERR_INVALID; }
+	// untrusted input: each side fits an int32 comfortably, and the grid cannot hold more voxels than the file has
+	// tokens (every value is at least one character and one space)
+	if (!(res[0] <= 65536.0f) || !(res[1] <= 65536.0f) || !(res[2] <= 65536.0f)) { set_error(".vol: resolution out of range (more than 65536 on a side)"); return NE_B200_ERR_INVALID; }
 	dims[0] = int32_t(res[0]); dims[1] = int32_t(res[1]); dims[2] = int32_t(res[2]);
 	if (!grid) return NE_B200_OK;
 	size_t n = size_t(dims[0]) * dims[1] * dims[2];
+	if (n > (size_t(1) << 36)) { set_error(".vol: W*H*D exceeds 2^36 voxels"); return NE_B200_ERR_INVALID; }
 	grid->assign(n, 0.0f);
 	if (l1 == std::string::npos) return NE_B200_OK;
 	size_t l2 = text.find('\n', l1 + 1);  // second line: discarded
@@ -240,6 +244,7 @@ bool png_decode(const std::string& data, int& w, int& h, std::vector<uint8_t>& r
 		o += 12 + size_t(len);
 	}
 	if (!haveHdr || w <= 0 || h <= 0) { err = "PNG without IHDR"; return false; }
+	if (w > 65536 || h > 65536 || size_t(w) * size_t(h) > (size_t(1) << 28)) { err = "PNG larger than 65536 on a side or 2^28 pixels"; return false; }
 	if (interlace) { err = "interlaced PNG is not supported"; return false; }
 	int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
 	if (!ch || (depth != 8 && depth != 16 && !(ctype == 3 || ctype == 0))) { err = "unsupported PNG colour type / depth"; return false; }
@@ -435,13 +440,19 @@ int gltf_parse(const std::string& file, const std::string& dir, std::vector<floa
 		out.comp = int(num(a, "componentType", 0));
 		size_t cs = out.comp == 5126 || out.comp == 5125 ? 4 : (out.comp == 5123 || out.comp == 5122) ? 2 : (out.comp == 5121 || out.comp == 5120) ? 1 : 0;
 		if (!out.n || !cs) return false;
-		out.count = size_t(num(a, "count", 0));
-		out.stride = size_t(num(v, "byteStride", 0));
+		// untrusted numbers: negative or huge values are rejected before they become sizes, and the bound check below is
+		// done in a form that cannot wrap around
+		const double dCount = num(a, "count", 0), dStride = num(v, "byteStride", 0), dOff = num(v, "byteOffset", 0) + num(a, "byteOffset", 0);
+		const double lim = double(data[buf].size());
+		if (!(dCount >= 0 && dCount <= lim) || !(dStride >= 0 && dStride <= 65536) || !(dOff >= 0 && dOff <= lim)) return false;
+		out.count = size_t(dCount);
+		out.stride = size_t(dStride);
 		if (!out.stride) out.stride = cs * out.n;
 		const JValue* nz = a.get("normalized");
 		out.normalized = nz && nz->kind == JValue::Bool && nz->b;
-		size_t off = size_t(num(v, "byteOffset", 0)) + size_t(num(a, "byteOffset", 0));
-		if (out.count && off + (out.count - 1) * out.stride + cs * out.n > data[buf].size()) return false;
+		size_t off = size_t(dOff);
+		const size_t elem = cs * out.n, size = data[buf].size();
+		if (out.count && (elem > size || off > size - elem || (out.count - 1) > (size - elem - off) / out.stride)) return false;
 		out.p = reinterpret_cast<const uint8_t*>(data[buf].data()) + off;
 		return true;
 	};
@@ -822,34 +833,59 @@ int build_scene(const std::string& text, const char* resources_dir, const std::s
 
 }  // namespace
 
+// No C++ exception may cross the C ABI (the caller is ctypes or the host engine: an unwinding std::bad_alloc would abort
+// the process). Every entry point that parses untrusted files or allocates runs inside this barrier.
+#define NE_GUARDED(...)                                                                                        \
+	try {                                                                                                      \
+		__VA_ARGS__                                                                                            \
+	} catch (const std::bad_alloc&) {                                                                          \
+		set_error("out of host memory");                                                                      \
+		return NE_B200_ERR_NOMEM;                                                                              \
+	} catch (const std::exception& e) {                                                                        \
+		set_error(std::string("malformed input: ") + e.what());                                               \
+		return NE_B200_ERR_INVALID;                                                                            \
+	} catch (...) {                                                                                            \
+		set_error("unknown failure");                                                                         \
+		return NE_B200_ERR_INVALID;                                                                            \
+	}
+
 extern "C" {
 
 int ne_b200_scene_file_load(const char* json_path, const char* resources_dir, ne_b200_scene_file** out) {
+	NE_GUARDED(
 	if (!json_path || !out) { set_error("null argument"); return NE_B200_ERR_INVALID; }
 	*out = nullptr;
 	std::string text;
 	if (!read_file(json_path, text)) { set_error(std::string("couldn't read ") + json_path); return NE_B200_ERR_INVALID; }
 	return build_scene(text, resources_dir, json_path, out);
+	)
 }
 int ne_b200_scene_file_parse(const char* json_text, const char* resources_dir, ne_b200_scene_file** out) {
+	NE_GUARDED(
 	if (!json_text || !out) { set_error("null argument"); return NE_B200_ERR_INVALID; }
 	*out = nullptr;
 	return build_scene(json_text, resources_dir, "<text>", out);
+	)
 }
 const ne_b200_scene_desc* ne_b200_scene_file_desc(const ne_b200_scene_file* f) { return f ? &f->desc : nullptr; }
 int ne_b200_scene_file_camera(const ne_b200_scene_file* f, ne_b200_camera* out) {
+	NE_GUARDED(
 	if (!f || !out) { set_error("null argument"); return NE_B200_ERR_INVALID; }
 	const float up[3] = {0, 1, 0};  // the JSON's up and aperture are read and ignored (Q26, SceneReader.cpp:668)
 	return ne_b200_camera_make(f->camPosition, f->camLookAt, up, f->vfov, float(f->settings.width) / float(f->settings.height), 0.0001f, f->focus, out);
+	)
 }
 int ne_b200_scene_file_settings(const ne_b200_scene_file* f, ne_b200_render_settings* out) {
+	NE_GUARDED(
 	if (!f || !out) { set_error("null argument"); return NE_B200_ERR_INVALID; }
 	*out = f->settings;
 	return NE_B200_OK;
+	)
 }
 void ne_b200_scene_file_free(ne_b200_scene_file* f) { delete f; }
 
 int ne_b200_vol_read(const char* path, int32_t dims[3], float* voxels) {
+	NE_GUARDED(
 	if (!path || !dims) { set_error("null argument"); return NE_B200_ERR_INVALID; }
 	std::string text;
 	if (!read_file(path, text)) { set_error(std::string("couldn't read the file at ") + path); return NE_B200_ERR_INVALID; }
@@ -859,8 +895,10 @@ int ne_b200_vol_read(const char* path, int32_t dims[3], float* voxels) {
 	if (rc) return rc;
 	memcpy(voxels, grid.data(), grid.size() * sizeof(float));
 	return NE_B200_OK;
+	)
 }
 int ne_b200_vol_write(const char* path, const int32_t dims[3], const float* voxels) {
+	NE_GUARDED(
 	if (!path || !dims || !voxels || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) { set_error("bad argument"); return NE_B200_ERR_INVALID; }
 	FILE* f = fopen(path, "wb");
 	if (!f) { set_error(std::string("couldn't write ") + path); return NE_B200_ERR_INVALID; }
@@ -880,9 +918,11 @@ int ne_b200_vol_write(const char* path, const int32_t dims[3], const float* voxe
 	fwrite(buf.data(), 1, buf.size(), f);
 	fclose(f);
 	return NE_B200_OK;
+	)
 }
 
 int ne_b200_image_read_png(const char* path, int32_t dims[2], uint8_t* rgba) {
+	NE_GUARDED(
 	if (!path || !dims) { set_error("null argument"); return NE_B200_ERR_INVALID; }
 	std::string data, err;
 	if (!read_file(path, data)) { set_error(std::string("couldn't read the file at ") + path); return NE_B200_ERR_INVALID; }
@@ -892,10 +932,12 @@ int ne_b200_image_read_png(const char* path, int32_t dims[2], uint8_t* rgba) {
 	dims[0] = w; dims[1] = h;
 	if (rgba) memcpy(rgba, px.data(), px.size());
 	return NE_B200_OK;
+	)
 }
 
 // saveImage(..., RGB32F, PNG, path), materials/Texture.h:48-62: clamp to [0,1], (uint8_t)(v * 255) truncation, 3 channels.
 int ne_b200_image_write_png(const char* path, int width, int height, const float* rgb) {
+	NE_GUARDED(
 	if (!path || !rgb || width <= 0 || height <= 0) { set_error("bad argument"); return NE_B200_ERR_INVALID; }
 	std::vector<uint8_t> raw((size_t(width) * 3 + 1) * height);
 	for (int y = 0; y < height; y++) {
@@ -924,11 +966,13 @@ int ne_b200_image_write_png(const char* path, int width, int height, const float
 	fwrite(out.data(), 1, out.size(), f);
 	fclose(f);
 	return NE_B200_OK;
+	)
 }
 
 // saveImage(..., EXR, path) = tinyexr SaveEXR(data, w, h, 3, /*fp16*/0, path): a single-part scanline OpenEXR file with
 // three FLOAT channels. Written uncompressed (tinyexr would zip it; the pixels any reader gets back are the same).
 int ne_b200_image_write_exr(const char* path, int width, int height, const float* rgb) {
+	NE_GUARDED(
 	if (!path || !rgb || width <= 0 || height <= 0) { set_error("bad argument"); return NE_B200_ERR_INVALID; }
 	std::vector<uint8_t> o;
 	auto put32 = [&](uint32_t x) { for (int k = 0; k < 4; k++) o.push_back(uint8_t(x >> (8 * k))); };
@@ -968,12 +1012,14 @@ int ne_b200_image_write_exr(const char* path, int width, int height, const float
 	fwrite(o.data(), 1, o.size(), f);
 	fclose(f);
 	return NE_B200_OK;
+	)
 }
 
 // OfflineEngine::coreLoop's output.ppm (core/OfflineEngine.cpp:82,119-138): "P6\nW H\n65535\n", 16-bit big-endian
 // samples, pixels written from the LAST to the first (so the file holds the frame rotated by 180 degrees), each channel
 // uint16_t(value * 65535) of the tone-mapped pixel.
 int ne_b200_image_write_ppm(const char* path, int width, int height, const float* rgb) {
+	NE_GUARDED(
 	if (!path || !rgb || width <= 0 || height <= 0) { set_error("bad argument"); return NE_B200_ERR_INVALID; }
 	FILE* f = fopen(path, "wb");
 	if (!f) { set_error(std::string("couldn't write ") + path); return NE_B200_ERR_INVALID; }
@@ -989,6 +1035,7 @@ int ne_b200_image_write_ppm(const char* path, int width, int height, const float
 	fwrite(o.data(), 1, o.size(), f);
 	fclose(f);
 	return NE_B200_OK;
+	)
 }
 
 }  // extern "C"

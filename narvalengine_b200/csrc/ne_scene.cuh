@@ -128,6 +128,9 @@ struct Hit {
 struct DCounters {
 	unsigned long long paths, extend_rays, shadow_rays, delta_steps, ratio_steps, brick_visits, bvh_nodes, tri_tests, prim_tests,
 		scatter_events, surface_events;
+	// folded in by the wavefront's last kernel (the render graph runs without the host): device time per stage kind
+	// (%globaltimer stamps between stages), iterations, kernel launches, request-array overflow flag
+	unsigned long long stage_ns[4], iterations, launches, overflow;
 };
 
 }  // namespace ne

@@ -25,7 +25,12 @@ NE_D float exp_variate(W& wr) { return -logf(1 - wr.next()); }
 
 // MODE 0 (= false): the reference's global-majorant walk. 1 (= true): per-brick majorants. 2: per-brick majorants + empty-space
 // skipping (TRACK_SKIP; the wavefront's tracking kernels pick it for sparse tables, see wavefront_render).
-enum { TRACK_GLOBAL = 0, TRACK_BRICK = 1, TRACK_SKIP = 2 };
+// 3: per-brick majorants read from a copy of the 2-byte table in SHARED memory (TRACK_BRICK_SM; the wavefront's tracking
+// kernels stage it with a bulk async copy when it fits, and point DVolume::maj16 of their staged scene at it).
+// 4: the same with empty-space skipping.
+enum { TRACK_GLOBAL = 0, TRACK_BRICK = 1, TRACK_SKIP = 2, TRACK_BRICK_SM = 3, TRACK_SKIP_SM = 4 };
+#define NE_TRACK_IS_SM(MODE) ((MODE) == TRACK_BRICK_SM || (MODE) == TRACK_SKIP_SM)
+#define NE_TRACK_IS_SKIP(MODE) ((MODE) == TRACK_SKIP || (MODE) == TRACK_SKIP_SM)
 template <int MODE>
 struct Tracker;
 
@@ -64,6 +69,7 @@ struct BrickTracker {
 	const int2* __restrict__ cells;
 	const float* __restrict__ pool;
 	const unsigned short* __restrict__ maj16;
+	uint32_t majS;  // TRACK_BRICK_SM: shared-window address of the table
 	float majScale;
 	int nbx, nby, nbz;
 	V3 g0, gd;      // grid-space ray g(t) = g0 + t * gd
@@ -83,6 +89,7 @@ struct BrickTracker {
 		cells = v.cells;
 		pool = v.pool;
 		maj16 = v.maj16;
+		if (NE_TRACK_IS_SM(MODE)) majS = uint32_t(__cvta_generic_to_shared(v.maj16));
 		majScale = v.maj_scale;
 		nbx = v.bx; nby = v.by; nbz = v.bz;
 		V3 res(float(v.W), float(v.H), float(v.D));
@@ -105,12 +112,17 @@ struct BrickTracker {
 	// bricks around it in this one move (nothing happens to tau in empty space, so the walk's law is untouched).
 	NE_D void enter_brick(Stats& st) {
 		st.brick_visits++;
-		const unsigned v = __ldg(maj16 + (dda.bz * nby + dda.by) * nbx + dda.bx);
+		unsigned v;
+		if (NE_TRACK_IS_SM(MODE)) {
+			unsigned short h;
+			asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(majS + 2u * uint32_t((dda.bz * nby + dda.by) * nbx + dda.bx)));
+			v = h;
+		} else v = __ldg(maj16 + (dda.bz * nby + dda.by) * nbx + dda.bx);
 		const bool empty = (v & 0x8000u) != 0;
 		majQ = empty ? 0.0f : float(v) * majScale;
 		sigMaj = sig * majQ;
 		const int r = int(v & 0x7fffu) - 1;
-		if (MODE == TRACK_SKIP && empty && r > 0) dda.jump(r, gd);
+		if (NE_TRACK_IS_SKIP(MODE) && empty && r > 0) dda.jump(r, gd);
 		tExit = fminf(dda.exit_t(), tFar);
 	}
 	template <class W>
@@ -140,6 +152,10 @@ template <>
 struct Tracker<TRACK_BRICK> : BrickTracker<TRACK_BRICK> {};
 template <>
 struct Tracker<TRACK_SKIP> : BrickTracker<TRACK_SKIP> {};
+template <>
+struct Tracker<TRACK_BRICK_SM> : BrickTracker<TRACK_BRICK_SM> {};
+template <>
+struct Tracker<TRACK_SKIP_SM> : BrickTracker<TRACK_SKIP_SM> {};
 
 // One event: TRACK_CANDIDATE (`dens` = density at the proposed collision point trk.t), TRACK_MOVED, or TRACK_END.
 template <class W, int BRICKMAJ>

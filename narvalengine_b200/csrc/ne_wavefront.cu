@@ -26,7 +26,10 @@
 // resident blocks): no host round trip sizes a launch; the host only polls a mapped "done" word every few iterations.
 // Every block stages the scene's instance / material / volume tables in shared memory first (stage_scene).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <string>
 #include <vector>
 
 #include "ne_ctx.h"
@@ -36,9 +39,26 @@ using namespace ne;
 
 namespace {
 
+// Per-render arguments. The renderer's launches live in a CUDA graph whose kernel parameters are fixed when it is built,
+// so what changes from one ne_b200_render to the next is written here by k_wf_init and read from global memory.
+struct WfDyn {
+	DCamera cam;
+	float* accum;
+	unsigned long long seed;
+	int sppBegin, bounces;
+};
+
+enum { STAGE_TRACE = 0, STAGE_VOLUME = 1, STAGE_SHADE = 2, STAGE_OTHER = 3, STAGE_KINDS = 4 };
+
 struct WfCounts {
-	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, genTaken, done, extHead, shHead, trfHead, pad_;
+	uint32_t extend, next, vol, volNext, volHead, scat, surf, freeN, shadow, tr, trNext, trHead, trNew0, gen, genTaken, done, extHead, shHead, trfHead;
+	uint32_t par;       // which buffer of each ping-pong pair is "current" (flipped by k_wf_plan)
+	uint32_t bump;      // slots >= bump have never been handed out: the pool needs no initialisation pass
+	uint32_t bumpBase, freeTake;  // this iteration's refill: freeTake slots off the free stack, the rest from bumpBase on
+	uint32_t overflow;  // a request array was full (cannot happen by construction; checked so it could never go unnoticed)
 	unsigned long long workNext, workTotal;
+	unsigned long long lastNs, stageNs[STAGE_KINDS], iterations, launches;
+	WfDyn dyn;
 };
 
 struct __align__(128) PathSlot {
@@ -51,26 +71,28 @@ struct __align__(128) PathSlot {
 struct WfBuf {
 	// One 128-byte record per path slot (path state + hit), so that a slot reached through a queue index - a random
 	// address - costs exactly one L2 line, every byte of it used:
-	//   path  pA=(o.xyz,d.x) pB=(d.yz,T.xy) pC=(T.z,pixel,sample,dim) pD=(bounce|guard<<8, nee, collision t, -)
+	//   path  pA=(o.xyz,d.x) pB=(d.yz,T.xy) pC=(T.z,pixel,sample,dim) pD=(bounce|guard<<16, nee, collision t, -)
 	//   hit   hA=(p.xyz,tNear) hB=(n.xyz,tFar) hC=(u,v,inst,prim)
 	PathSlot* rec;
 	// shadow request: A=(o.xyz,C.x) B=(C.yz,w.xy) C=(w.z,pixel)
 	float4 *sA, *sB;
 	float2* sC;
-	// transmittance request (current / next pass): A=(o.xyz,d.x) B=(d.yz,w.xy) C=(w.z,pixel,sample,stream)
+	// transmittance request, [par] = this pass, [par ^ 1] = next pass: A=(o.xyz,d.x) B=(d.yz,w.xy) C=(w.z,pixel,sample,stream)
 	// D=(Tr so far, remaining tFar, medium instance or -1 = not found yet, dim)
-	float4 *tA, *tB, *tC, *tD;
-	float4 *uA, *uB, *uC, *uD;
-	uint32_t *qExtend, *qNext, *qVol, *qVolNext, *qScat, *qSurf, *qFree;
+	float4 *tA[2], *tB[2], *tC[2], *tD[2];
+	// index queues; [par] = this iteration's, [par ^ 1] = the next one's
+	uint32_t *qExt[2], *qVol[2];
+	uint32_t *qScat, *qSurf, *qFree;
 	WfCounts* c;
+	// capacities: every live slot sits in exactly one stage queue and is shaded at most once per iteration, so one
+	// iteration pushes at most nSlots shadow and nSlots new transmittance requests; walks cut by the event budget are
+	// carried over only while there is room (else they simply keep walking), so trCap = nSlots + carryCap is never exceeded
+	uint32_t nSlots, shadowCap, trCap, carryCap;
 };
 
 struct WfParams {
 	DScene s;
-	DCamera cam;
-	float* accum;
-	int W, H, sppBegin, bounces, budget, refill, moves, walkBudget, walkRefill;
-	uint64_t seed;
+	int W, H, budget, refill, moves, walkBudget, walkRefill, cutAlways;
 	DCounters* counters;
 };
 
@@ -127,8 +149,8 @@ __device__ __forceinline__ PathRec load_path(const WfBuf& b, uint32_t slot) {
 	r.pixel = __float_as_uint(C.y);
 	r.sample = __float_as_uint(C.z);
 	r.dim = __float_as_uint(C.w);
-	r.ps.bounce = int(D.x & 0xff);
-	r.ps.guard = int(D.x >> 8);
+	r.ps.bounce = int(D.x & 0xffffu);  // 16 bits each: ne_b200_render rejects more than 65535 bounces
+	r.ps.guard = int(D.x >> 16);
 	r.ps.nee = D.y;
 	r.tHit = __uint_as_float(D.z);
 	return r;
@@ -137,7 +159,7 @@ __device__ __forceinline__ void store_path(const WfBuf& b, uint32_t slot, const 
 	b.rec[slot].pA = make_float4(r.ps.ray.o.x, r.ps.ray.o.y, r.ps.ray.o.z, r.ps.ray.d.x);
 	b.rec[slot].pB = make_float4(r.ps.ray.d.y, r.ps.ray.d.z, r.ps.T.x, r.ps.T.y);
 	b.rec[slot].pC = make_float4(r.ps.T.z, __uint_as_float(r.pixel), __uint_as_float(r.sample), __uint_as_float(r.dim));
-	b.rec[slot].pD = make_uint4(uint32_t(r.ps.bounce) | (uint32_t(r.ps.guard) << 8), r.ps.nee, __float_as_uint(r.tHit), 0u);
+	b.rec[slot].pD = make_uint4(uint32_t(r.ps.bounce) | (uint32_t(r.ps.guard) << 16), r.ps.nee, __float_as_uint(r.tHit), 0u);
 }
 __device__ __forceinline__ Hit load_hit(const WfBuf& b, uint32_t slot) {
 	float4 A = b.rec[slot].hA, B = b.rec[slot].hB, C = b.rec[slot].hC;
@@ -199,7 +221,7 @@ struct QueueSink {
 	float sel_pdf;
 	const WfBuf* b;
 	float* accum;
-	uint32_t pixel, sample;
+	uint32_t pixel, sample, par;
 	__device__ __forceinline__ void begin() {}
 	__device__ __forceinline__ void emit(V3 v) { splat(accum, pixel, v); }
 	__device__ __forceinline__ V3 end(float) { return V3(0.0f); }
@@ -207,6 +229,7 @@ struct QueueSink {
 		V3 w = scale * ((f * Li * weight / pdf) / sel_pdf);
 		if (is_black(w)) return;
 		uint32_t i = warp_push(&b->c->shadow);
+		if (i >= b->shadowCap) { b->c->overflow = 1u; return; }
 		b->sA[i] = make_float4(p.x, p.y, p.z, C.x);
 		b->sB[i] = make_float4(C.y, C.z, w.x, w.y);
 		b->sC[i] = make_float2(w.z, __uint_as_float(pixel));
@@ -216,47 +239,84 @@ struct QueueSink {
 		V3 w = scale * ((f * Li * weight / pdf) / sel_pdf);
 		if (is_black(w)) return;
 		uint32_t i = warp_push(&b->c->tr);
-		b->tA[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-		b->tB[i] = make_float4(ray.d.y, ray.d.z, w.x, w.y);
-		b->tC[i] = make_float4(w.z, __uint_as_float(pixel), __uint_as_float(sample), __uint_as_float(stream));
-		b->tD[i] = make_float4(1.0f, 0.0f, __int_as_float(-1), __uint_as_float(0u));
+		if (i >= b->trCap) { b->c->overflow = 1u; return; }
+		b->tA[par][i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+		b->tB[par][i] = make_float4(ray.d.y, ray.d.z, w.x, w.y);
+		b->tC[par][i] = make_float4(w.z, __uint_as_float(pixel), __uint_as_float(sample), __uint_as_float(stream));
+		b->tD[par][i] = make_float4(1.0f, 0.0f, __int_as_float(-1), __uint_as_float(0u));
 	}
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // Kernels
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_wf_init(WfBuf b, uint32_t nSlots, unsigned long long workTotal) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < nSlots) b.qFree[i] = nSlots - 1 - i;  // slot 0 is handed out first
-	if (i == 0) {
-		WfCounts c;
-		memset(&c, 0, sizeof(c));
-		c.freeN = nSlots;
-		c.workTotal = workTotal;
-		*b.c = c;
-	}
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
 }
 
-// One thread: retire the finished iteration (next -> extend, unfinished walks -> vol / tr, clear stage queues) and
-// plan the refill. The host alternates which buffer of each ping-pong pair is "current".
-__global__ void k_wf_plan(WfBuf b, volatile uint32_t* hostDone) {
+// One thread: reset the bookkeeping and take this render's arguments. The pool itself is not touched: slots are handed
+// out from a bump counter until the first ones come back through the free stack.
+__global__ void k_wf_init(WfBuf b, unsigned long long workTotal, WfDyn dyn) {
+	WfCounts c;
+	memset(&c, 0, sizeof(c));
+	c.workTotal = workTotal;
+	c.dyn = dyn;
+	c.lastNs = global_ns();
+	*b.c = c;
+}
+
+// One thread, between two stages: device time since the previous stamp goes to that stage's account.
+__global__ void k_wf_stamp(WfBuf b, int kind) {
 	WfCounts& c = *b.c;
+	unsigned long long now = global_ns();
+	c.stageNs[kind] += now - c.lastNs;
+	c.lastNs = now;
+}
+
+// One thread: retire the finished iteration (flip the ping-pong pairs: what was "next" is current now; clear the stage
+// queues) and plan the refill of the pool. Inside the render graph it also decides whether the WHILE node runs its body
+// again (cudaGraphSetConditional); the host-driven loop reads the mapped `hostDone` word instead.
+__global__ void k_wf_plan(WfBuf b, cudaGraphConditionalHandle loop, int inGraph, volatile uint32_t* hostDone, uint32_t launchesPerIteration) {
+	WfCounts& c = *b.c;
+	c.par ^= 1u;
 	c.extend = c.next;
 	c.next = 0;
 	c.vol = c.volNext;
 	c.volNext = 0;
-	c.tr = c.trNext;
-	c.trNew0 = c.trNext;  // requests pushed from here on are new: k_wf_trfind locates their medium
+	c.tr = min(c.trNext, b.carryCap);  // reservations beyond the room for carried walks were never written (k_wf_tr)
+	c.trNew0 = c.tr;  // requests pushed from here on are new: k_wf_trfind locates their medium
 	c.trNext = 0;
 	c.scat = c.surf = c.shadow = 0;
 	c.volHead = c.trHead = c.extHead = c.shHead = c.trfHead = 0;
-	unsigned long long remaining = c.workTotal - c.workNext;
-	uint32_t gen = uint32_t(remaining < c.freeN ? remaining : c.freeN);
+	const unsigned long long remaining = c.workTotal - c.workNext;
+	const unsigned long long room = (unsigned long long)c.freeN + (b.nSlots - c.bump);
+	const uint32_t gen = uint32_t(remaining < room ? remaining : room);
 	c.gen = gen;
-	c.freeN -= gen;
+	c.freeTake = gen < c.freeN ? gen : c.freeN;
+	c.freeN -= c.freeTake;
+	c.bumpBase = c.bump;
+	c.bump += gen - c.freeTake;
 	c.done = (c.extend == 0 && gen == 0 && c.vol == 0 && c.tr == 0) ? 1u : 0u;
+	if (!c.done) {
+		c.iterations++;
+		c.launches += launchesPerIteration;
+	}
 	if (hostDone) *hostDone = c.done;
+	if (inGraph) cudaGraphSetConditional(loop, c.done ? 0u : 1u);
+}
+
+// One thread, after the loop: fold this render's bookkeeping into the context's counters.
+__global__ void k_wf_finish(WfBuf b, DCounters* counters, int foldTimes) {
+	WfCounts& c = *b.c;
+	unsigned long long now = global_ns();
+	c.stageNs[STAGE_OTHER] += now - c.lastNs;
+	if (foldTimes)
+		for (int k = 0; k < STAGE_KINDS; k++) counters->stage_ns[k] += c.stageNs[k];
+	counters->iterations += c.iterations;
+	counters->launches += c.launches + 3;  // + init, the first plan, this kernel
+	if (c.overflow) counters->overflow = 1;
 }
 
 // OfflineEngine.cpp:64-67 + Li's first intersectScene (:187-193, :244-260) fused: sample jitter,
@@ -268,8 +328,13 @@ template <int MINB>  // resident blocks per SM: 3 without meshes, 4 with (the BV
 __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
 	const uint32_t gen = b.c->gen;
-	const uint32_t freeN = b.c->freeN;
+	if (gen == 0) return;
+	const uint32_t freeN = b.c->freeN, freeTake = b.c->freeTake, bumpBase = b.c->bumpBase, par = b.c->par;
 	const unsigned long long workBase = b.c->workNext;
+	const DCamera cam = b.c->dyn.cam;
+	float* const accum = b.c->dyn.accum;
+	const unsigned long long seed = b.c->dyn.seed;
+	const uint32_t sppBegin = uint32_t(b.c->dyn.sppBegin);
 	const uint32_t npix = uint32_t(P.W) * uint32_t(P.H);
 	const bool tiled = (P.W % 8 == 0) && (P.H % 4 == 0);  // else the frame is walked row by row (any bijection will do: Philox is keyed by pixel)
 	Stats st;
@@ -281,14 +346,14 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 			const uint32_t t = pixel >> 5, l = pixel & 31u, tilesX = uint32_t(P.W) >> 3;
 			pixel = ((t / tilesX) * 4u + (l >> 3)) * uint32_t(P.W) + (t % tilesX) * 8u + (l & 7u);
 		}
-		uint32_t sample = uint32_t(P.sppBegin) + uint32_t(w / npix);
+		uint32_t sample = sppBegin + uint32_t(w / npix);
 		int x = int(pixel % uint32_t(P.W)), y = int(pixel / uint32_t(P.W));
 		PhiloxRng rng;
-		rng.init(P.seed, pixel, sample);
+		rng.init(seed, pixel, sample);
 		float u = float(float(x) + rng.next()) / float(P.W);
 		float v = float(float(y) + rng.next()) / float(P.H);
 		PathRec r;
-		r.ps.ray = camera_ray(P.cam, u, v, rng);
+		r.ps.ray = camera_ray(cam, u, v, rng);
 		r.ps.T = V3(1.0f);
 		r.ps.bounce = 0;
 		r.ps.guard = 0;
@@ -301,44 +366,53 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 		st.extend_rays++;
 		bool did = intersect_scene(S, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
 		QueueSink sink;
-		sink.accum = P.accum;
+		sink.accum = accum;
 		sink.pixel = pixel;
 		int kind = classify_hit(S, did, h, r.ps, sink);
 		if (kind == HIT_TERMINATE) continue;
-		uint32_t slot = b.qFree[freeN + gen - 1 - warp_push(&b.c->genTaken)];
+		// the j-th survivor takes the j-th reserved slot: first the freeTake entries popped off the free stack, then fresh ones
+		const uint32_t j = warp_push(&b.c->genTaken);
+		const uint32_t slot = j < freeTake ? b.qFree[freeN + freeTake - 1u - j] : bumpBase + (j - freeTake);
 		store_path(b, slot, r);
 		store_hit(b, slot, h);
 		if (kind == HIT_VOLUME) {
-			if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[warp_push(&b.c->vol)] = slot;
+			if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[par][warp_push(&b.c->vol)] = slot;
 			else b.qScat[warp_push(&b.c->scat)] = slot;
 		} else b.qSurf[warp_push(&b.c->surf)] = slot;
 	}
 	flush_stats_wf(st, P.counters);
 }
-// One thread: publish the refill (after generate has read the old counts); unused reserved slots go back to the free list.
+// One thread: publish the refill (after generate has read the old counts); reserved slots no survivor took go back.
 __global__ void k_wf_commit(WfBuf b, DCounters* counters) {
 	WfCounts& c = *b.c;
-	c.freeN += c.gen - c.genTaken;
+	if (c.genTaken <= c.freeTake) {  // the untouched part of the free-stack reservation is still in place; no fresh slot was used
+		c.freeN += c.freeTake - c.genTaken;
+		c.bump = c.bumpBase;
+	} else c.bump = c.bumpBase + (c.genTaken - c.freeTake);
 	c.workNext += c.gen;
-	atomicAdd(&counters->paths, (unsigned long long)c.gen);
+	if (c.gen) atomicAdd(&counters->paths, (unsigned long long)c.gen);
 	c.gen = 0;
 	c.genTaken = 0;
+	c.freeTake = 0;
 }
 
 // Scene::intersectScene for every path of the extend queue + classify (Li :187-193, :244-260).
 __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->extend;
+	if (n == 0) return;
+	const uint32_t par = b.c->par;
+	float* const accum = b.c->dyn.accum;
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		uint32_t slot = b.qExtend[i];
+		uint32_t slot = b.qExt[par][i];
 		PathRec r = load_path(b, slot);
 		Hit h;
 		st.extend_rays++;
 		bool did = intersect_scene(S, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
 		QueueSink sink;
-		sink.accum = P.accum;
+		sink.accum = accum;
 		sink.pixel = r.pixel;
 		int kind = classify_hit(S, did, h, r.ps, sink);
 		if (kind == HIT_TERMINATE) {
@@ -347,7 +421,7 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 			store_hit(b, slot, h);
 			if (kind == HIT_VOLUME) {
 				// a grid medium is walked by k_wf_track; a HomogeneousMedia needs no walk and goes straight to k_wf_scatter
-				if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[warp_push(&b.c->vol)] = slot;
+				if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[par][warp_push(&b.c->vol)] = slot;
 				else b.qScat[warp_push(&b.c->scat)] = slot;
 			} else b.qSurf[warp_push(&b.c->surf)] = slot;
 		}
@@ -395,11 +469,66 @@ struct WarpReserve {
 //                    record) and accepts or rejects it
 // A walk ends on a real collision, on leaving the medium, or after P.budget events (it then continues from the point
 // reached in the next pass), so a warp is never left with one lane grinding through a long walk while 31 idle.
-template <int BRICKMAJ>  // TRACK_GLOBAL / TRACK_BRICK / TRACK_SKIP (ne_tracking.cuh)
-__global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(WfBuf b, WfParams P) {
-	NE_STAGE_SCENE();
-	typedef typename WalkRngOf<(BRICKMAJ != 0), PhiloxRng>::type WalkRng;
+// TRACK_*_SM variants: every block copies the 2-byte majorant tables of the scene's volumes (64 KB for a 256^3 grid) into
+// its shared memory with bulk async copies (cp.async.bulk, completion counted by an mbarrier) and points the staged
+// DVolume entries at the copy, so the one load on a walk's critical path - the majorant at every brick crossing - is a
+// shared-memory access instead of an L1/L2 round trip (18.5 % of k_wf_track's stall samples in round 1). The host picks
+// these variants when the tables fit (wavefront_render); the kernels then run ONE 1024-thread block per SM, which is
+// the same 32 warps and 64 registers per thread as four 256-thread blocks, with one copy of the table instead of four.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t maj_table_bytes(const DVolume& v) { return (uint32_t(v.bx * v.by * v.bz) * 2u + 15u) & ~15u; }
+__device__ __forceinline__ void stage_majorants(const DScene& g, SceneCache& sh, unsigned char* table, unsigned long long* bar) {
+	const uint32_t barS = smem_u32(bar);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barS), "r"(1));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t total = 0;
+		for (int i = 0; i < g.n_vol; i++) total += maj_table_bytes(g.vol[i]);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barS), "r"(total) : "memory");
+		uint32_t off = 0;
+		for (int i = 0; i < g.n_vol; i++) {
+			const uint32_t bytes = maj_table_bytes(g.vol[i]);
+			const unsigned char* src = reinterpret_cast<const unsigned char*>(g.vol[i].maj16);
+			for (uint32_t o = 0; o < bytes; o += 32768u) {
+				const uint32_t n = min(32768u, bytes - o);
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(table + off + o)),
+				             "l"(src + o), "r"(n), "r"(barS)
+				             : "memory");
+			}
+			sh.vol[i].maj16 = reinterpret_cast<const unsigned short*>(table + off);
+			off += bytes;
+		}
+	}
+	__syncthreads();  // the patched table pointers
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"NE_MAJ_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra NE_MAJ_DONE;\n"
+		"bra NE_MAJ_WAIT;\n"
+		"NE_MAJ_DONE:\n"
+		"}\n" ::"r"(barS),
+		"r"(0)
+		: "memory");
+}
+#define NE_STAGE_MAJORANTS(MODE)                                              \
+	extern __shared__ __align__(128) unsigned char majTable_[];              \
+	__shared__ unsigned long long majBar_;                                    \
+	if (NE_TRACK_IS_SM(MODE)) stage_majorants(P.s, sceneCache_, majTable_, &majBar_)
+
+template <int BRICKMAJ, int THREADS, int MINB>  // TRACK_GLOBAL / TRACK_BRICK / TRACK_SKIP / TRACK_*_SM (ne_tracking.cuh)
+__global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P) {
 	const uint32_t n = b.c->vol;
+	if (n == 0) return;
+	NE_STAGE_SCENE();
+	NE_STAGE_MAJORANTS(BRICKMAJ);
+	typedef typename WalkRngOf<(BRICKMAJ != 0), PhiloxRng>::type WalkRng;
+	const uint32_t par = b.c->par;
+	const unsigned long long seed = b.c->dyn.seed;
 	Stats st;
 	st.clear();
 	int state = L_IDLE;
@@ -418,11 +547,11 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 			// ---- finish + refill
 			const bool fin = state >= L_FIN_HIT;
 			const bool esc = state == L_FIN_END;
-			const uint32_t bg2 = bg + 256u;  // volume_escape (Li :209-213, Q1): the guard lives in bits 8..31
-			const bool dead = esc && (bg2 >> 8) > NE_MAX_NULL_SEGMENTS;
+			const uint32_t bg2 = bg + 65536u;  // volume_escape (Li :209-213, Q1): the guard lives in bits 16..31
+			const bool dead = esc && (bg2 >> 16) > NE_MAX_NULL_SEGMENTS;
 			WarpReserve rScat, rVolNext, rNext, rFree, rFetch;
 			rScat.issue(&b.c->scat, state == L_FIN_HIT);
-			rVolNext.issue(&b.c->volNext, state == L_FIN_BUDGET);
+			rVolNext.issue(&b.c->volNext, state == L_FIN_BUDGET);  // (at most one entry per live slot: cannot overflow)
 			rNext.issue(&b.c->next, esc && !dead);
 			rFree.issue(&b.c->freeN, dead);
 			rFetch.issue(&b.c->volHead, !exhausted && (state == L_IDLE || fin));
@@ -438,14 +567,14 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 					V3 o = ray.at(trk.t);
 					b.rec[slot].pA = make_float4(o.x, o.y, o.z, ray.d.x);
 					b.rec[slot].hB.w = tFar - trk.t;
-					b.qVolNext[iVolNext] = slot;
+					b.qVol[par ^ 1u][iVolNext] = slot;
 				} else if (dead) {
 					b.qFree[iFree] = slot;
 				} else {
 					V3 o = ray.at(tFar + 0.01f);  // step past the far side, same bounce
 					b.rec[slot].pA = make_float4(o.x, o.y, o.z, ray.d.x);
 					b.rec[slot].pD.x = bg2;
-					b.qNext[iNext] = slot;
+					b.qExt[par ^ 1u][iNext] = slot;
 				}
 				b.rec[slot].pC.w = __uint_as_float(rng.dim);
 				b.rec[slot].hA.w = 0.0f;
@@ -454,7 +583,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 			if (!exhausted) {
 				const uint32_t i = iFetch;
 				if (state == L_IDLE && i < n) {
-					slot = b.qVol[i];
+					slot = b.qVol[par][i];
 					float4 A = b.rec[slot].pA, B = b.rec[slot].pB, C = b.rec[slot].pC;
 					bg = b.rec[slot].pD.x;
 					float tNear = b.rec[slot].hA.w;
@@ -466,7 +595,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 					const DInstance& in = S.inst[inst];
 					const DMaterial& m = S.mat[in.material];
 					vol = &S.vol[m.volume];
-					rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(C.w));
+					rng.init(seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(C.w));
 					wr.start(rng);
 					trk.init(*vol, m, transform_ray(ray, in.Mi), 0.0f, tFar, wr, st);
 					budget = P.budget;
@@ -480,7 +609,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_track(
 #pragma unroll 1
 		for (int k = 0; k < P.moves; k++) {
 			if (state == L_MOVING) {
-				if (budget-- <= 0) state = L_FIN_BUDGET;
+				if (budget-- <= 0 && (exhausted || P.cutAlways)) state = L_FIN_BUDGET;
 				else if (trk.wants_candidate(wr)) state = L_CAND;
 				else if (trk.move(st) == TRACK_END) state = L_FIN_END;
 			}
@@ -504,6 +633,11 @@ template <bool FUSE>
 __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->scat;
+	if (n == 0) return;
+	const uint32_t par = b.c->par;
+	float* const accum = b.c->dyn.accum;
+	const unsigned long long seed = b.c->dyn.seed;
+	const int bounces = b.c->dyn.bounces;
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -511,12 +645,13 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 		PathRec r = load_path(b, slot);
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
-		rng.init(P.seed, r.pixel, r.sample, r.dim);
+		rng.init(seed, r.pixel, r.sample, r.dim);
 		QueueSink sink;
 		sink.b = &b;
-		sink.accum = P.accum;
+		sink.accum = accum;
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
+		sink.par = par;
 		int next;
 		if (S.mat[S.inst[h.inst].material].volume < 0) {
 			next = shade_volume_homog(S, r.ps, h, rng, sink, st);
@@ -525,7 +660,7 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 			next = volume_scatter(S, r.ps, h, rayO, r.tHit, rng, sink, st);
 		}
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
-		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
+		if (next == PATH_DONE || r.ps.bounce >= bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
 		} else {
 			r.dim = rng.dim;
@@ -533,13 +668,18 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 				Hit h2;
 				const uint32_t prims0 = st.prim_tests;
 				bool did = intersect_scene_nomesh(S, r.ps.ray, h2, float(NE_EPSILON12), INFINITY, st);
-				int kind = classify_hit(S, did, h2, r.ps, sink);
-				const bool grid = kind == HIT_VOLUME && S.mat[S.inst[h2.inst].material].volume >= 0;
-				if (kind == HIT_VOLUME && !grid) {
-					// a HomogeneousMedia hit belongs in the scatter queue, which this kernel is draining: leave it to k_wf_extend
+				int kind = HIT_TERMINATE;
+				const bool grid = did && h2.inst >= 0 && S.inst[h2.inst].material >= 0 && S.mat[S.inst[h2.inst].material].has_bsdf &&
+				                  S.mat[S.inst[h2.inst].material].transmissive && S.mat[S.inst[h2.inst].material].volume >= 0;
+				// only a path that goes on through a grid medium (or ends) is settled here. A HomogeneousMedia hit belongs in
+				// the scatter queue this kernel is draining, and a surface hit would be shaded a second time in this iteration
+				// (the request arrays are sized for one shading event per live slot): both take the trip through k_wf_extend
+				const bool ends = !did || is_black(r.ps.T) || (!grid && (S.inst[h2.inst].material < 0 || !S.mat[S.inst[h2.inst].material].has_bsdf));
+				if (grid || ends) kind = classify_hit(S, did, h2, r.ps, sink);
+				else {
 					st.prim_tests = prims0;  // k_wf_extend will count the query
 					store_path(b, slot, r);
-					b.qNext[warp_push(&b.c->next)] = slot;
+					b.qExt[par ^ 1u][warp_push(&b.c->next)] = slot;
 					continue;
 				}
 				st.extend_rays++;
@@ -549,12 +689,11 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 				}
 				store_path(b, slot, r);
 				store_hit(b, slot, h2);
-				if (grid) b.qVolNext[warp_push(&b.c->volNext)] = slot;
-				else b.qSurf[warp_push(&b.c->surf)] = slot;
+				b.qVol[par ^ 1u][warp_push(&b.c->volNext)] = slot;
 				continue;
 			}
 			store_path(b, slot, r);
-			b.qNext[warp_push(&b.c->next)] = slot;
+			b.qExt[par ^ 1u][warp_push(&b.c->next)] = slot;
 		}
 	}
 	flush_stats_wf(st, P.counters);
@@ -564,6 +703,11 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->surf;
+	if (n == 0) return;
+	const uint32_t par = b.c->par;
+	float* const accum = b.c->dyn.accum;
+	const unsigned long long seed = b.c->dyn.seed;
+	const int bounces = b.c->dyn.bounces;
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -571,20 +715,21 @@ __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
 		PathRec r = load_path(b, slot);
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
-		rng.init(P.seed, r.pixel, r.sample, r.dim);
+		rng.init(seed, r.pixel, r.sample, r.dim);
 		QueueSink sink;
 		sink.b = &b;
-		sink.accum = P.accum;
+		sink.accum = accum;
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
+		sink.par = par;
 		int next = shade_surface<PhiloxRng>(S, r.ps, h, rng, sink, st);
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
-		if (next == PATH_DONE || r.ps.bounce >= P.bounces) {
+		if (next == PATH_DONE || r.ps.bounce >= bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
 		} else {
 			r.dim = rng.dim;
 			store_path(b, slot, r);
-			b.qNext[warp_push(&b.c->next)] = slot;
+			b.qExt[par ^ 1u][warp_push(&b.c->next)] = slot;
 		}
 	}
 	flush_stats_wf(st, P.counters);
@@ -593,7 +738,9 @@ __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
 // visibilityTr requests: splat the weight when nothing or an emitter is hit first.
 __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
-	const uint32_t n = b.c->shadow;
+	const uint32_t n = min(b.c->shadow, b.shadowCap);
+	if (n == 0) return;
+	float* const accum = b.c->dyn.accum;
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -601,7 +748,7 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 		float2 C = b.sC[i];
 		PhiloxRng dummy;
 		float vis = visibility_tr<PhiloxRng, false, true>(S, V3(A.x, A.y, A.z), V3(A.w, B.x, B.y), dummy, st);
-		if (vis != 0) splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * vis);
+		if (vis != 0) splat(accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * vis);
 	}
 	flush_stats_wf(st, P.counters);
 }
@@ -610,11 +757,14 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 // (the request gets its instance, entry point and segment length) or nothing (the request is dropped: Li = 0).
 __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 	NE_STAGE_SCENE();
-	const uint32_t first = b.c->trNew0, n = b.c->tr;
+	const uint32_t first = b.c->trNew0, n = min(b.c->tr, b.trCap);
+	if (n <= first) return;
+	const uint32_t par = b.c->par;
+	float* const accum = b.c->dyn.accum;
 	Stats st;
 	st.clear();
 	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 A = b.tA[i], B = b.tB[i];
+		float4 A = b.tA[par][i], B = b.tB[par][i];
 		Ray ray;
 		ray.o = V3(A.x, A.y, A.z);
 		ray.d = V3(A.w, B.x, B.y);
@@ -632,14 +782,14 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 				break;
 			}
 			if (mi >= 0 && S.mat[mi].has_medium) {  // HomogeneousMedia: closed-form transmittance, nothing to walk
-				float4 C = b.tC[i];
-				splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * homog_tr(S.mat[mi], hh.tFar - hh.tNear));
+				float4 C = b.tC[par][i];
+				splat(accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * homog_tr(S.mat[mi], hh.tFar - hh.tNear));
 				break;  // inst stays -2: the request is done
 			}
 			ray.o = hh.p;
 		}
-		b.tA[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-		b.tD[i] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
+		b.tA[par][i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+		b.tD[par][i] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
 	}
 	flush_stats_wf(st, P.counters);
 }
@@ -666,9 +816,9 @@ struct ExtendJob {
 	__device__ __forceinline__ static uint32_t first(const WfBuf&) { return 0; }
 	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->extend; }
 	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
-		slot = b.qExtend[i];
+		slot = b.qExt[b.c->par][i];
 		float4 A = b.rec[slot].pA, B = b.rec[slot].pB, C = b.rec[slot].pC;
-		bounce = int(b.rec[slot].pD.x & 0xff);
+		bounce = int(b.rec[slot].pD.x & 0xffffu);
 		Ray ray;
 		ray.o = V3(A.x, A.y, A.z);
 		ray.d = V3(A.w, B.x, B.y);
@@ -683,7 +833,7 @@ struct ExtendJob {
 		ps.T = T;
 		ps.bounce = bounce;
 		QueueSink sink;
-		sink.accum = P.accum;
+		sink.accum = b.c->dyn.accum;
 		sink.pixel = pixel;
 		int kind = classify_hit(S, tr.did, tr.hit, ps, sink);
 		if (kind == HIT_TERMINATE) {
@@ -691,7 +841,7 @@ struct ExtendJob {
 		} else {
 			store_hit(b, slot, tr.hit);
 			if (kind == HIT_VOLUME) {
-				if (S.mat[S.inst[tr.hit.inst].material].volume >= 0) b.qVol[warp_push(&b.c->vol)] = slot;
+				if (S.mat[S.inst[tr.hit.inst].material].volume >= 0) b.qVol[b.c->par][warp_push(&b.c->vol)] = slot;
 				else b.qScat[warp_push(&b.c->scat)] = slot;
 			} else b.qSurf[warp_push(&b.c->surf)] = slot;
 		}
@@ -704,7 +854,7 @@ struct ShadowJob {
 	uint32_t req;
 	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->shHead; }
 	__device__ __forceinline__ static uint32_t first(const WfBuf&) { return 0; }
-	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->shadow; }
+	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return min(b.c->shadow, b.shadowCap); }
 	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
 		req = i;
 		float4 A = b.sA[i], B = b.sB[i];
@@ -723,7 +873,7 @@ struct ShadowJob {
 		if (vis) {
 			float4 B = b.sB[req];
 			float2 C = b.sC[req];
-			splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x));
+			splat(b.c->dyn.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x));
 		}
 		return false;
 	}
@@ -735,11 +885,12 @@ struct TrFindJob {
 	int seg;
 	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->trfHead; }
 	__device__ __forceinline__ static uint32_t first(const WfBuf& b) { return b.c->trNew0; }
-	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->tr - b.c->trNew0; }
+	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return min(b.c->tr, b.trCap) - b.c->trNew0; }
 	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
 		req = i;
 		seg = 0;
-		float4 A = b.tA[i], B = b.tB[i];
+		const uint32_t par = b.c->par;
+		float4 A = b.tA[par][i], B = b.tB[par][i];
 		Ray ray;
 		ray.o = V3(A.x, A.y, A.z);
 		ray.d = V3(A.w, B.x, B.y);
@@ -750,6 +901,7 @@ struct TrFindJob {
 		Ray ray = tr.rayW;
 		int inst = -2;
 		float tRemain = 0;
+		const uint32_t par = b.c->par;
 		if (tr.did) {
 			const Hit& hh = tr.hit;
 			int mi = S.inst[hh.inst].material;
@@ -758,8 +910,8 @@ struct TrFindJob {
 				ray.o = ray.at(hh.tNear);
 				tRemain = hh.tFar - hh.tNear;
 			} else if (mi >= 0 && S.mat[mi].has_medium) {  // HomogeneousMedia: closed-form transmittance, nothing to walk
-				float4 B = b.tB[req], C = b.tC[req];
-				splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * homog_tr(S.mat[mi], hh.tFar - hh.tNear));
+				float4 B = b.tB[par][req], C = b.tC[par][req];
+				splat(b.c->dyn.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * homog_tr(S.mat[mi], hh.tFar - hh.tNear));
 			} else {
 				ray.o = hh.p;
 				if (++seg < NE_MAX_TR_SEGMENTS) {  // through the surface: next segment of the same request
@@ -769,8 +921,8 @@ struct TrFindJob {
 				}
 			}
 		}
-		b.tA[req] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-		b.tD[req] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
+		b.tA[par][req] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+		b.tD[par][req] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
 		return false;
 	}
 };
@@ -781,8 +933,9 @@ struct TrFindJob {
 #endif
 template <class JOB>
 __global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfParams P) {
-	NE_STAGE_SCENE();
 	const uint32_t first = JOB::first(b), n = JOB::count(b);
+	if (n == 0) return;
+	NE_STAGE_SCENE();
 	Stats st;
 	st.clear();
 	JOB job;
@@ -828,11 +981,16 @@ __global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfPa
 // Transmittance requests whose medium is known: ratio tracking through it (at most P.budget events per pass), splat
 // weight * Tr. Persistent warps and phases like k_wf_track; the weight and pixel are re-read from the request when the
 // walk ends.
-template <int BRICKMAJ>
-__global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfBuf b, WfParams P) {
+template <int BRICKMAJ, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
+	const uint32_t n = min(b.c->tr, b.trCap);
+	if (n == 0) return;
 	NE_STAGE_SCENE();
+	NE_STAGE_MAJORANTS(BRICKMAJ);
 	typedef typename WalkRngOf<(BRICKMAJ != 0), PhiloxRng>::type WalkRng;
-	const uint32_t n = b.c->tr;
+	const uint32_t par = b.c->par;
+	const unsigned long long seed = b.c->dyn.seed;
+	float* const accum = b.c->dyn.accum;
 	Stats st;
 	st.clear();
 	int state = L_IDLE;
@@ -850,38 +1008,45 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 		unsigned walking = __ballot_sync(0xffffffffu, state == L_MOVING || state == L_CAND);
 		if (walking == 0 || (!exhausted && 32 - __popc(walking) >= P.refill)) {
 			// ---- finish + refill
-			const bool fin = state >= L_FIN_HIT;
+			// walks are cut only in the kernel's tail (or always, in test mode): no atomic is issued here otherwise
 			WarpReserve rNext, rFetch;
 			rNext.issue(&b.c->trNext, state == L_FIN_BUDGET);
+			const uint32_t iNext = rNext.get();
+			if (state == L_FIN_BUDGET && iNext >= b.carryCap) {
+				// no room to carry the walk over: it simply goes on where it stands (the budget is a scheduling device)
+				budget = P.budget;
+				state = L_MOVING;
+			}
+			const bool fin = state >= L_FIN_HIT;
 			rFetch.issue(&b.c->trHead, !exhausted && (state == L_IDLE || fin));
-			const uint32_t iNext = rNext.get(), iFetch = rFetch.get();  // warp-wide shuffles: before the lanes part ways
+			const uint32_t iFetch = rFetch.get();  // warp-wide shuffles: before the lanes part ways
 			if (fin) {
-				float4 B = b.tB[req], C = b.tC[req];
+				float4 B = b.tB[par][req], C = b.tC[par][req];
 				if (state == L_FIN_BUDGET) {
 					uint32_t j = iNext;
 					V3 o = ray.at(trk.t);
-					b.uA[j] = make_float4(o.x, o.y, o.z, ray.d.x);
-					b.uB[j] = B;
-					b.uC[j] = C;
-					b.uD[j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
+					b.tA[par ^ 1u][j] = make_float4(o.x, o.y, o.z, ray.d.x);
+					b.tB[par ^ 1u][j] = B;
+					b.tC[par ^ 1u][j] = C;
+					b.tD[par ^ 1u][j] = make_float4(Tr, tRemain - trk.t, __int_as_float(inst), __uint_as_float(rng.dim));
 				} else if (Tr != 0) {
-					splat(P.accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
+					splat(accum, __float_as_uint(C.y), V3(B.z, B.w, C.x) * V3(Tr));
 				}
 				state = L_IDLE;
 			}
 			if (!exhausted) {
 				const uint32_t i = iFetch;
 				if (state == L_IDLE && i < n) {
-					float4 D = b.tD[i];
+					float4 D = b.tD[par][i];
 					inst = __float_as_int(D.z);
 					if (inst >= 0) {  // else no medium along the ray: the request is dropped
-						float4 A = b.tA[i], B = b.tB[i], C = b.tC[i];
+						float4 A = b.tA[par][i], B = b.tB[par][i], C = b.tC[par][i];
 						req = i;
 						ray.o = V3(A.x, A.y, A.z);
 						ray.d = V3(A.w, B.x, B.y);
 						Tr = D.x;
 						tRemain = D.y;
-						rng.init(P.seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
+						rng.init(seed, __float_as_uint(C.y), __float_as_uint(C.z), __float_as_uint(D.w), __float_as_uint(C.w));
 						const DInstance& in = S.inst[inst];
 						const DMaterial& m = S.mat[in.material];
 						vol = &S.vol[m.volume];
@@ -902,7 +1067,7 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 #pragma unroll 1
 		for (int k = 0; k < P.moves; k++) {
 			if (state == L_MOVING) {
-				if (budget-- <= 0) state = L_FIN_BUDGET;
+				if (budget-- <= 0 && (exhausted || P.cutAlways)) state = L_FIN_BUDGET;
 				else if (trk.wants_candidate(wr)) state = L_CAND;
 				else if (trk.move(st) == TRACK_END) state = L_FIN_END;
 			}
@@ -919,60 +1084,246 @@ __global__ void __launch_bounds__(NE_TRACK_THREADS, NE_TRACK_BLOCKS) k_wf_tr(WfB
 
 }  // namespace
 
+// What decides which kernels one wavefront iteration launches and with which fixed parameters: the render graph is
+// rebuilt when any of it changes.
+struct WfVariant {
+	unsigned long long sceneGen;
+	int W, H;
+	int trace, fuse, brick, skip, sm, genBlocks, stamps;
+	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist;
+	uint32_t nSlots;
+};
+
 struct ne_wavefront_state {
 	WfBuf b{};
 	uint32_t nSlots = 0;
 	std::vector<void*> allocs;
-	uint32_t* hostDone = nullptr;  // pinned, mapped
+	uint32_t* hostDone = nullptr;  // pinned, mapped (host-driven loop only)
 	uint32_t* devDone = nullptr;
 	int gridBlocks = 0, smCount = 0;
+	size_t smemOptin = 0;
 	std::vector<cudaEvent_t> events;
+	// the render graph: first plan -> WHILE(not done){ one wavefront iteration; plan } -> finish
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t exec = nullptr;
+	cudaStream_t capStream = nullptr;
+	WfVariant built{};
+	bool haveGraph = false, graphBroken = false;
 };
 
 namespace ne {
 
-void wavefront_free(ne_b200_ctx* ctx) {
-	ne_wavefront_state* w = ctx->wf;
+static void graph_free(ne_wavefront_state* w) {
+	if (w->exec) cudaGraphExecDestroy(w->exec);
+	if (w->graph) cudaGraphDestroy(w->graph);
+	w->exec = nullptr;
+	w->graph = nullptr;
+	w->haveGraph = false;
+}
+
+static void wavefront_free_state(ne_wavefront_state* w) {
 	if (!w) return;
+	graph_free(w);
+	if (w->capStream) cudaStreamDestroy(w->capStream);
 	for (void* p : w->allocs) cudaFree(p);
 	if (w->hostDone) cudaFreeHost(w->hostDone);
 	for (cudaEvent_t e : w->events) cudaEventDestroy(e);
 	delete w;
+}
+
+size_t wavefront_record_bytes() { return sizeof(PathSlot); }
+
+void wavefront_free(ne_b200_ctx* ctx) {
+	wavefront_free_state(ctx->wf);
 	ctx->wf = nullptr;
 }
 
 template <class T>
-static int wf_alloc(ne_wavefront_state* w, T** p, size_t n) {
-	NE_CUDA_OK(cudaMalloc(p, n * sizeof(T)));
-	w->allocs.push_back(*p);
-	return NE_B200_OK;
+static cudaError_t wf_alloc(ne_wavefront_state* w, T** p, size_t n) {
+	cudaError_t e = cudaMalloc(p, n * sizeof(T));
+	if (e == cudaSuccess) w->allocs.push_back(*p);
+	return e;
 }
 
-static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
-	if (ctx->wf && ctx->wf->nSlots >= nSlots) return NE_B200_OK;
-	wavefront_free(ctx);
+// Builds the pool for `nSlots` path slots into a fresh state object; the context only sees it once it is complete.
+static cudaError_t wavefront_build(ne_b200_ctx* ctx, uint32_t nSlots, ne_wavefront_state** out) {
 	ne_wavefront_state* w = new ne_wavefront_state();
-	ctx->wf = w;
 	w->nSlots = nSlots;
-	int rc;
 	WfBuf& b = w->b;
-#define A(field) if ((rc = wf_alloc(w, &b.field, nSlots))) return rc;
-	A(rec) A(sA) A(sB) A(sC) A(tA) A(tB) A(tC) A(tD) A(uA) A(uB) A(uC) A(uD)
-	A(qExtend) A(qNext) A(qVol) A(qVolNext) A(qScat) A(qSurf) A(qFree)
+	b.nSlots = nSlots;
+	b.shadowCap = nSlots;
+	b.carryCap = std::max(nSlots / 4, 1u << 18);
+	b.trCap = nSlots + b.carryCap;
+	cudaError_t e = cudaSuccess;
+#define A(field, n) if (e == cudaSuccess) e = wf_alloc(w, &b.field, n);
+	A(rec, nSlots) A(sA, b.shadowCap) A(sB, b.shadowCap) A(sC, b.shadowCap)
+	for (int k = 0; k < 2; k++) {
+		A(tA[k], b.trCap) A(tB[k], b.trCap) A(tC[k], b.trCap) A(tD[k], b.trCap)
+		A(qExt[k], nSlots) A(qVol[k], nSlots)
+	}
+	A(qScat, nSlots) A(qSurf, nSlots) A(qFree, nSlots) A(c, 1)
 #undef A
-	if ((rc = wf_alloc(w, &b.c, 1))) return rc;
-	NE_CUDA_OK(cudaHostAlloc(&w->hostDone, sizeof(uint32_t), cudaHostAllocMapped));
-	NE_CUDA_OK(cudaHostGetDevicePointer(&w->devDone, w->hostDone, 0));
+	if (e == cudaSuccess) e = cudaHostAlloc(&w->hostDone, sizeof(uint32_t), cudaHostAllocMapped);
+	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&w->devDone, w->hostDone, 0);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->capStream, cudaStreamNonBlocking);
 	cudaDeviceProp prop;
-	NE_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+	if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, ctx->device);
+	if (e != cudaSuccess) {
+		wavefront_free_state(w);
+		return e;
+	}
 	w->smCount = prop.multiProcessorCount;
 	w->gridBlocks = prop.multiProcessorCount * 8;  // 148 SMs x 8 resident 256-thread blocks
-	return NE_B200_OK;
+	w->smemOptin = prop.sharedMemPerBlockOptin;
+	*out = w;
+	return cudaSuccess;
+}
+
+// A pool that does not fit (a smaller or busy GPU: the default is 64 Mi slots, ~29 GB) is retried at half the size down
+// to a floor; the renderer then simply runs more, shorter iterations.
+static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
+	if (ctx->wf && ctx->wf->nSlots >= nSlots) return NE_B200_OK;
+	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	wavefront_free(ctx);
+	const uint32_t floorSlots = std::min(nSlots, 1u << 16);
+	for (uint32_t n = nSlots;; n = std::max(floorSlots, n / 2)) {
+		ne_wavefront_state* w = nullptr;
+		cudaError_t e = wavefront_build(ctx, n, &w);
+		if (e == cudaSuccess) {
+			ctx->wf = w;
+			return NE_B200_OK;
+		}
+		cudaGetLastError();  // clear the sticky-less allocation error
+		if (e != cudaErrorMemoryAllocation || n == floorSlots) {
+			set_error(std::string("wavefront pool allocation (") + std::to_string(n) + " slots): " + cudaGetErrorString(e));
+			return e == cudaErrorMemoryAllocation ? NE_B200_ERR_NOMEM : NE_B200_ERR_CUDA;
+		}
+	}
 }
 
 static uint32_t env_u32(const char* name, uint32_t dflt) {
 	const char* e = getenv(name);
 	return e ? (uint32_t)strtoul(e, nullptr, 10) : dflt;
+}
+
+// The launches of ONE wavefront iteration on stream `st`. `stamp(kind)` closes a stage: a k_wf_stamp launch inside the
+// graph, a CUDA event in the host-driven loop.
+template <class STAMP>
+static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const WfBuf& b, const WfParams& P, const WfVariant& V, DCounters* counters,
+                             STAMP&& stamp) {
+	const int G = w->gridBlocks, B = 256;
+	const int GR = w->smCount * NE_TRACE_BLOCKS;
+	const int GT = w->smCount * NE_TRACK_BLOCKS;  // persistent tracking kernels: exactly the resident blocks
+	const int GS = w->smCount;                    // ... or one 1024-thread block per SM with the majorant tables in shared memory
+	const size_t smem = size_t(V.sm);
+	// camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
+	if (V.genBlocks >= 4) k_wf_generate<4><<<G, B, 0, st>>>(b, P);
+	else if (V.genBlocks == 3) k_wf_generate<3><<<G, B, 0, st>>>(b, P);
+	else k_wf_generate<2><<<G, B, 0, st>>>(b, P);
+	k_wf_commit<<<1, 1, 0, st>>>(b, counters);
+	stamp(STAGE_OTHER);
+	if (V.trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
+	else k_wf_extend<<<G, B, 0, st>>>(b, P);
+	stamp(STAGE_TRACE);
+	if (!V.brick) k_wf_track<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+	else if (V.sm && V.skip) k_wf_track<TRACK_SKIP_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+	else if (V.sm) k_wf_track<TRACK_BRICK_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+	else if (V.skip) k_wf_track<TRACK_SKIP, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+	else k_wf_track<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+	stamp(STAGE_VOLUME);
+	if (V.fuse) k_wf_scatter<true><<<G, B, 0, st>>>(b, P);
+	else k_wf_scatter<false><<<G, B, 0, st>>>(b, P);
+	k_wf_surface<<<G, B, 0, st>>>(b, P);
+	stamp(STAGE_SHADE);
+	if (V.trace) {
+		k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
+		k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
+	} else {
+		k_wf_shadow<<<G, B, 0, st>>>(b, P);
+		k_wf_trfind<<<G, B, 0, st>>>(b, P);
+	}
+	stamp(STAGE_TRACE);
+	if (!V.brick) k_wf_tr<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+	else if (V.sm && V.skip) k_wf_tr<TRACK_SKIP_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+	else if (V.sm) k_wf_tr<TRACK_BRICK_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+	else if (V.skip) k_wf_tr<TRACK_SKIP, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+	else k_wf_tr<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+	stamp(STAGE_VOLUME);
+}
+#define NE_LAUNCHES_PER_ITERATION 11u  // generate, commit, extend, track, scatter, surface, shadow, trfind, tr, plan (+ stamps, not counted)
+
+// Optional: keep the largest brick pool resident in L2 (persisting access-policy window on the launching stream; kernel
+// nodes captured from the stream inherit it) so that streaming path records cannot evict voxel data.
+static void set_l2_window(ne_b200_ctx* ctx, cudaStream_t st, bool on) {
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	if (on && ctx->l2Pool) {
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return;
+		size_t bytes = std::min<size_t>(ctx->l2PoolBytes, size_t(prop.accessPolicyMaxWindowSize));
+		size_t carve = std::min<size_t>(bytes, size_t(prop.persistingL2CacheMaxSize));
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+		v.accessPolicyWindow.base_ptr = const_cast<void*>(ctx->l2Pool);
+		v.accessPolicyWindow.num_bytes = bytes;
+		v.accessPolicyWindow.hitRatio = bytes ? float(std::min(1.0, double(carve) / double(bytes))) : 0.0f;
+		v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	}
+	cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+	cudaGetLastError();
+}
+
+// first plan -> WHILE(loop handle){ iteration; plan } -> finish, instantiated once per variant. The loop condition is set on the
+// device by k_wf_plan, so a whole render is ONE graph launch: no host round trip, no empty iteration after the last one,
+// and ne_b200_render returns while the GPU works.
+static int graph_build(ne_b200_ctx* ctx, ne_wavefront_state* w, const WfParams& P, const WfVariant& V) {
+	graph_free(w);
+	NE_CUDA_OK(cudaGraphCreate(&w->graph, 0));
+	cudaGraphConditionalHandle loop;
+	NE_CUDA_OK(cudaGraphConditionalHandleCreate(&loop, w->graph, 1, cudaGraphCondAssignDefault));
+	WfBuf b = w->b;
+	int inGraph = 1;
+	volatile uint32_t* noHost = nullptr;
+	uint32_t perIter = NE_LAUNCHES_PER_ITERATION;
+	void* planArgs[] = {&b, &loop, &inGraph, &noHost, &perIter};
+	cudaKernelNodeParams kp;
+	memset(&kp, 0, sizeof(kp));
+	kp.func = reinterpret_cast<void*>(k_wf_plan);
+	kp.gridDim = dim3(1);
+	kp.blockDim = dim3(1);
+	kp.kernelParams = planArgs;
+	cudaGraphNode_t nPlan, nLoop, nFinish;
+	NE_CUDA_OK(cudaGraphAddKernelNode(&nPlan, w->graph, nullptr, 0, &kp));
+	cudaGraphNodeParams np = {};
+	np.type = cudaGraphNodeTypeConditional;
+	np.conditional.handle = loop;
+	np.conditional.type = cudaGraphCondTypeWhile;
+	np.conditional.size = 1;
+	NE_CUDA_OK(cudaGraphAddNode(&nLoop, w->graph, &nPlan, 1, &np));
+	cudaGraph_t body = np.conditional.phGraph_out[0];
+	set_l2_window(ctx, w->capStream, V.l2persist != 0);
+	NE_CUDA_OK(cudaStreamBeginCaptureToGraph(w->capStream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+	launch_iteration(w->capStream, w, b, P, V, ctx->dCounters, [&](int kind) {
+		if (V.stamps) k_wf_stamp<<<1, 1, 0, w->capStream>>>(b, kind);
+	});
+	k_wf_plan<<<1, 1, 0, w->capStream>>>(b, loop, 1, nullptr, perIter);
+	cudaGraph_t captured = nullptr;
+	cudaError_t ce = cudaStreamEndCapture(w->capStream, &captured);
+	if (ce != cudaSuccess) {
+		set_error(std::string("render graph capture: ") + cudaGetErrorString(ce));
+		cudaGetLastError();
+		return NE_B200_ERR_CUDA;
+	}
+	DCounters* counters = ctx->dCounters;
+	int foldTimes = 1;
+	void* finArgs[] = {&b, &counters, &foldTimes};
+	kp.func = reinterpret_cast<void*>(k_wf_finish);
+	kp.kernelParams = finArgs;
+	NE_CUDA_OK(cudaGraphAddKernelNode(&nFinish, w->graph, &nLoop, 1, &kp));
+	NE_CUDA_OK(cudaGraphInstantiate(&w->exec, w->graph, 0));
+	w->built = V;
+	w->haveGraph = true;
+	return NE_B200_OK;
 }
 
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
@@ -985,35 +1336,85 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	ne_wavefront_state* w = ctx->wf;
 	nSlots = w->nSlots;
 	WfParams P;
+	memset(&P, 0, sizeof(P));
 	P.s = ctx->scene;
-	P.cam = ctx->cam;
-	P.accum = ctx->accum;
 	P.W = ctx->W;
 	P.H = ctx->H;
-	P.sppBegin = sppBegin;
-	P.bounces = bounces;
 	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
 	P.moves = int(std::max(1u, env_u32("NE_B200_TRACK_MOVES", 4)));  // brick crossings per lane between two candidate phases
 	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 20))));  // refill a warp once this many lanes are idle
 	P.walkBudget = int(std::max(1u, env_u32("NE_B200_WALK_BUDGET", 24)));  // inner-node visits per walking lane between two votes
 	P.walkRefill = int(std::min(32u, std::max(1u, env_u32("NE_B200_WALK_REFILL", 12))));  // refill a trace warp once this many lanes are not walking
-	P.seed = seed;
+	// a walk over its event budget is cut (and queued for the next pass) only once its kernel's queue has run dry, i.e. in
+	// the tail, where redistributing long walks over all SMs pays; NE_B200_TRACK_CUT_ALWAYS=1 cuts everywhere (tests)
+	P.cutAlways = env_u32("NE_B200_TRACK_CUT_ALWAYS", 0) ? 1 : 0;
 	P.counters = ctx->dCounters;
+	WfVariant V;
+	memset(&V, 0, sizeof(V));
+	V.sceneGen = ctx->sceneGen;
+	V.W = ctx->W;
+	V.H = ctx->H;
+	V.nSlots = nSlots;
 	// persistent trace kernels when there are BVHs to walk (NE_B200_TRACE=0/1 overrides)
-	const bool trace = env_u32("NE_B200_TRACE", ctx->nMeshes > 0 ? 1 : 0) != 0;
-	const int GR = w->smCount * NE_TRACE_BLOCKS;
+	V.trace = env_u32("NE_B200_TRACE", ctx->nMeshes > 0 ? 1 : 0) != 0;
 	// without meshes, k_wf_scatter traces its own continuation ray (NE_B200_FUSE=0/1 overrides)
-	const bool fuse = ctx->nMeshes == 0 && env_u32("NE_B200_FUSE", 1) != 0;
-	const bool brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
-	const int genBlocks = int(env_u32("NE_B200_GEN_BLOCKS", trace ? 4 : 3));  // resident blocks k_wf_generate is compiled for (C2: 2: 33.9, 3: 33.2, 4: 33.6 ms)
+	V.fuse = ctx->nMeshes == 0 && env_u32("NE_B200_FUSE", 1) != 0;
+	V.brick = !(flags & NE_B200_RENDER_GLOBAL_MAJORANT);
+	V.genBlocks = int(env_u32("NE_B200_GEN_BLOCKS", V.trace ? 4 : 3));  // resident blocks k_wf_generate is compiled for (C2: 2: 33.9, 3: 33.2, 4: 33.6 ms)
 	// empty-space skipping in the tracking walks pays where a good part of a brick table is far from any density
 	// (ctx->skipWorthwhile, decided at upload; NE_B200_SKIP=0/1 overrides)
-	const bool skip = env_u32("NE_B200_SKIP", ctx->skipWorthwhile ? 1 : 0) != 0;
+	V.skip = env_u32("NE_B200_SKIP", ctx->skipWorthwhile ? 1 : 0) != 0;
+	// majorant tables in shared memory when they fit beside the staged scene tables (and the scene is one stage_scene
+	// stages: NE_CACHE_* entries); V.sm holds the dynamic shared-memory bytes. NE_B200_SMEM_MAJ=0 keeps them in global memory.
+	{
+		const size_t room = w->smemOptin > sizeof(SceneCache) + 1024 ? w->smemOptin - sizeof(SceneCache) - 1024 : 0;
+		const bool staged = P.s.n_inst <= NE_CACHE_INST && P.s.n_mat <= NE_CACHE_MAT && P.s.n_vol <= NE_CACHE_VOL;
+		const bool fits = V.brick && staged && ctx->majTableBytes > 0 && ctx->majTableBytes <= room;
+		V.sm = (fits && env_u32("NE_B200_SMEM_MAJ", 1) != 0) ? int(ctx->majTableBytes) : 0;
+	}
+	V.stamps = getenv("NE_B200_NO_STAGE_TIMES") == nullptr;
+	V.budget = P.budget; V.refill = P.refill; V.moves = P.moves; V.walkBudget = P.walkBudget; V.walkRefill = P.walkRefill; V.cutAlways = P.cutAlways;
+	V.l2persist = env_u32("NE_B200_L2_PERSIST", 0) ? 1 : 0;
 	cudaStream_t st = ctx->stream;
-	const int G = w->gridBlocks, B = 256;
-	const int GT = w->smCount * NE_TRACK_BLOCKS;  // persistent tracking kernels: exactly the resident blocks
+	if (V.sm) {
+		static const void* smKernels[] = {(const void*)k_wf_track<TRACK_BRICK_SM, 1024, 1>, (const void*)k_wf_track<TRACK_SKIP_SM, 1024, 1>,
+		                                  (const void*)k_wf_tr<TRACK_BRICK_SM, 1024, 1>, (const void*)k_wf_tr<TRACK_SKIP_SM, 1024, 1>};
+		for (const void* k : smKernels) NE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, V.sm));
+	}
 
-	// event pool for per-stage device times, resolved after every host poll
+	WfDyn dyn;
+	dyn.cam = ctx->cam;
+	dyn.accum = ctx->accum;
+	dyn.seed = seed;
+	dyn.sppBegin = sppBegin;
+	dyn.bounces = bounces;
+
+	// ---- production: one graph launch, no host involvement until ne_b200_wait
+	const bool hostLoop = env_u32("NE_B200_HOST_LOOP", 0) != 0 || w->graphBroken;
+	if (!hostLoop) {
+		if (!w->haveGraph || memcmp(&w->built, &V, sizeof(V)) != 0) {
+			rc = graph_build(ctx, w, P, V);
+			if (rc) {
+				// a driver that cannot build the conditional graph still renders: host-driven loop over the same kernels
+				// (NE_B200_REQUIRE_GRAPH=1 makes it an error instead: tests)
+				fprintf(stderr, "narvalengine_b200: render graph unavailable (%s); using the host-driven loop\n", ne_b200_last_error());
+				graph_free(w);
+				cudaGetLastError();
+				if (env_u32("NE_B200_REQUIRE_GRAPH", 0)) return rc;
+				w->graphBroken = true;
+			}
+		}
+		if (w->haveGraph) {
+			k_wf_init<<<1, 1, 0, st>>>(w->b, work, dyn);
+			NE_CUDA_OK(cudaGetLastError());
+			NE_CUDA_OK(cudaGraphLaunch(w->exec, st));
+			ctx->renderPending = true;
+			return NE_B200_OK;
+		}
+	}
+
+	// ---- host-driven loop over the same kernels (NE_B200_HOST_LOOP=1: per-stage CUDA events)
+	set_l2_window(ctx, st, V.l2persist != 0);
 	size_t evUsed = 0;
 	auto ev = [&]() -> cudaEvent_t {
 		if (evUsed == w->events.size()) {
@@ -1027,64 +1428,23 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	};
 	struct Span { cudaEvent_t a, b; int kind; };
 	std::vector<Span> spans;
-	const bool timeStages = getenv("NE_B200_NO_STAGE_TIMES") == nullptr;
-
-	k_wf_init<<<(nSlots + 255) / 256, 256, 0, st>>>(w->b, nSlots, work);
-	ctx->kernelLaunches++;
+	const bool timeStages = V.stamps != 0;
+	cudaGraphConditionalHandle noLoop = 0;
+	k_wf_init<<<1, 1, 0, st>>>(w->b, work, dyn);
 	*w->hostDone = 0;
+	k_wf_plan<<<1, 1, 0, st>>>(w->b, noLoop, 0, w->devDone, NE_LAUNCHES_PER_ITERATION);
 	bool done = false;
-	unsigned long long iter = 0;
 	while (!done) {
 		// a few iterations per host poll; finished iterations cost only empty launches
 		for (int k = 0; k < 4; k++) {
-			WfBuf b = w->b;
-			if (iter & 1) {
-				std::swap(b.qExtend, b.qNext);
-				std::swap(b.qVol, b.qVolNext);
-				std::swap(b.tA, b.uA);
-				std::swap(b.tB, b.uB);
-				std::swap(b.tC, b.uC);
-				std::swap(b.tD, b.uD);
-			}
-			k_wf_plan<<<1, 1, 0, st>>>(b, w->devDone);
-			// camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
-			if (genBlocks >= 4) k_wf_generate<4><<<G, B, 0, st>>>(b, P);
-			else if (genBlocks == 3) k_wf_generate<3><<<G, B, 0, st>>>(b, P);
-			else k_wf_generate<2><<<G, B, 0, st>>>(b, P);
-			k_wf_commit<<<1, 1, 0, st>>>(b, ctx->dCounters);
-			cudaEvent_t e0 = timeStages ? ev() : nullptr;
-			if (trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
-			else k_wf_extend<<<G, B, 0, st>>>(b, P);
-			cudaEvent_t e1 = timeStages ? ev() : nullptr;
-			if (!brick) k_wf_track<TRACK_GLOBAL><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			else if (skip) k_wf_track<TRACK_SKIP><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			else k_wf_track<TRACK_BRICK><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			cudaEvent_t e2 = timeStages ? ev() : nullptr;
-			if (fuse) k_wf_scatter<true><<<G, B, 0, st>>>(b, P);
-			else k_wf_scatter<false><<<G, B, 0, st>>>(b, P);
-			k_wf_surface<<<G, B, 0, st>>>(b, P);
-			cudaEvent_t e3 = timeStages ? ev() : nullptr;
-			if (trace) {
-				k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
-				k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
-			} else {
-				k_wf_shadow<<<G, B, 0, st>>>(b, P);
-				k_wf_trfind<<<G, B, 0, st>>>(b, P);
-			}
-			cudaEvent_t e4 = timeStages ? ev() : nullptr;
-			if (!brick) k_wf_tr<TRACK_GLOBAL><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			else if (skip) k_wf_tr<TRACK_SKIP><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			else k_wf_tr<TRACK_BRICK><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-			cudaEvent_t e5 = timeStages ? ev() : nullptr;
-			if (timeStages) {
-				spans.push_back({e0, e1, 0});  // extend
-				spans.push_back({e1, e2, 1});  // delta tracking
-				spans.push_back({e2, e3, 2});  // scatter + surface shading
-				spans.push_back({e3, e4, 0});  // shadow rays
-				spans.push_back({e4, e5, 1});  // ratio tracking
-			}
-			ctx->kernelLaunches += 10;
-			iter++;
+			cudaEvent_t last = timeStages ? ev() : nullptr;
+			launch_iteration(st, w, w->b, P, V, ctx->dCounters, [&](int kind) {
+				if (!timeStages) return;
+				cudaEvent_t e = ev();
+				spans.push_back({last, e, kind});
+				last = e;
+			});
+			k_wf_plan<<<1, 1, 0, st>>>(w->b, noLoop, 0, w->devDone, NE_LAUNCHES_PER_ITERATION);
 		}
 		NE_CUDA_OK(cudaStreamSynchronize(st));
 		NE_CUDA_OK(cudaGetLastError());
@@ -1093,13 +1453,17 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 			for (const Span& s : spans) {
 				float ms = 0;
 				cudaEventElapsedTime(&ms, s.a, s.b);
-				(s.kind == 0 ? ctx->msExtend : s.kind == 1 ? ctx->msVolume : ctx->msShade) += ms;
+				(s.kind == STAGE_TRACE ? ctx->msExtend : s.kind == STAGE_VOLUME ? ctx->msVolume : s.kind == STAGE_SHADE ? ctx->msShade : ctx->msOther) += ms;
+				ctx->msRender += ms;
 			}
 			spans.clear();
 			evUsed = 0;
 		}
 	}
-	ctx->wavefrontIterations += iter;
+	// iterations, launches and the overflow flag go through the same device counters as in the graph (the stage times of this
+	// mode are the CUDA events above: the stamps were not launched, so k_wf_finish adds only the idle tail to "other")
+	k_wf_finish<<<1, 1, 0, st>>>(w->b, ctx->dCounters, 0);
+	ctx->renderPending = true;
 	return NE_B200_OK;
 }
 

@@ -73,8 +73,10 @@ class SceneBuilder:
         self.names[name] = len(self.materials) - 1
         return self.names[name]
 
-    def add_microfacet(self, name, albedo, roughness, metallic, normal_map=None, albedo_image=None):
-        """albedo: (r,g,b) -> 1x1 RGB32F clamp texture, or albedo_image=(rgba8 HxWx4 array) -> RGBA8 mirror."""
+    def add_microfacet(self, name, albedo, roughness, metallic, normal_map=None, albedo_image=None, normal_image=None):
+        """albedo: (r,g,b) -> 1x1 RGB32F clamp texture, or albedo_image=(rgba8 HxWx4 array) -> RGBA8 mirror.
+        normal_map: (x,y,z) -> the 1x1 RGB32F texture SceneReader builds for "normalMap" (SceneReader.cpp:117-121);
+        normal_image: an RGBA8 image attached as TextureName::NORMAL (mirror wrap, like any loaded image)."""
         m = abi.Material()
         m.type = abi.MAT_MICROFACET
         if albedo_image is not None:
@@ -89,6 +91,10 @@ class SceneBuilder:
         if normal_map is not None:
             m.normal_tex = self.add_texture(normal_map, abi.TEX_RGB32F)
             m.has_normal_flag = 1  # NORMAL is the last addTexture call (Q24)
+        if normal_image is not None:
+            img = np.asarray(normal_image, dtype=np.uint8)
+            m.normal_tex = self.add_texture(img, abi.TEX_RGBA8, img.shape[1], img.shape[0], abi.WRAP_MIRROR)
+            m.has_normal_flag = 1
         m.volume = -1
         m.env_tex = -1
         return self._mat(name, m)

@@ -15,8 +15,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import scenes  # noqa: E402
 from refclient import RefOracle  # noqa: E402
 
-SIZES = {"cornell": (24, 16, 65536), "volume": (24, 16, 65536), "mixed": (16, 12, 131072), "mesh": (24, 16, 32768),
-         "directional": (24, 16, 32768), "environment": (24, 16, 32768), "homogeneous": (24, 16, 32768)}
+SIZES = {"cornell": (24, 16, 65536), "volume": (24, 16, 65536), "mixed": (16, 12, 524288), "mesh": (24, 16, 131072),
+         "directional": (24, 16, 32768), "environment": (24, 16, 32768), "homogeneous": (24, 16, 32768),
+         "c2": (48, 27, 16384), "mesh100k": (24, 16, 65536), "pointlit": (24, 16, 32768)}
 
 
 def main():

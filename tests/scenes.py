@@ -136,6 +136,47 @@ def noise_volume_scene(res=(64, 64, 64), leaves=False, density=100.0, light="poi
     return b
 
 
+def c2_density(n=256, seed=1337):
+    """BASELINE configs[1] density as SURVEY 8d C2 specifies it: FastNoise SimplexFractal (seed 1337, frequency 4/N, 5
+    octaves) remapped max(0, v*0.5+0.5-0.35)/0.65, times smoothstep(0.5, 0.35, |p|). Read from the data file
+    tools/make_c2_density.py wrote (workload/, travels to the GPU box), else generated by oracle/_ref/libc2noise.so
+    (the reference tree's vendored FastNoise compiled in place, oracle/ref/c2noise.cpp)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = os.path.join(root, "workload", f"c2_fastnoise_{n}.f32")
+    if seed == 1337 and os.path.exists(p) and os.path.getsize(p) == 4 * n ** 3:
+        return np.fromfile(p, np.float32).reshape(n, n, n)
+    import ctypes as C
+    lib = C.CDLL(os.path.join(root, "oracle", "_ref", "libc2noise.so"))
+    g = np.zeros((n, n, n), np.float32)
+    lib.c2noise_generate(n, n, n, seed, g.ctypes.data_as(C.POINTER(C.c_float)))
+    return g
+
+
+def c2_scene(grid=None, n=256, transform_fn=None):
+    """BASELINE configs[1] / SURVEY 8d C2, exactly what bench.py renders: FastNoise density, sigma_s 1.1, sigma_a 0.01,
+    HG g=0, density multiplier 100, volume scale 5 at the origin, POINT emitter Li=(100,100,70) at (0,6,0)."""
+    grid = c2_density(n) if grid is None else grid
+    return noise_volume_scene(res=grid.shape[::-1], density=100.0, light="point", scale=(5, 5, 5), pos=(0, 0, 0), li=(100, 100, 70),
+                              grid=grid, transform_fn=transform_fn)
+
+
+C2_CAMERA = CameraParams((0, 0, -12), (0, 0, 0), 45.0)
+
+
+def point_lit_surface_scene(transform_fn=None):
+    """A GGX floor and back wall lit by a POINT emitter only (primitives/Point.cpp:10-26; position = M * p with M already
+    translated by p, Q25): the light of BASELINE configs[1] on surfaces."""
+    b = SceneBuilder(transform_fn)
+    b.add_microfacet("floor", (.8, .7, .6), 0.6, 0.1)
+    b.add_microfacet("wall", (.3, .5, .8), 0.9, 0.0)
+    b.add_emitter("light", (100, 100, 70))
+    b.add_rectangle("floor", (0, 0, 0), (90, 0, 0), (8, 8, 1))
+    b.add_rectangle("wall", (0, 2, 3), (0, 0, 0), (8, 6, 1))
+    b.add_point("light", (0.3, 1.5, 0.2))
+    return b
+
+
 def displaced_grid(n, size=4.0, amp=0.35, seed=11):
     """n x n quads (2 n^2 triangles) displaced by fBm: the config-4 mesh shape at any size."""
     from scipy.ndimage import zoom
@@ -161,10 +202,12 @@ def displaced_grid(n, size=4.0, amp=0.35, seed=11):
     return pos, idx, uv
 
 
-def mesh_scene(n=64, transform_fn=None, roughness=0.6, li=(60, 60, 60)):
-    """Config-4 shape: a displaced-grid OBJ-style mesh with one GGX material and two rectangle area lights."""
+def mesh_scene(n=64, transform_fn=None, roughness=0.6, li=(60, 60, 60), normal_map=None, normal_image=None):
+    """Config-4 shape: a displaced-grid OBJ-style mesh with one GGX material and two rectangle area lights. normal_map /
+    normal_image: the material carries TextureName::NORMAL, so Triangle::intersect bends the geometric normal
+    (primitives/Triangle.cpp:74-77, utils/Math.h:1209-1215)."""
     b = SceneBuilder(transform_fn)
-    b.add_microfacet("mesh", (.7, .6, .5), roughness, 0.0)
+    b.add_microfacet("mesh", (.7, .6, .5), roughness, 0.0, normal_map=normal_map, normal_image=normal_image)
     b.add_emitter("light", li)
     pos, idx, uv = displaced_grid(n)
     b.add_mesh("mesh", pos, idx, uv, pos=(0, 0, 0))

@@ -473,3 +473,125 @@ def test_li_tape_homogeneous_media(ctx, oracle, grey):
     assert same.mean() > 0.97, f"Li(homogeneous) draw-count agreement {same.mean()}"
     assert_close(L[same], rL[same], what="Li homogeneous", rtol=2e-4, atol=1e-5, frac=0.99)
     assert (rused > 0).mean() > 0.2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The light of BASELINE configs[1]: a DiffuseLight on a Point primitive (primitives/Point.cpp:10-26; never hit, pdf 1,
+# position = M * p with M already translated by p, Q25).
+# ---------------------------------------------------------------------------------------------------------------
+def test_sample_one_light_tape_point_emitter(ctx, oracle):
+    """uniformSampleOneLight with a point emitter, on GGX surface hits and on a grid medium's boundary hits."""
+    for b, center, spread in ((scenes.point_lit_surface_scene(), (0, 1.5, -1), 1.0),
+                              (scenes.noise_volume_scene(res=(24, 24, 24), density=12.0, light="point"), (0, 1, -4), 0.8)):
+        ctx.upload(b)
+        rs = oracle.scene(b)
+        o, d = random_rays(3000, 33, center=center, spread=spread)
+        d[:, 2] = np.abs(d[:, 2])
+        hits = rs.intersect(o, d)
+        keep = [i for i in range(len(o)) if hits[i].hit and not hits[i].is_light]
+        assert len(keep) > 300
+        hh = (abi.Hit * len(keep))(*[hits[i] for i in keep])
+        dirs = d[keep]
+        seeds = np.arange(len(keep), dtype=np.uint32) + 800
+        tape = np.stack([oracle.tape(int(s), 4096) for s in seeds])
+        rL, rused = rs.sample_one_light(dirs, hh, seeds)
+        L, used = ctx.sample_one_light(dirs, hh, tape)
+        same = used == rused
+        assert same.mean() > 0.995, f"draw-count agreement {same.mean()}"
+        assert_close(L[same], rL[same], what="uniformSampleOneLight(point)", rtol=5e-5, atol=1e-6, frac=0.998)
+        assert (rL.sum(axis=1) > 0).mean() > 0.1
+
+
+def test_li_tape_point_light_surfaces(ctx, oracle):
+    b = scenes.point_lit_surface_scene()
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    cp = scenes.CameraParams((0, 2, -5), (0, 1, 0), 45.0)
+    cam_o, cam_d = oracle.camera_rays(cp, 1.0, 17, np.random.default_rng(12).uniform(0, 1, (3000, 2)))
+    seeds = np.arange(len(cam_o), dtype=np.uint32) + 130000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, cam_o, cam_d, 6, seeds)
+    same = used == rused
+    assert same.mean() > 0.99, f"Li(point, surfaces) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li point-lit surfaces", rtol=1e-4, atol=1e-5, frac=0.995)
+    assert (rL.sum(axis=1) > 0).mean() > 0.5
+
+
+def test_li_tape_point_light_volume(ctx, oracle):
+    """BASELINE configs[1]'s shape end to end, draw for draw: heterogeneous grid medium + point emitter."""
+    b = scenes.noise_volume_scene(res=(24, 24, 24), density=12.0, light="point")
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    rng = np.random.default_rng(41)
+    n = 1500
+    o = np.tile([0, 1, -6], (n, 1)).astype(np.float32)
+    tgt = np.stack([rng.uniform(-1, 1, n), 1 + rng.uniform(-1, 1, n), np.zeros(n)], 1)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    seeds = np.arange(n, dtype=np.uint32) + 150000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, o, d, 6, seeds, stride=16384)
+    same = used == rused
+    assert same.mean() > 0.97, f"Li(point, volume) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li point-lit volume", rtol=2e-4, atol=1e-6, frac=0.99)
+    assert (rL.sum(axis=1) > 0).mean() > 0.05
+
+
+def test_li_tape_c2_scene(ctx, oracle):
+    """The benchmarked scene itself (scenes.c2_scene: FastNoise 256^3, density 100, scale 5, point emitter, camera
+    (0,0,-12)): whole Li paths with the reference's global-majorant walk, draw for draw."""
+    b = scenes.c2_scene()
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    rng = np.random.default_rng(43)
+    xy = np.stack([rng.uniform(0.3, 0.7, 600), rng.uniform(0.15, 0.85, 600)], 1)  # the part of the frame the volume covers
+    cam_o, cam_d = oracle.camera_rays(scenes.C2_CAMERA, 1920 / 1080, 19, xy)
+    seeds = np.arange(len(cam_o), dtype=np.uint32) + 170000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, cam_o, cam_d, 6, seeds, stride=8192)
+    assert rused.max() < 8192
+    same = used == rused
+    assert same.mean() > 0.95, f"Li(C2) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li C2", rtol=5e-4, atol=1e-6, frac=0.99)
+    assert (rused > 100).mean() > 0.3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Normal-mapped triangles: Triangle.cpp:74-77 + convertNormalFromTextureMap (utils/Math.h:1209-1215), Q24.
+# ---------------------------------------------------------------------------------------------------------------
+def _normal_map_cases():
+    rng = np.random.default_rng(23)
+    img = rng.integers(0, 256, (12, 20, 4), dtype=np.uint8)
+    img[..., 2] = np.maximum(img[..., 2], 160)  # mostly outward-facing, like a real tangent-space map
+    return {"constant": dict(normal_map=(0.35, 0.6, 0.95)), "image": dict(normal_image=img)}
+
+
+@pytest.mark.parametrize("kind", ["constant", "image"])
+def test_intersect_normal_mapped_mesh(ctx, oracle, kind):
+    b = scenes.mesh_scene(n=24, **_normal_map_cases()[kind])
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    rng = np.random.default_rng(2)
+    n = 20000
+    o = np.stack([rng.uniform(-2, 2, n), rng.uniform(0.5, 3, n), rng.uniform(-2, 2, n)], 1).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d[:, 1] = -np.abs(d[:, 1])
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    a, r, m = compare_hits(ctx, rs, o, d, what=f"normal-mapped mesh ({kind})", min_frac=0.9995)
+    # the map really bends the normals: compare with the same mesh without one
+    plain = scenes.mesh_scene(n=24)
+    ctx.upload(plain)
+    g = hits_to_arrays(ctx.intersect(o, d), n)
+    mm = m & (g["hit"] == 1) & (a["inst"] == 0)
+    assert mm.sum() > 1000
+    assert (np.abs(g["nrm"][mm] - a["nrm"][mm]).max(axis=1) > 1e-3).mean() > 0.9
+
+
+def test_li_tape_normal_mapped_mesh(ctx, oracle):
+    b = scenes.mesh_scene(n=24, **_normal_map_cases()["image"])
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    cam_o, cam_d = oracle.camera_rays(scenes.MESH_CAMERA, 1.0, 27, np.random.default_rng(14).uniform(0, 1, (2000, 2)))
+    seeds = np.arange(len(cam_o), dtype=np.uint32) + 190000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, cam_o, cam_d, 6, seeds)
+    same = used == rused
+    assert same.mean() > 0.98, f"Li(normal-mapped mesh) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what="Li normal-mapped mesh", rtol=2e-4, atol=1e-5, frac=0.99)
+    assert rL.mean() > 0.05

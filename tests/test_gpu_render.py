@@ -41,10 +41,19 @@ CASES = {
     "directional": (lambda: scenes.directional_scene(g=0.0), scenes.DIRECTIONAL_CAMERA),
     "environment": (scenes.environment_scene, scenes.ENVIRONMENT_CAMERA),
     "homogeneous": (lambda: scenes.homogeneous_scene(g=0.0), scenes.HOMOGENEOUS_CAMERA),
+    # BASELINE configs[1] EXACTLY as bench.py renders it (FastNoise 256^3 density, density 100, scale 5, point emitter,
+    # camera (0,0,-12)), at a 16:9 frame small enough for the oracle to converge
+    "c2": (scenes.c2_scene, scenes.C2_CAMERA),
+    # BASELINE configs[3] shape above 100 k triangles (2 x 232^2 = 107 648) under two area lights
+    "mesh100k": (lambda: scenes.mesh_scene(n=232), scenes.MESH_CAMERA),
+    # the point emitter of configs[1] on GGX surfaces
+    "pointlit": (scenes.point_lit_surface_scene, scenes.CameraParams((0, 2, -5), (0, 1, 0), 45.0)),
 }
+# cases whose converged golden exists (the A/B tests below run on every case but the 256^3 one, to keep them quick)
+AB_CASES = [k for k in CASES if k != "c2"]
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", AB_CASES)
 def test_wavefront_equals_megakernel(ctx, name, monkeypatch):
     mk, cam = CASES[name]
     b = mk()
@@ -229,11 +238,63 @@ def test_bounded_walks_are_unbiased(ctx, name, monkeypatch):
     mk, cam = CASES[name]
     b = mk()
     monkeypatch.setenv("NE_B200_TRACK_BUDGET", "3")
+    monkeypatch.setenv("NE_B200_TRACK_CUT_ALWAYS", "1")  # by default walks are cut only in a tracking kernel's tail
     a = render(ctx, b, cam, 24, 16, 8192, seed=11)
     monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
     u = render(ctx, b, cam, 24, 16, 8192, seed=11)
     assert abs(luminance(a).mean() - luminance(u).mean()) / luminance(u).mean() < 0.01
     assert rel_mse(a, u) < 5e-3
+
+
+def test_render_graph_equals_host_driven_loop(ctx, monkeypatch):
+    """The production path runs a whole render as ONE CUDA graph (WHILE node, loop condition set on the device); the
+    host-driven loop launches the same kernels one by one. Same paths, same counters, images equal up to splat order."""
+    mk, cam = CASES["mixed"]
+    b = mk()
+    monkeypatch.setenv("NE_B200_POOL", "20000")  # many iterations, pool refilled through the free stack
+    monkeypatch.setenv("NE_B200_REQUIRE_GRAPH", "1")  # fail instead of falling back to the host-driven loop
+    a, ca = render_counted(ctx, b, cam, 96, 64, 16)
+    monkeypatch.setenv("NE_B200_HOST_LOOP", "1")
+    h, ch = render_counted(ctx, b, cam, 96, 64, 16)
+    assert ca == ch, (ca, ch)
+    np.testing.assert_allclose(a, h, rtol=2e-4, atol=1e-5 * float(h.mean()))
+    c = ctx.counters()
+    assert c.wavefront_iterations > 10 and c.ms_render > 0
+
+
+def test_request_arrays_cannot_overflow(ctx, monkeypatch):
+    """A saturated tiny pool in a closed box filled with a medium, every walk cut after two events: shadow and transmittance
+    requests stay within their arrays (each live slot is shaded once per iteration; walks that cannot be carried over keep
+    walking), the frame completes without the overflow flag, and the estimate is the uncut one."""
+    b = scenes.s1_cornell(with_sphere=False)
+    vol = b.add_volume_dense(np.full((16, 16, 16), 0.6, np.float32))
+    b.add_volume_material("fog", (1.1, 1.1, 1.1), (.01, .01, .01), 1.2, vol, "hg", 0.0)
+    b.add_volume("fog", (0, 2, 0), (0, 0, 0), (3.6, 3.6, 3.6))
+    cam = scenes.CORNELL_CAMERA
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    ref = render(ctx, b, cam, 48, 48, 256, seed=5)
+    monkeypatch.setenv("NE_B200_POOL", "1024")
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "2")
+    monkeypatch.setenv("NE_B200_TRACK_CUT_ALWAYS", "1")
+    a = render(ctx, b, cam, 48, 48, 256, seed=5)  # ne_b200_wait inside render_frame raises on overflow
+    assert np.isfinite(a).all()
+    assert abs(luminance(a).mean() - luminance(ref).mean()) / luminance(ref).mean() < 0.02
+
+
+def test_more_than_255_bounces(ctx, monkeypatch):
+    """The bounce count has its own 16 bits in the path record (it shared a byte with the null-segment guard): a
+    high-albedo cloud at 300 bounces renders like the one-thread-per-path megakernel; 65536 bounces are refused."""
+    mk, cam = CASES["volume"]
+    b = mk()
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")  # uncut walks: same paths as the megakernel
+    a = render(ctx, b, cam, 32, 24, 16, bounces=300)
+    m = render(ctx, b, cam, 32, 24, 16, bounces=300, flags=abi.RENDER_MEGAKERNEL)
+    np.testing.assert_allclose(a, m, rtol=5e-4, atol=1e-5 * float(m.mean()))
+    short = render(ctx, b, cam, 32, 24, 16, bounces=6)
+    assert a.mean() > short.mean()
+    from narvalengine_b200.abi import NarvalB200Error
+    with pytest.raises(NarvalB200Error):
+        render(ctx, b, cam, 32, 24, 1, bounces=65536)
 
 
 def test_global_and_brick_majorants_agree_statistically(ctx):
@@ -246,7 +307,7 @@ def test_global_and_brick_majorants_agree_statistically(ctx):
     assert c0.delta_steps > 0
 
 
-@pytest.mark.parametrize("name", ["cornell", "volume", "mixed", "mesh", "directional", "environment", "homogeneous"])
+@pytest.mark.parametrize("name", list(CASES))
 def test_image_parity_with_oracle_golden(ctx, name):
     """Converged-image parity against the committed oracle render (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, f"image_{name}.npz"))
@@ -258,11 +319,13 @@ def test_image_parity_with_oracle_golden(ctx, name):
     err = rel_mse(img, ref)
     lum, lref = luminance(img).mean(), luminance(ref).mean()
     print(f"{name}: rel-MSE {err:.3e} (oracle-vs-oracle noise floor {floor:.3e}), luminance {lum:.5f} vs {lref:.5f}")
-    # equal-spp comparison of two independent estimates: gate = the stated 1e-3, or the measured noise floor when
-    # that is higher (reported alongside)
-    assert err <= max(1e-3, 1.3 * floor)
+    # equal-spp comparison of two independent estimates against the stated gates (BASELINE north_star: rel-MSE <= 1e-3,
+    # mean luminance within 0.5 %). The golden must be converged well below the gate, or the test proves nothing:
     lum_floor = abs(luminance(ref2).mean() - lref) / lref
-    assert abs(lum - lref) / lref <= max(0.005, 2.0 * lum_floor)
+    assert floor < 5e-4, f"golden image_{name}.npz is not converged (oracle-vs-oracle rel-MSE {floor:.2e}): regenerate at higher spp"
+    assert lum_floor < 0.0025, f"golden image_{name}.npz: oracle-vs-oracle luminance differs by {lum_floor:.2%}"
+    assert err <= 1e-3
+    assert abs(lum - lref) / lref <= 0.005
 
 
 def test_offline_engine_tile_protocol(ctx):
