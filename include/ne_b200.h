@@ -263,7 +263,10 @@ int ne_b200_camera_set(ne_b200_ctx* ctx, const ne_b200_camera* camera);
  * Render samples [spp_begin, spp_end) of every pixel of a width x height frame and ADD their radiance into the
  * context's fp32 linear accumulation buffer (OfflineEngine::renderTile's two hot loops, OfflineEngine.cpp:61-69,
  * for the whole frame). Philox4x32-10 keyed (seed, pixel, sample): any sample range can be rendered on any
- * GPU in any order and the sum is the same up to fp32 addition order. Asynchronous; ne_b200_wait() joins.
+ * GPU in any order and the sum is the same up to fp32 addition order. ASYNCHRONOUS: the whole render is enqueued on the
+ * context's stream as one CUDA graph (its loop condition is evaluated on the device) and the call returns at once, so one
+ * host thread can keep several GPUs busy; ne_b200_wait() joins and reports the outcome. (The debug megakernel flag and
+ * NE_B200_HOST_LOOP=1 are synchronous.)
  * The buffer is (re)allocated and zeroed when width/height change or after ne_b200_clear().
  */
 int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int spp_end, int bounces,
@@ -293,6 +296,36 @@ int ne_b200_read_tonemapped(ne_b200_ctx* ctx, float* rgb);
  * tone-mapped frame (and optionally the linear one, may be NULL) to host memory. Synchronous. */
 int ne_b200_render_frame(ne_b200_ctx* ctx, const ne_b200_camera* camera, int width, int height, int spp, int bounces,
                          uint64_t seed, uint32_t flags, float* pixels_tonemapped, float* pixels_linear);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Several GPUs of one box behind one handle, in ONE process (SURVEY 8b `ne_b200_create(gpu_ids, n_gpus, ...)`, 8e).
+ * NarvalEngine is a single process (SceneEditor::startOffEngine, src/SceneEditor.cpp:590-604): these calls give it the
+ * sample-index partition and the exchange step without a launcher or a collective of its own. GPU g of G holds a scene
+ * replica and renders samples [g*spp/G, (g+1)*spp/G) of every pixel (one worker thread per device issues its work; the
+ * renders run concurrently); ONE kernel on the first device then reads every peer's accumulation buffer over NVLink
+ * (peer access; staged copies where unavailable), sums them in rank order, divides by spp and tone-maps.
+ * The image is the single-GPU image up to fp32 addition order. gpu_ids may name a device more than once (each entry gets
+ * its own context; used by the tests on one-GPU boxes).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct ne_b200_multi ne_b200_multi;
+int ne_b200_create_multi(const int* gpu_ids, int n_gpus, ne_b200_multi** out);
+void ne_b200_multi_destroy(ne_b200_multi* m);
+int ne_b200_multi_count(const ne_b200_multi* m);
+/* rank's own context (counters, stream, checkpointing); owned by the multi handle */
+ne_b200_ctx* ne_b200_multi_ctx(ne_b200_multi* m, int rank);
+/* 1 when the first device reads rank's accumulation buffer in place (peer access or same device), 0 when it is copied first */
+int ne_b200_multi_peer_access(const ne_b200_multi* m, int rank);
+/* the scene replicated on every GPU (uploads run concurrently) */
+int ne_b200_multi_scene_upload(ne_b200_multi* m, const ne_b200_scene_desc* scene);
+/* every GPU renders its share of the frame's spp samples per pixel. Asynchronous on every device. */
+int ne_b200_multi_render(ne_b200_multi* m, const ne_b200_camera* camera, int width, int height, int spp, int bounces,
+                         uint64_t seed, uint32_t flags);
+/* joins the renders; fused reduce + resolve on the first device; frames to HOST memory (either pointer may be NULL).
+ * Rank 0's accumulation buffer holds the whole frame's sums afterwards (checkpoint with ne_b200_accum_download). */
+int ne_b200_multi_resolve(ne_b200_multi* m, float* pixels_tonemapped, float* pixels_linear);
+/* ne_b200_multi_render + ne_b200_multi_resolve: the multi-GPU ne_b200_render_frame. Synchronous. */
+int ne_b200_multi_render_frame(ne_b200_multi* m, const ne_b200_camera* camera, int width, int height, int spp, int bounces,
+                               uint64_t seed, uint32_t flags, float* pixels_tonemapped, float* pixels_linear);
 
 /* Work counters of everything rendered since the last ne_b200_counters_reset (device counters; they are what
  * bench.py's roofline uses). Byte sizes of the records are exported so the check is reproducible. */

@@ -38,14 +38,19 @@ public:
 	uint64_t seed = 1;
 	uint32_t flags = 0;
 
-	B200OfflineEngine(const ne_b200_camera& cam, const ne_b200_render_settings& st, const ne_b200_scene_desc* scene, int cudaDevice = 0) {
+	B200OfflineEngine(const ne_b200_camera& cam, const ne_b200_render_settings& st, const ne_b200_scene_desc* scene, int cudaDevice = 0)
+	    : B200OfflineEngine(cam, st, scene, std::vector<int>{cudaDevice}) {}
+	// Several GPUs of the box: scene replicas, the frame's samples split by index, one fused reduce + resolve kernel over
+	// peer memory on the first device (ne_b200_create_multi). One device = the single-GPU path.
+	B200OfflineEngine(const ne_b200_camera& cam, const ne_b200_render_settings& st, const ne_b200_scene_desc* scene, const std::vector<int>& cudaDevices) {
 		for (auto& d : isThreadDone) d = false;
-		check(ne_b200_create(cudaDevice, &ctx), "ne_b200_create");
+		check(ne_b200_create_multi(cudaDevices.data(), int(cudaDevices.size()), &multi), "ne_b200_create_multi");
+		ctx = ne_b200_multi_ctx(multi, 0);
 		updateOfflineEngine(cam, st, scene);
 	}
 	~B200OfflineEngine() {
 		delete[] pixels;  // the engine owns `pixels` (OfflineEngine.cpp:4-6), not the scene or the camera
-		ne_b200_destroy(ctx);
+		ne_b200_multi_destroy(multi);
 	}
 	B200OfflineEngine(const B200OfflineEngine&) = delete;
 	B200OfflineEngine& operator=(const B200OfflineEngine&) = delete;
@@ -61,7 +66,7 @@ public:
 		pixels = new vec3[n]();       // readable (zeros) before any tile is final
 		frame.assign(n * 3, 0.0f);
 		linear.assign(n * 3, 0.0f);
-		if (scene) check(ne_b200_scene_upload(ctx, scene), "ne_b200_scene_upload");
+		if (scene) check(ne_b200_multi_scene_upload(multi, scene), "ne_b200_multi_scene_upload");
 		frameReady = false;
 	}
 
@@ -70,8 +75,8 @@ public:
 		{
 			std::lock_guard<std::mutex> lock(frameMutex);
 			if (!frameReady) {  // the first tile of a frame kicks the whole frame on the GPU
-				check(ne_b200_render_frame(ctx, &cam, settings.width, settings.height, settings.spp, settings.bounces, seed, flags, frame.data(),
-				                           linear.data()), "ne_b200_render_frame");
+				check(ne_b200_multi_render_frame(multi, &cam, settings.width, settings.height, settings.spp, settings.bounces, seed, flags, frame.data(),
+				                                 linear.data()), "ne_b200_multi_render_frame");
 				frameReady = true;
 			}
 		}
@@ -103,9 +108,11 @@ public:
 		for (int t = 0; t < nt; t++) threadPool[t].join();
 	}
 
-	ne_b200_ctx* context() const { return ctx; }
+	ne_b200_ctx* context() const { return ctx; }  // the first device's context
+	int deviceCount() const { return ne_b200_multi_count(multi); }
 
 private:
+	ne_b200_multi* multi = nullptr;
 	ne_b200_ctx* ctx = nullptr;
 	std::vector<float> frame;
 	bool frameReady = false;

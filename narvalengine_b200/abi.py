@@ -120,6 +120,16 @@ SYMBOLS = {
     "ne_b200_read_tonemapped": (C.c_int, [_ctx, pf32]),
     "ne_b200_render_frame": (C.c_int, [_ctx, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, u64, u32,
                                        pf32, pf32]),
+    "ne_b200_create_multi": (C.c_int, [pi32, C.c_int, C.POINTER(C.c_void_p)]),
+    "ne_b200_multi_destroy": (None, [C.c_void_p]),
+    "ne_b200_multi_count": (C.c_int, [C.c_void_p]),
+    "ne_b200_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "ne_b200_multi_peer_access": (C.c_int, [C.c_void_p, C.c_int]),
+    "ne_b200_multi_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
+    "ne_b200_multi_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, u64, u32]),
+    "ne_b200_multi_resolve": (C.c_int, [C.c_void_p, pf32, pf32]),
+    "ne_b200_multi_render_frame": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, u64, u32,
+                                             pf32, pf32]),
     "ne_b200_get_counters": (C.c_int, [_ctx, C.POINTER(Counters)]),
     "ne_b200_counters_reset": (C.c_int, [_ctx]),
     "ne_b200_test_intersect": (C.c_int, [_ctx, C.c_int, pf32, pf32, f32, f32, C.POINTER(Hit)]),

@@ -1334,7 +1334,8 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	int rc = wavefront_ensure(ctx, nSlots);
 	if (rc) return rc;
 	ne_wavefront_state* w = ctx->wf;
-	nSlots = w->nSlots;
+	nSlots = std::min(nSlots, w->nSlots);  // a pool kept from a larger render is used up to what this one asks for
+	w->b.nSlots = nSlots;
 	WfParams P;
 	memset(&P, 0, sizeof(P));
 	P.s = ctx->scene;

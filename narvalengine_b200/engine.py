@@ -34,17 +34,21 @@ class SceneSettings:
 
 
 class Context:
-    def __init__(self, device=0, lib=None):
+    def __init__(self, device=0, lib=None, handle=None):
+        """handle: wrap a context owned by someone else (a rank of a MultiContext); close() then leaves it alone."""
         self.lib = lib or abi.load_library()
-        h = C.c_void_p()
-        check(self.lib, self.lib.ne_b200_create(device, C.byref(h)), "ne_b200_create")
-        self.h = h
+        self._owned = handle is None
+        if handle is None:
+            h = C.c_void_p()
+            check(self.lib, self.lib.ne_b200_create(device, C.byref(h)), "ne_b200_create")
+            handle = h
+        self.h = handle
         self._scene_keep = None
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             self.lib.ne_b200_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -198,8 +202,59 @@ class Context:
         return out
 
 
+class MultiContext:
+    """Several GPUs of one box behind one handle in ONE process (ne_b200_create_multi, csrc/ne_multi.cu): scene replicas,
+    sample-index partition, fused peer-memory reduce + resolve on the first device. `devices` may repeat an index."""
+
+    def __init__(self, devices, lib=None):
+        self.lib = lib or abi.load_library()
+        ids = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(self.lib, self.lib.ne_b200_create_multi(ids, len(devices), C.byref(h)), "ne_b200_create_multi")
+        self.h = h
+        self._scene_keep = None
+
+    def __len__(self):
+        return self.lib.ne_b200_multi_count(self.h)
+
+    def rank(self, r):
+        return Context(lib=self.lib, handle=C.c_void_p(self.lib.ne_b200_multi_ctx(self.h, r)))
+
+    def peer_access(self, r):
+        return bool(self.lib.ne_b200_multi_peer_access(self.h, r))
+
+    def upload(self, builder_or_desc):
+        desc = builder_or_desc.desc() if hasattr(builder_or_desc, "desc") else builder_or_desc
+        self._scene_keep = builder_or_desc
+        check(self.lib, self.lib.ne_b200_multi_scene_upload(self.h, C.byref(desc)), "ne_b200_multi_scene_upload")
+
+    def render(self, cam, W, H, spp, bounces, seed=1, flags=0):
+        check(self.lib, self.lib.ne_b200_multi_render(self.h, C.byref(cam) if cam is not None else None, W, H, spp, bounces, seed, flags),
+              "ne_b200_multi_render")
+
+    def resolve(self, tonemapped=None, linear=None):
+        check(self.lib, self.lib.ne_b200_multi_resolve(self.h, _p(tonemapped) if tonemapped is not None else None,
+                                                       _p(linear) if linear is not None else None), "ne_b200_multi_resolve")
+
+    def render_frame(self, cam, W, H, spp, bounces, seed=1, flags=0, tonemapped=None, linear=None):
+        check(self.lib, self.lib.ne_b200_multi_render_frame(self.h, C.byref(cam) if cam is not None else None, W, H, spp, bounces, seed, flags,
+                                                            _p(tonemapped) if tonemapped is not None else None,
+                                                            _p(linear) if linear is not None else None), "ne_b200_multi_render_frame")
+
+    def close(self):
+        if self.h:
+            self.lib.ne_b200_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class B200OfflineEngine:
-    """Drop-in for `OfflineEngine` (src/core/OfflineEngine.{h,cpp}) on one GPU.
+    """Drop-in for `OfflineEngine` (src/core/OfflineEngine.{h,cpp}) on one GPU, or on several (`device` = a list).
 
     Reference protocol (SceneEditor.cpp:547-604): the caller starts `renderTile(cam, index, finished)` for tile indices
     0..numberOfTiles.x*numberOfTiles.y-1 and re-uploads `pixels` whenever one finishes. Here the first `renderTile`
@@ -208,7 +263,7 @@ class B200OfflineEngine:
     W%40 / H%10 remainder, so `pixels` is fully defined."""
 
     def __init__(self, camera, settings, scene, device=0, seed=1, flags=0):
-        self.ctx = Context(device)
+        self.ctx = MultiContext(device) if isinstance(device, (list, tuple)) else Context(device)
         self.seed, self.flags = seed, flags
         self.numberOfThreads = 16
         self.numberOfTiles = (40, 10)
