@@ -656,6 +656,9 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	ctx->nMeshes = int(meshes.size());
 	ctx->haveScene = true;
 	ctx->sceneGen++;
+	ctx->nSurfaces = 0;
+	for (const DInstance& in : insts)
+		if (in.material >= 0 && mats[in.material].has_bsdf && !mats[in.material].transmissive) ctx->nSurfaces++;
 	ctx->majTableBytes = 0;
 	ctx->l2Pool = nullptr;
 	ctx->l2PoolBytes = 0;

@@ -93,6 +93,7 @@ struct WfBuf {
 struct WfParams {
 	DScene s;
 	int W, H, budget, refill, moves, walkBudget, walkRefill, cutAlways;
+	int prevStage;  // stage kind of the kernel launched before this one, or -1: no stage accounting (see stage_stamp)
 	DCounters* counters;
 };
 
@@ -267,18 +268,23 @@ __global__ void k_wf_init(WfBuf b, unsigned long long workTotal, WfDyn dyn) {
 	*b.c = c;
 }
 
-// One thread, between two stages: device time since the previous stamp goes to that stage's account.
-__global__ void k_wf_stamp(WfBuf b, int kind) {
-	WfCounts& c = *b.c;
-	unsigned long long now = global_ns();
-	c.stageNs[kind] += now - c.lastNs;
-	c.lastNs = now;
+// Per-stage device time without extra launches: the kernels of an iteration run back to back on one stream, so the first
+// thread of each, before anything else, books the time since the previous stamp on the account of the stage that just
+// ended (the kind of the kernel launched before it; the host names it in WfParams::prevStage).
+__device__ __forceinline__ void stage_stamp(const WfBuf& b, int prevStage) {
+	if (prevStage >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+		WfCounts& c = *b.c;
+		unsigned long long now = global_ns();
+		c.stageNs[prevStage] += now - c.lastNs;
+		c.lastNs = now;
+	}
 }
 
 // One thread: retire the finished iteration (flip the ping-pong pairs: what was "next" is current now; clear the stage
 // queues) and plan the refill of the pool. Inside the render graph it also decides whether the WHILE node runs its body
 // again (cudaGraphSetConditional); the host-driven loop reads the mapped `hostDone` word instead.
-__global__ void k_wf_plan(WfBuf b, cudaGraphConditionalHandle loop, int inGraph, volatile uint32_t* hostDone, uint32_t launchesPerIteration) {
+__global__ void k_wf_plan(WfBuf b, cudaGraphConditionalHandle loop, int inGraph, volatile uint32_t* hostDone, uint32_t launchesPerIteration, int prevStage) {
+	stage_stamp(b, prevStage);
 	WfCounts& c = *b.c;
 	c.par ^= 1u;
 	c.extend = c.next;
@@ -326,6 +332,7 @@ __global__ void k_wf_finish(WfBuf b, DCounters* counters, int foldTimes) {
 // together, straight into the volume / surface queue. In the C2 frame 5 of 6 camera paths miss the medium's box.
 template <int MINB>  // resident blocks per SM: 3 without meshes, 4 with (the BVH walk is latency-bound: warps in flight count)
 __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t gen = b.c->gen;
 	if (gen == 0) return;
@@ -383,7 +390,8 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	flush_stats_wf(st, P.counters);
 }
 // One thread: publish the refill (after generate has read the old counts); reserved slots no survivor took go back.
-__global__ void k_wf_commit(WfBuf b, DCounters* counters) {
+__global__ void k_wf_commit(WfBuf b, DCounters* counters, int prevStage) {
+	stage_stamp(b, prevStage);
 	WfCounts& c = *b.c;
 	if (c.genTaken <= c.freeTake) {  // the untouched part of the free-stack reservation is still in place; no fresh slot was used
 		c.freeN += c.freeTake - c.genTaken;
@@ -398,6 +406,7 @@ __global__ void k_wf_commit(WfBuf b, DCounters* counters) {
 
 // Scene::intersectScene for every path of the extend queue + classify (Li :187-193, :244-260).
 __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->extend;
 	if (n == 0) return;
@@ -522,6 +531,7 @@ __device__ __forceinline__ void stage_majorants(const DScene& g, SceneCache& sh,
 
 template <int BRICKMAJ, int THREADS, int MINB>  // TRACK_GLOBAL / TRACK_BRICK / TRACK_SKIP / TRACK_*_SM (ne_tracking.cuh)
 __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	const uint32_t n = b.c->vol;
 	if (n == 0) return;
 	NE_STAGE_SCENE();
@@ -629,8 +639,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P)
 // classified right here, so a path that goes on through a grid medium enters the NEXT iteration's volume queue
 // directly, one that reaches a surface enters this iteration's surface queue, and one that ends frees its slot: no
 // trip through the extend queue, i.e. one 128-byte record read and one hit write fewer per scatter event.
-template <bool FUSE>
-__global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
+template <bool FUSE, int MINB>  // MINB resident blocks per SM (2: 128, 3: 80, 4: 64 registers): swept per scene family
+__global__ void __launch_bounds__(256, MINB) k_wf_scatter(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->scat;
 	if (n == 0) return;
@@ -701,6 +712,7 @@ __global__ void __launch_bounds__(256) k_wf_scatter(WfBuf b, WfParams P) {
 
 // Surface hits: GGX shading, next-event setup, continuation (Li :262-283).
 __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->surf;
 	if (n == 0) return;
@@ -737,6 +749,7 @@ __global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
 
 // visibilityTr requests: splat the weight when nothing or an emitter is hit first.
 __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = min(b.c->shadow, b.shadowCap);
 	if (n == 0) return;
@@ -756,6 +769,7 @@ __global__ void __launch_bounds__(256) k_wf_shadow(WfBuf b, WfParams P) {
 // intersectTr :13-31 for the requests pushed in this iteration: march THROUGH non-medium surfaces until a medium
 // (the request gets its instance, entry point and segment length) or nothing (the request is dropped: Li = 0).
 __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t first = b.c->trNew0, n = min(b.c->tr, b.trCap);
 	if (n <= first) return;
@@ -933,6 +947,7 @@ struct TrFindJob {
 #endif
 template <class JOB>
 __global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	const uint32_t first = JOB::first(b), n = JOB::count(b);
 	if (n == 0) return;
 	NE_STAGE_SCENE();
@@ -983,6 +998,7 @@ __global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfPa
 // walk ends.
 template <int BRICKMAJ, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
+	stage_stamp(b, P.prevStage);
 	const uint32_t n = min(b.c->tr, b.trCap);
 	if (n == 0) return;
 	NE_STAGE_SCENE();
@@ -1089,7 +1105,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
 struct WfVariant {
 	unsigned long long sceneGen;
 	int W, H;
-	int trace, fuse, brick, skip, sm, genBlocks, stamps;
+	int trace, fuse, brick, skip, sm, genBlocks, scatBlocks, stamps, media, surfaces;
 	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist;
 	uint32_t nSlots;
 };
@@ -1206,51 +1222,83 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 	return e ? (uint32_t)strtoul(e, nullptr, 10) : dflt;
 }
 
-// The launches of ONE wavefront iteration on stream `st`. `stamp(kind)` closes a stage: a k_wf_stamp launch inside the
-// graph, a CUDA event in the host-driven loop.
-template <class STAMP>
-static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const WfBuf& b, const WfParams& P, const WfVariant& V, DCounters* counters,
-                             STAMP&& stamp) {
+// The launches of ONE wavefront iteration on stream `st`, followed by the plan of the next one. Stages the scene cannot
+// need are not launched at all (no medium: no tracking / scatter / transmittance kernels; no shadeable surface: no
+// k_wf_surface). `mark(kind)` closes a stage in the host-driven loop (a CUDA event); inside the graph the kernels stamp
+// the device clock themselves (stage_stamp) and `mark` does nothing.
+static uint32_t launches_per_iteration(const WfVariant& V) {
+	// generate, commit, extend, shadow, plan + (track, scatter, trfind, tr with media) + (surface with shadeable surfaces)
+	return 5u + (V.media ? 4u : 0u) + (V.surfaces ? 1u : 0u);
+}
+
+template <class MARK>
+static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const WfBuf& b, WfParams P, const WfVariant& V, DCounters* counters,
+                             cudaGraphConditionalHandle loop, int inGraph, volatile uint32_t* hostDone, MARK&& mark) {
 	const int G = w->gridBlocks, B = 256;
 	const int GR = w->smCount * NE_TRACE_BLOCKS;
 	const int GT = w->smCount * NE_TRACK_BLOCKS;  // persistent tracking kernels: exactly the resident blocks
 	const int GS = w->smCount;                    // ... or one 1024-thread block per SM with the majorant tables in shared memory
 	const size_t smem = size_t(V.sm);
+	int prev = STAGE_OTHER;  // the plan that precedes every iteration
+	auto next = [&](int kind) {
+		P.prevStage = V.stamps ? prev : -1;
+		prev = kind;
+	};
 	// camera rays are coherent: the grid-stride kernel is as fast as a trace job (measured)
+	next(STAGE_OTHER);
 	if (V.genBlocks >= 4) k_wf_generate<4><<<G, B, 0, st>>>(b, P);
 	else if (V.genBlocks == 3) k_wf_generate<3><<<G, B, 0, st>>>(b, P);
 	else k_wf_generate<2><<<G, B, 0, st>>>(b, P);
-	k_wf_commit<<<1, 1, 0, st>>>(b, counters);
-	stamp(STAGE_OTHER);
+	next(STAGE_OTHER);
+	k_wf_commit<<<1, 1, 0, st>>>(b, counters, P.prevStage);
+	mark(STAGE_OTHER);
+	next(STAGE_TRACE);
 	if (V.trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
 	else k_wf_extend<<<G, B, 0, st>>>(b, P);
-	stamp(STAGE_TRACE);
-	if (!V.brick) k_wf_track<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-	else if (V.sm && V.skip) k_wf_track<TRACK_SKIP_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
-	else if (V.sm) k_wf_track<TRACK_BRICK_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
-	else if (V.skip) k_wf_track<TRACK_SKIP, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-	else k_wf_track<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-	stamp(STAGE_VOLUME);
-	if (V.fuse) k_wf_scatter<true><<<G, B, 0, st>>>(b, P);
-	else k_wf_scatter<false><<<G, B, 0, st>>>(b, P);
-	k_wf_surface<<<G, B, 0, st>>>(b, P);
-	stamp(STAGE_SHADE);
-	if (V.trace) {
-		k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
-		k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
-	} else {
-		k_wf_shadow<<<G, B, 0, st>>>(b, P);
-		k_wf_trfind<<<G, B, 0, st>>>(b, P);
+	mark(STAGE_TRACE);
+	if (V.media) {
+		next(STAGE_VOLUME);
+		if (!V.brick) k_wf_track<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+		else if (V.sm && V.skip) k_wf_track<TRACK_SKIP_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+		else if (V.sm) k_wf_track<TRACK_BRICK_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+		else if (V.skip) k_wf_track<TRACK_SKIP, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+		else k_wf_track<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+		mark(STAGE_VOLUME);
+		next(STAGE_SHADE);
+		if (V.fuse) {
+			if (V.scatBlocks >= 4) k_wf_scatter<true, 4><<<G, B, 0, st>>>(b, P);
+			else if (V.scatBlocks == 3) k_wf_scatter<true, 3><<<G, B, 0, st>>>(b, P);
+			else k_wf_scatter<true, 2><<<G, B, 0, st>>>(b, P);
+		} else {
+			if (V.scatBlocks >= 4) k_wf_scatter<false, 4><<<G, B, 0, st>>>(b, P);
+			else if (V.scatBlocks == 3) k_wf_scatter<false, 3><<<G, B, 0, st>>>(b, P);
+			else k_wf_scatter<false, 2><<<G, B, 0, st>>>(b, P);
+		}
 	}
-	stamp(STAGE_TRACE);
-	if (!V.brick) k_wf_tr<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-	else if (V.sm && V.skip) k_wf_tr<TRACK_SKIP_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
-	else if (V.sm) k_wf_tr<TRACK_BRICK_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
-	else if (V.skip) k_wf_tr<TRACK_SKIP, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-	else k_wf_tr<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
-	stamp(STAGE_VOLUME);
+	if (V.surfaces) {
+		next(STAGE_SHADE);
+		k_wf_surface<<<G, B, 0, st>>>(b, P);
+	}
+	mark(STAGE_SHADE);
+	next(STAGE_TRACE);
+	if (V.trace) k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
+	else k_wf_shadow<<<G, B, 0, st>>>(b, P);
+	if (V.media) {
+		next(STAGE_TRACE);
+		if (V.trace) k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
+		else k_wf_trfind<<<G, B, 0, st>>>(b, P);
+		mark(STAGE_TRACE);
+		next(STAGE_VOLUME);
+		if (!V.brick) k_wf_tr<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+		else if (V.sm && V.skip) k_wf_tr<TRACK_SKIP_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+		else if (V.sm) k_wf_tr<TRACK_BRICK_SM, 1024, 1><<<GS, 1024, smem, st>>>(b, P);
+		else if (V.skip) k_wf_tr<TRACK_SKIP, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+		else k_wf_tr<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
+		mark(STAGE_VOLUME);
+	} else mark(STAGE_TRACE);
+	next(STAGE_OTHER);
+	k_wf_plan<<<1, 1, 0, st>>>(b, loop, inGraph, hostDone, launches_per_iteration(V), P.prevStage);
 }
-#define NE_LAUNCHES_PER_ITERATION 11u  // generate, commit, extend, track, scatter, surface, shadow, trfind, tr, plan (+ stamps, not counted)
 
 // Optional: keep the largest brick pool resident in L2 (persisting access-policy window on the launching stream; kernel
 // nodes captured from the stream inherit it) so that streaming path records cannot evict voxel data.
@@ -1284,8 +1332,9 @@ static int graph_build(ne_b200_ctx* ctx, ne_wavefront_state* w, const WfParams& 
 	WfBuf b = w->b;
 	int inGraph = 1;
 	volatile uint32_t* noHost = nullptr;
-	uint32_t perIter = NE_LAUNCHES_PER_ITERATION;
-	void* planArgs[] = {&b, &loop, &inGraph, &noHost, &perIter};
+	uint32_t perIter = launches_per_iteration(V);
+	int noStage = -1;
+	void* planArgs[] = {&b, &loop, &inGraph, &noHost, &perIter, &noStage};
 	cudaKernelNodeParams kp;
 	memset(&kp, 0, sizeof(kp));
 	kp.func = reinterpret_cast<void*>(k_wf_plan);
@@ -1303,10 +1352,7 @@ static int graph_build(ne_b200_ctx* ctx, ne_wavefront_state* w, const WfParams& 
 	cudaGraph_t body = np.conditional.phGraph_out[0];
 	set_l2_window(ctx, w->capStream, V.l2persist != 0);
 	NE_CUDA_OK(cudaStreamBeginCaptureToGraph(w->capStream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-	launch_iteration(w->capStream, w, b, P, V, ctx->dCounters, [&](int kind) {
-		if (V.stamps) k_wf_stamp<<<1, 1, 0, w->capStream>>>(b, kind);
-	});
-	k_wf_plan<<<1, 1, 0, w->capStream>>>(b, loop, 1, nullptr, perIter);
+	launch_iteration(w->capStream, w, b, P, V, ctx->dCounters, loop, 1, nullptr, [](int) {});
 	cudaGraph_t captured = nullptr;
 	cudaError_t ce = cudaStreamEndCapture(w->capStream, &captured);
 	if (ce != cudaSuccess) {
@@ -1373,7 +1419,10 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 		const bool fits = V.brick && staged && ctx->majTableBytes > 0 && ctx->majTableBytes <= room;
 		V.sm = (fits && env_u32("NE_B200_SMEM_MAJ", 1) != 0) ? int(ctx->majTableBytes) : 0;
 	}
+	V.scatBlocks = int(env_u32("NE_B200_SCAT_BLOCKS", 2));
 	V.stamps = getenv("NE_B200_NO_STAGE_TIMES") == nullptr;
+	V.media = ctx->scene.has_medium ? 1 : 0;
+	V.surfaces = ctx->nSurfaces > 0 ? 1 : 0;
 	V.budget = P.budget; V.refill = P.refill; V.moves = P.moves; V.walkBudget = P.walkBudget; V.walkRefill = P.walkRefill; V.cutAlways = P.cutAlways;
 	V.l2persist = env_u32("NE_B200_L2_PERSIST", 0) ? 1 : 0;
 	cudaStream_t st = ctx->stream;
@@ -1433,19 +1482,20 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	cudaGraphConditionalHandle noLoop = 0;
 	k_wf_init<<<1, 1, 0, st>>>(w->b, work, dyn);
 	*w->hostDone = 0;
-	k_wf_plan<<<1, 1, 0, st>>>(w->b, noLoop, 0, w->devDone, NE_LAUNCHES_PER_ITERATION);
+	k_wf_plan<<<1, 1, 0, st>>>(w->b, noLoop, 0, w->devDone, launches_per_iteration(V), -1);
 	bool done = false;
+	WfVariant VH = V;
+	VH.stamps = 0;  // this mode's stage times are the CUDA events below
 	while (!done) {
 		// a few iterations per host poll; finished iterations cost only empty launches
 		for (int k = 0; k < 4; k++) {
 			cudaEvent_t last = timeStages ? ev() : nullptr;
-			launch_iteration(st, w, w->b, P, V, ctx->dCounters, [&](int kind) {
+			launch_iteration(st, w, w->b, P, VH, ctx->dCounters, noLoop, 0, w->devDone, [&](int kind) {
 				if (!timeStages) return;
 				cudaEvent_t e = ev();
 				spans.push_back({last, e, kind});
 				last = e;
 			});
-			k_wf_plan<<<1, 1, 0, st>>>(w->b, noLoop, 0, w->devDone, NE_LAUNCHES_PER_ITERATION);
 		}
 		NE_CUDA_OK(cudaStreamSynchronize(st));
 		NE_CUDA_OK(cudaGetLastError());
