@@ -107,26 +107,30 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter) {
 	return base + __popc(m & ((1u << lane) - 1));
 }
 
+// Work counters: per thread -> warp (one reduction instruction per field) -> block (shared-memory atomics) -> ONE global
+// atomic per field and block. Every warp used to add its totals to the ten global counters itself: thousands of
+// same-address atomics at the end of every launch, serialised in L2 - 10 to 20 microseconds per kernel, as much as the
+// work itself in the late, nearly empty iterations of a frame (found in the 8-spp-per-GPU frames of the strong-scaling run).
+// Must be reached by EVERY thread of the block (it synchronises).
+#define NE_STAT_FIELDS 10
 __device__ __forceinline__ void flush_stats_wf(const Stats& st, DCounters* c) {
-	unsigned m = __activemask();
-	unsigned lane = threadIdx.x & 31;
-	unsigned leader = __ffs(m) - 1;
-#define NE_FLUSH(field)                                                        \
-	{                                                                          \
-		unsigned v = __reduce_add_sync(m, (unsigned)(st.field));               \
-		if (lane == leader && v) atomicAdd(&c->field, (unsigned long long)v);  \
+	__shared__ unsigned long long blockTotals_[NE_STAT_FIELDS];
+	if (threadIdx.x < NE_STAT_FIELDS) blockTotals_[threadIdx.x] = 0;
+	__syncthreads();
+	const unsigned lane = threadIdx.x & 31;
+	const uint32_t v[NE_STAT_FIELDS] = {st.extend_rays, st.shadow_rays, st.delta_steps, st.ratio_steps, st.brick_visits,
+	                                    st.bvh_nodes,   st.tri_tests,   st.prim_tests,  st.scatter_events, st.surface_events};
+#pragma unroll
+	for (int k = 0; k < NE_STAT_FIELDS; k++) {
+		unsigned w = __reduce_add_sync(0xffffffffu, v[k]);
+		if (lane == 0 && w) atomicAdd(&blockTotals_[k], (unsigned long long)w);
 	}
-	NE_FLUSH(extend_rays)
-	NE_FLUSH(shadow_rays)
-	NE_FLUSH(delta_steps)
-	NE_FLUSH(ratio_steps)
-	NE_FLUSH(brick_visits)
-	NE_FLUSH(bvh_nodes)
-	NE_FLUSH(tri_tests)
-	NE_FLUSH(prim_tests)
-	NE_FLUSH(scatter_events)
-	NE_FLUSH(surface_events)
-#undef NE_FLUSH
+	__syncthreads();
+	if (threadIdx.x < NE_STAT_FIELDS && blockTotals_[threadIdx.x]) {
+		unsigned long long* dst[NE_STAT_FIELDS] = {&c->extend_rays, &c->shadow_rays, &c->delta_steps, &c->ratio_steps, &c->brick_visits,
+		                                           &c->bvh_nodes,   &c->tri_tests,   &c->prim_tests,  &c->scatter_events, &c->surface_events};
+		atomicAdd(dst[threadIdx.x], blockTotals_[threadIdx.x]);
+	}
 }
 
 __device__ __forceinline__ void splat(float* accum, uint32_t pixel, V3 v) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of run-time knobs on the headline frame. usage: gpurun -- 'bash tools/gpu_ab.sh "VAR=1" "VAR=2 OTHER=3" ...'  ("" = defaults)
 mkdir -p gpurun_out
-BARGS="--steps ${STEPS:-3} --warmup 2 --no-cpu-baseline --no-e2e"
+BARGS="--steps ${STEPS:-3} --warmup 2 --no-cpu-baseline --no-e2e ${EXTRA:-}"
 for V in "$@"; do
   N=$(echo "$V" | tr ' =' '__')
   env $V timeout 600 python bench.py $BARGS > gpurun_out/ab_$N.json 2> gpurun_out/ab_$N.err
