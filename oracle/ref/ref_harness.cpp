@@ -43,6 +43,7 @@
 #include "primitives/Rectangle.h"
 #include "primitives/Sphere.h"
 #include "primitives/Point.h"
+#include "flatten.h"
 #include "primitives/AABB.h"
 #include "primitives/Model.h"
 #include "primitives/InstancedModel.h"
@@ -544,10 +545,19 @@ void neref_tonemap(const float* in, int n, float* out) {
 
 void neref_camera_make(const float* lookFrom, const float* lookAt, const float* up, float vfov, float aspect, float aperture, float focus, ne_b200_camera* out) {
 	Camera c = makeCamera(lookFrom, lookAt, up, vfov, aspect, aperture, focus);
-	put3(out->position, c.position); put3(out->lower_left, c.lowerLeft); put3(out->horizontal, c.horizontal);
-	put3(out->vertical, c.vertical); put3(out->side, c.side); put3(out->up, c.up);
-	out->lens_radius = c.lensRadius;
+	*out = narval_b200_adapter::toPod(c);  // the reference-side adapter (oracle/ref/flatten.cpp)
 }
+
+// The reference-side adapter on a Scene* built by this harness: Scene* -> ne_b200_scene_desc (oracle/ref/flatten.cpp).
+// The returned handle owns the descriptor; free it with neref_flat_free.
+void* neref_flatten(void* h) {
+	RefScene* rs = (RefScene*)h;
+	auto* f = new narval_b200_adapter::FlatScene();
+	narval_b200_adapter::flatten(rs->scene, *f);
+	return f;
+}
+const ne_b200_scene_desc* neref_flat_desc(void* f) { return &((narval_b200_adapter::FlatScene*)f)->desc; }
+void neref_flat_free(void* f) { delete (narval_b200_adapter::FlatScene*)f; }
 // getRayPassingThrough for n (x,y) pairs in sequence after mt.seed(seed).
 void neref_camera_rays(const float* lookFrom, const float* lookAt, const float* up, float vfov, float aspect, float aperture, float focus,
                        uint32_t seed, int n, const float* xy, float* o, float* d) {

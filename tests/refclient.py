@@ -157,6 +157,21 @@ class RefOracle:
         return RefScene(self, h, builder_or_desc)
 
 
+class FlatDesc:
+    """Handle of a flattened scene; desc() is what Context.upload / RefOracle.scene take."""
+
+    def __init__(self, ref_scene, handle):
+        self.rs, self.h = ref_scene, C.c_void_p(handle)
+
+    def desc(self):
+        return self.rs.lib.neref_flat_desc(self.h).contents
+
+    def close(self):
+        if self.h:
+            self.rs.lib.neref_flat_free(self.h)
+            self.h = None
+
+
 class RefScene:
     def __init__(self, oracle, handle, keep):
         self.o, self.h, self._keep = oracle, C.c_void_p(handle), keep
@@ -164,6 +179,16 @@ class RefScene:
 
     def close(self):
         self.lib.neref_scene_destroy(self.h)
+
+    def flatten(self):
+        """The reference-side adapter (oracle/ref/flatten.cpp) on this Scene*: a FlatDesc holding the ne_b200_scene_desc it
+        produced (pointers alias this scene's buffers: keep the RefScene alive while it is used)."""
+        self.lib.neref_flatten.restype = C.c_void_p
+        self.lib.neref_flatten.argtypes = [C.c_void_p]
+        self.lib.neref_flat_desc.restype = C.POINTER(abi.SceneDesc)
+        self.lib.neref_flat_desc.argtypes = [C.c_void_p]
+        self.lib.neref_flat_free.argtypes = [C.c_void_p]
+        return FlatDesc(self, self.lib.neref_flatten(self.h))
 
     def counts(self):
         a, b = C.c_int(), C.c_int()
