@@ -327,6 +327,20 @@ int ne_b200_multi_resolve(ne_b200_multi* m, float* pixels_tonemapped, float* pix
 int ne_b200_multi_render_frame(ne_b200_multi* m, const ne_b200_camera* camera, int width, int height, int spp, int bounces,
                                uint64_t seed, uint32_t flags, float* pixels_tonemapped, float* pixels_linear);
 
+/* Progressive rendering with a stopping rule ("adaptive stopping"): samples are rendered in batches of
+ * spp_batch; even and odd batches accumulate separately, and after every pair the GPU estimates the frame's rel-MSE
+ * (SURVEY 8d's image metric, eps 1e-4) from the difference of the two half-estimates. Rendering stops when the estimate
+ * is <= target_rel_mse with at least spp_min samples in, or at spp_max. The accumulation buffer then holds all samples
+ * (checkpointable / resumable as usual). Host pointers may be NULL. Synchronous. */
+typedef struct ne_b200_adaptive_result {
+	int32_t spp_rendered;
+	float rel_mse_estimate;       /* of the frame returned, against the converged image */
+	int32_t converged;            /* 1: stopped by the target; 0: stopped by spp_max */
+} ne_b200_adaptive_result;
+int ne_b200_render_adaptive(ne_b200_ctx* ctx, const ne_b200_camera* camera, int width, int height, int spp_min, int spp_max,
+                            int spp_batch, float target_rel_mse, int bounces, uint64_t seed, uint32_t flags,
+                            float* pixels_tonemapped, float* pixels_linear, ne_b200_adaptive_result* result);
+
 /* Work counters of everything rendered since the last ne_b200_counters_reset (device counters; they are what
  * bench.py's roofline uses). Byte sizes of the records are exported so the check is reproducible. */
 typedef struct ne_b200_counters {

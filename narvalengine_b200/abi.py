@@ -82,6 +82,10 @@ class Counters(C.Structure):
                [("ms_other_kernel", C.c_double)]
 
 
+class AdaptiveResult(C.Structure):
+    _fields_ = [("spp_rendered", i32), ("rel_mse_estimate", f32), ("converged", i32)]
+
+
 # Every symbol include/ne_b200.h declares: name -> (restype, argtypes). tests/test_abi.py checks the list
 # against the header and that the built library exports each one.
 _ctx = C.c_void_p
@@ -130,6 +134,8 @@ SYMBOLS = {
     "ne_b200_multi_resolve": (C.c_int, [C.c_void_p, pf32, pf32]),
     "ne_b200_multi_render_frame": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, u64, u32,
                                              pf32, pf32]),
+    "ne_b200_render_adaptive": (C.c_int, [_ctx, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32, C.c_int, u64, u32,
+                                          pf32, pf32, C.POINTER(AdaptiveResult)]),
     "ne_b200_get_counters": (C.c_int, [_ctx, C.POINTER(Counters)]),
     "ne_b200_counters_reset": (C.c_int, [_ctx]),
     "ne_b200_test_intersect": (C.c_int, [_ctx, C.c_int, pf32, pf32, f32, f32, C.POINTER(Hit)]),

@@ -109,6 +109,33 @@ __global__ void k_resolve(const float* accum, float invSamples, size_t n, float*
 	if (tonemapped) tonemapped[i] = tonemap1(c);
 }
 
+// Adaptive stopping: A holds the sums of the even-numbered sample batches (nA samples per pixel), B of the odd ones (nB).
+// Two independent estimates of the same frame: ((A/nA - B/nB) / 2)^2 estimates the squared error of their average, so
+// the mean over pixels and channels of that over (mean^2 + eps) estimates the rel-MSE (SURVEY 8d's metric, eps = 1e-4) of
+// the frame rendered so far against the converged one. out[0] += the block's partial sum (double).
+__global__ void __launch_bounds__(256) k_adaptive_error(const float* A, const float* B, float invA, float invB, float invN, size_t n, double* out) {
+	double acc = 0;
+	for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+		float a = A[i], b = B[i];
+		float d = 0.5f * (a * invA - b * invB);
+		float m = (a + b) * invN;
+		acc += double(d * d / (m * m + 1e-4f));
+	}
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+	__shared__ double part[8];
+	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double t = 0;
+		for (int k = 0; k < 8; k++) t += part[k];
+		atomicAdd(out, t);
+	}
+}
+__global__ void k_add_into(float* A, const float* B, size_t n) {
+	size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n) A[i] += B[i];
+}
+
 __global__ void k_test_intersect(DScene s, int n, const float* o, const float* d, float tMin, float tMax, ne_b200_hit* out) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -833,6 +860,67 @@ int ne_b200_render_frame(ne_b200_ctx* ctx, const ne_b200_camera* camera, int wid
 	if ((rc = ne_b200_clear(ctx))) return rc;
 	if ((rc = ne_b200_render(ctx, width, height, 0, spp, bounces, seed, flags))) return rc;
 	if ((rc = ne_b200_wait(ctx))) return rc;
+	if (!pixels_tonemapped && !pixels_linear) return NE_B200_OK;
+	return read_resolved(ctx, pixels_linear, pixels_tonemapped);
+}
+
+// Progressive rendering with a stopping rule: sample batches go alternately into two accumulation
+// buffers; after every pair the GPU estimates the frame's rel-MSE from their difference (k_adaptive_error) and the loop
+// stops once it is below the target (and at least spp_min samples are in) or spp_max is reached. The buffers are then
+// summed into the context's accumulation buffer, so the frame can still be checkpointed or continued.
+int ne_b200_render_adaptive(ne_b200_ctx* ctx, const ne_b200_camera* camera, int width, int height, int spp_min, int spp_max, int spp_batch,
+                            float target_rel_mse, int bounces, uint64_t seed, uint32_t flags, float* pixels_tonemapped, float* pixels_linear,
+                            ne_b200_adaptive_result* result) {
+	int rc;
+	if (spp_batch < 1 || spp_min < 0 || spp_max < 2 * spp_batch || spp_min > spp_max || !(target_rel_mse >= 0)) { set_error("bad adaptive arguments (spp_max >= 2 * spp_batch, spp_batch >= 1)"); return NE_B200_ERR_INVALID; }
+	if (camera && (rc = ne_b200_camera_set(ctx, camera))) return rc;
+	if ((rc = ne_b200_render(ctx, width, height, 0, 0, bounces, seed, flags))) return rc;  // (re)allocate
+	if ((rc = ne_b200_clear(ctx))) return rc;
+	const size_t n = size_t(width) * height * 3;
+	float* A = ctx->accum;
+	float* B = nullptr;
+	double* dErr = nullptr;
+	NE_CUDA_OK(cudaMallocAsync(&B, n * sizeof(float), ctx->stream));
+	NE_CUDA_OK(cudaMallocAsync(&dErr, sizeof(double), ctx->stream));
+	NE_CUDA_OK(cudaMemsetAsync(B, 0, n * sizeof(float), ctx->stream));
+	int done = 0, nA = 0, nB = 0, batches = 0;
+	double err = INFINITY;
+	bool converged = false;
+	rc = NE_B200_OK;
+	while (done < spp_max) {
+		const int take = std::min(spp_batch, spp_max - done);
+		ctx->accum = (batches & 1) ? B : A;  // the renderer splats into whichever buffer the context names
+		rc = ne_b200_render(ctx, width, height, done, done + take, bounces, seed, flags);
+		ctx->accum = A;
+		if (rc) break;
+		((batches & 1) ? nB : nA) += take;
+		done += take;
+		batches++;
+		if ((batches & 1) == 0) {  // a complete pair: two estimates with (nearly) the same sample count
+			cudaMemsetAsync(dErr, 0, sizeof(double), ctx->stream);
+			k_adaptive_error<<<592, 256, 0, ctx->stream>>>(A, B, 1.0f / float(nA), 1.0f / float(nB), 1.0f / float(nA + nB), n, dErr);
+			ctx->kernelLaunches++;
+			double sum = 0;
+			if (cudaMemcpyAsync(&sum, dErr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+			    cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("adaptive error read-back failed"); rc = NE_B200_ERR_CUDA; break; }
+			err = sum / double(n);
+			if (done >= spp_min && err <= double(target_rel_mse)) { converged = true; break; }
+		}
+	}
+	if (!rc) {
+		k_add_into<<<blocks(n, 256), 256, 0, ctx->stream>>>(A, B, n);
+		ctx->kernelLaunches++;
+	}
+	cudaFreeAsync(B, ctx->stream);
+	cudaFreeAsync(dErr, ctx->stream);
+	ctx->samples = done;
+	if (rc) return rc;
+	if ((rc = ne_b200_wait(ctx))) return rc;
+	if (result) {
+		result->spp_rendered = done;
+		result->rel_mse_estimate = float(err);
+		result->converged = converged ? 1 : 0;
+	}
 	if (!pixels_tonemapped && !pixels_linear) return NE_B200_OK;
 	return read_resolved(ctx, pixels_linear, pixels_tonemapped);
 }

@@ -114,6 +114,14 @@ class Context:
                                                       flags, _p(tonemapped) if tonemapped is not None else None,
                                                       _p(linear) if linear is not None else None), "ne_b200_render_frame")
 
+    def render_adaptive(self, cam, W, H, spp_min, spp_max, spp_batch, target_rel_mse, bounces, seed=1, flags=0, tonemapped=None, linear=None):
+        """Progressive rendering with the stopping rule of ne_b200_render_adaptive; returns (spp_rendered, rel_mse_estimate, converged)."""
+        r = abi.AdaptiveResult()
+        check(self.lib, self.lib.ne_b200_render_adaptive(self.h, C.byref(cam) if cam is not None else None, W, H, spp_min, spp_max, spp_batch,
+                                                         target_rel_mse, bounces, seed, flags, _p(tonemapped) if tonemapped is not None else None,
+                                                         _p(linear) if linear is not None else None, C.byref(r)), "ne_b200_render_adaptive")
+        return r.spp_rendered, r.rel_mse_estimate, bool(r.converged)
+
     def counters(self):
         c = abi.Counters()
         check(self.lib, self.lib.ne_b200_get_counters(self.h, C.byref(c)), "ne_b200_get_counters")

@@ -317,3 +317,51 @@ def test_image_writers(lib, tmp_path):
     assert raw.startswith(head) and len(raw) == len(head) + 9 * 13 * 6
     px = np.frombuffer(raw[len(head):], ">u2").reshape(9 * 13, 3)
     assert np.array_equal(px, (tm.reshape(-1, 3)[::-1] * np.float32(65535)).astype(np.uint16))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The scenes the reference ships (resources/scenes/**/*.json, 25 files). Runs where /root/reference exists.
+# ---------------------------------------------------------------------------------------------------------------
+REF_RESOURCES = "/root/reference/resources"
+
+
+def shipped_scenes():
+    import glob
+    return sorted(glob.glob(os.path.join(REF_RESOURCES, "scenes", "**", "*.json"), recursive=True))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RESOURCES), reason="the reference tree is not present on this machine")
+def test_every_shipped_scene_loads_or_fails_cleanly(lib):
+    """Every JSON scene of the reference through ne_b200_scene_file_load: either a descriptor comes back, or an error code
+    with a message naming what is missing (an absent .vol / .vdb / .obj asset, a material type the reference's own reader
+    aborts on) - never an abort, never an exception across the C ABI (the reference LOG(FATAL)s)."""
+    files = shipped_scenes()
+    assert len(files) >= 20
+    loaded, failed = [], {}
+    for f in files:
+        h = C.c_void_p()
+        rc = lib.ne_b200_scene_file_load(f.encode(), (REF_RESOURCES + "/").encode(), C.byref(h))
+        if rc == 0:
+            d = lib.ne_b200_scene_file_desc(h).contents
+            assert d.n_primitives >= 0 and d.n_materials >= 0  # empty.json is an empty scene
+            st = abi.RenderSettings()
+            assert lib.ne_b200_scene_file_settings(h, C.byref(st)) == 0 and st.width > 0 and st.height > 0
+            lib.ne_b200_scene_file_free(h)
+            loaded.append(os.path.basename(f))
+        else:
+            msg = lib.ne_b200_last_error().decode()
+            assert rc in (abi.ERR_INVALID, abi.ERR_UNSUPPORTED, abi.ERR_NOMEM) and len(msg) > 8, (f, rc, msg)
+            failed[os.path.basename(f)] = msg
+    assert "surfaceAndLight.json" in loaded
+    # the failures are about assets or features the reference tree itself lacks, not about the JSON
+    for name, msg in failed.items():
+        assert any(k in msg for k in ("couldn't read the file at", "needs OpenVDB", "invalid material type")), (name, msg)
+    print(f"{len(loaded)} shipped scenes load ({', '.join(loaded)}); {len(failed)} fail cleanly")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RESOURCES), reason="the reference tree is not present on this machine")
+def test_shipped_scene_fixture_is_current():
+    """tests/golden/scene_surfaceAndLight.npz (made by tests/golden/make_scene_golden.py) holds the shipped scene's JSON
+    text: it must still be the file the reference ships."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_surfaceAndLight.npz"))
+    assert bytes(g["scene_json"]).decode() == open(os.path.join(REF_RESOURCES, "scenes", "testing", "surfaceAndLight.json")).read()

@@ -382,3 +382,56 @@ def test_json_scene_file_renders_like_the_builder(ctx, tmp_path):
     assert m.mean() > 0
     np.testing.assert_allclose(a, m, rtol=2e-4, atol=1e-5 * float(m.mean()))
     sf.close()
+
+
+def test_shipped_reference_scene_end_to_end(ctx):
+    """resources/scenes/testing/surfaceAndLight.json - a scene file the reference SHIPS (its text travels in the golden
+    fixture, tests/golden/make_scene_golden.py) - through the library's JSON front end, its camera and settings, the GPU
+    renderer, against the oracle's converged render of the same file: rel-MSE <= 1e-3, luminance within 0.5 %."""
+    from narvalengine_b200.scene import SceneFile
+    g = np.load(os.path.join(GOLDEN, "scene_surfaceAndLight.npz"))
+    sf = SceneFile(text=bytes(g["scene_json"]).decode(), resources_dir="", lib=ctx.lib)
+    st = sf.settings()
+    assert (st.width, st.height, st.spp, st.bounces) == (600, 300, 1, 6)
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    ctx.upload(sf)
+    img = np.zeros((H, W, 3), np.float32)
+    ctx.render_frame(sf.camera(), W, H, spp, st.bounces, 1, 0, None, img)  # the file's own camera (aspect 2:1 as in the file)
+    ref, ref2 = g["linear"], g["linear_b"]
+    floor, err = rel_mse(ref2, ref), rel_mse(img, ref)
+    lum, lref = luminance(img).mean(), luminance(ref).mean()
+    print(f"surfaceAndLight.json: rel-MSE {err:.3e} (floor {floor:.3e}), luminance {lum:.5f} vs {lref:.5f}")
+    assert floor < 5e-4
+    assert err <= 1e-3 and abs(lum - lref) / lref <= 0.005
+    sf.close()
+
+
+def test_adaptive_stopping(ctx):
+    """ne_b200_render_adaptive: batches go alternately into two accumulation buffers, the GPU estimates
+    the frame's rel-MSE from their difference, rendering stops at the target. The estimate must track the true error
+    (against a converged render), a looser target must stop earlier, spp_max must bound it, and the accumulation buffer
+    must hold all samples afterwards (resumable)."""
+    b = scenes.cornell_c1()
+    cp = scenes.CORNELL_CAMERA
+    W, H = 48, 48
+    truth = render(ctx, b, cp, W, H, 32768, seed=77)
+    ctx.upload(b)
+    cam = cp.make(W / H, ctx.lib)
+    out = {}
+    for target in (2e-2, 2e-3):
+        lin = np.zeros((H, W, 3), np.float32)
+        spp, est, conv = ctx.render_adaptive(cam, W, H, 16, 16384, 16, target, 6, seed=5, linear=lin)
+        true = rel_mse(lin, truth)
+        print(f"target {target:g}: stopped at {spp} spp, estimate {est:.3e}, true rel-MSE {true:.3e}")
+        assert conv and est <= target and spp % 32 == 0
+        assert 0.3 * true <= est <= 3.0 * true + 1e-5   # two half-estimates predict the error of their average
+        np.testing.assert_allclose(ctx.read_linear(W, H), lin, rtol=1e-6)
+        sums, n = ctx.accum_download(W, H)
+        assert n == spp
+        out[target] = spp
+    assert out[2e-2] < out[2e-3]
+    spp, est, conv = ctx.render_adaptive(cam, W, H, 8, 64, 8, 1e-9, 6, seed=5)
+    assert spp == 64 and not conv and est > 1e-9
+    from narvalengine_b200.abi import NarvalB200Error
+    with pytest.raises(NarvalB200Error):
+        ctx.render_adaptive(cam, W, H, 8, 8, 8, 1e-3, 6)
