@@ -683,6 +683,27 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	ctx->nMeshes = int(meshes.size());
 	ctx->haveScene = true;
 	ctx->sceneGen++;
+	// bounds of everything hittable, in world space (camera-ray culling): OCS extent of each primitive kind through M
+	ctx->boundCorners.clear();
+	ctx->cullable = s.n_directional == 0 && s.n_infinite == 0;
+	for (const DInstance& in : insts) {
+		if (!in.collision || in.type == PRIM_POINT) continue;  // never hit (InstancedModel.cpp:25, Point.cpp:10-12)
+		float lo[3] = {-0.5f, -0.5f, -0.5f}, hi[3] = {0.5f, 0.5f, 0.5f};  // volume proxy cube
+		if (in.type == PRIM_RECTANGLE) { lo[2] = hi[2] = 0.0f; }
+		else if (in.type == PRIM_SPHERE) { for (int k = 0; k < 3; k++) { lo[k] = -std::fabs(in.radius); hi[k] = std::fabs(in.radius); } }
+		else if (in.type == PRIM_MESH) {
+			if (in.mesh < 0) { ctx->cullable = false; continue; }
+			for (int k = 0; k < 3; k++) { lo[k] = meshes[in.mesh].bbmin[k]; hi[k] = meshes[in.mesh].bbmax[k]; }
+		}
+		for (int c = 0; c < 8; c++) {
+			const float p[3] = {(c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]};
+			for (int r = 0; r < 3; r++) {
+				float w = in.M[r] * p[0] + in.M[4 + r] * p[1] + in.M[8 + r] * p[2] + in.M[12 + r];
+				if (!std::isfinite(w)) ctx->cullable = false;
+				ctx->boundCorners.push_back(w);
+			}
+		}
+	}
 	ctx->nSurfaces = 0;
 	for (const DInstance& in : insts)
 		if (in.material >= 0 && mats[in.material].has_bsdf && !mats[in.material].transmissive) ctx->nSurfaces++;
@@ -933,7 +954,7 @@ int ne_b200_get_counters(ne_b200_ctx* ctx, ne_b200_counters* out) {
 	DCounters c;
 	NE_CUDA_OK(cudaMemcpy(&c, ctx->dCounters, sizeof(c), cudaMemcpyDeviceToHost));
 	memset(out, 0, sizeof(*out));
-	out->paths = c.paths; out->extend_rays = c.extend_rays; out->shadow_rays = c.shadow_rays; out->delta_steps = c.delta_steps;
+	out->paths = c.paths + ctx->pathsCulled; out->extend_rays = c.extend_rays; out->shadow_rays = c.shadow_rays; out->delta_steps = c.delta_steps;
 	out->ratio_steps = c.ratio_steps; out->brick_visits = c.brick_visits; out->bvh_nodes = c.bvh_nodes; out->tri_tests = c.tri_tests;
 	out->prim_tests = c.prim_tests; out->scatter_events = c.scatter_events; out->surface_events = c.surface_events;
 	out->wavefront_iterations = c.iterations;
@@ -961,6 +982,7 @@ int ne_b200_counters_reset(ne_b200_ctx* ctx) {
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	NE_CUDA_OK(cudaMemset(ctx->dCounters, 0, sizeof(DCounters)));
 	ctx->kernelLaunches = ctx->wavefrontIterations = 0;
+	ctx->pathsCulled = 0;
 	ctx->msRender = ctx->msVolume = ctx->msExtend = ctx->msShade = ctx->msOther = 0;
 	return NE_B200_OK;
 }

@@ -35,6 +35,12 @@ struct ne_b200_ctx {
 	bool skipWorthwhile = false;  // some volume's brick table is mostly skippable empty space (ne_bricks.cu device_build_majorants)
 	int nMeshes = 0;  // triangle meshes with a BVH: the wavefront then runs its persistent trace kernels
 	int nSurfaces = 0;  // fold instances a path can be shaded on (a BSDF that is not a medium's): none -> k_wf_surface is never launched
+	// world-space corner points (xyz) of everything a camera ray can hit, for the camera-ray culling rectangle
+	// (ne_wavefront.cu cull_rect); cullable = false when some instance cannot be bounded or the scene has lights that
+	// add radiance to rays that miss everything (directional, environment)
+	std::vector<float> boundCorners;
+	bool cullable = false;
+	unsigned long long pathsCulled = 0;  // camera paths proven to carry no radiance without tracing them (counted as paths)
 	unsigned long long sceneGen = 0;  // bumped by every upload: the wavefront's render graph is rebuilt when it changes
 	size_t majTableBytes = 0;  // sum of the volumes' 2-byte majorant tables, each padded to 16 bytes (shared-memory staging)
 	const void* l2Pool = nullptr;  // the largest brick pool (optional L2 persisting window, NE_B200_L2_PERSIST)

@@ -46,6 +46,8 @@ struct WfDyn {
 	float* accum;
 	unsigned long long seed;
 	int sppBegin, bounces;
+	// camera rays are generated for the pixels of this rectangle only (cull_rect: everything hittable projects inside it)
+	int rx0, ry0, rw, rh;
 };
 
 enum { STAGE_TRACE = 0, STAGE_VOLUME = 1, STAGE_SHADE = 2, STAGE_OTHER = 3, STAGE_KINDS = 4 };
@@ -346,19 +348,24 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	float* const accum = b.c->dyn.accum;
 	const unsigned long long seed = b.c->dyn.seed;
 	const uint32_t sppBegin = uint32_t(b.c->dyn.sppBegin);
-	const uint32_t npix = uint32_t(P.W) * uint32_t(P.H);
-	const bool tiled = (P.W % 8 == 0) && (P.H % 4 == 0);  // else the frame is walked row by row (any bijection will do: Philox is keyed by pixel)
+	// work items enumerate (sample, pixel of the culling rectangle); the rectangle is the whole frame unless cull_rect found less
+	const uint32_t rx0 = uint32_t(b.c->dyn.rx0), ry0 = uint32_t(b.c->dyn.ry0), rw = uint32_t(b.c->dyn.rw), rh = uint32_t(b.c->dyn.rh);
+	const uint32_t npix = rw * rh;
+	const bool tiled = (rw % 8 == 0) && (rh % 4 == 0);  // else the rectangle is walked row by row (any bijection will do: Philox is keyed by pixel)
 	Stats st;
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < gen; i += gridDim.x * blockDim.x) {
 		unsigned long long w = workBase + i;
-		uint32_t pixel = uint32_t(w % npix);
+		const uint32_t p = uint32_t(w % npix);
+		uint32_t px = p % rw, py = p / rw;
 		if (tiled) {  // a warp's 32 consecutive work items cover an 8x4 pixel tile, not a 32x1 strip: coherent camera rays
-			const uint32_t t = pixel >> 5, l = pixel & 31u, tilesX = uint32_t(P.W) >> 3;
-			pixel = ((t / tilesX) * 4u + (l >> 3)) * uint32_t(P.W) + (t % tilesX) * 8u + (l & 7u);
+			const uint32_t t = p >> 5, l = p & 31u, tilesX = rw >> 3;
+			px = (t % tilesX) * 8u + (l & 7u);
+			py = (t / tilesX) * 4u + (l >> 3);
 		}
+		const int x = int(rx0 + px), y = int(ry0 + py);
+		const uint32_t pixel = uint32_t(y) * uint32_t(P.W) + uint32_t(x);
 		uint32_t sample = sppBegin + uint32_t(w / npix);
-		int x = int(pixel % uint32_t(P.W)), y = int(pixel / uint32_t(P.W));
 		PhiloxRng rng;
 		rng.init(seed, pixel, sample);
 		float u = float(float(x) + rng.next()) / float(P.W);
@@ -1376,9 +1383,67 @@ static int graph_build(ne_b200_ctx* ctx, ne_wavefront_state* w, const WfParams& 
 	return NE_B200_OK;
 }
 
+// Camera-ray culling: the pixel rectangle outside of which NO camera ray can hit anything. Every hittable instance's
+// world-space bounds (ctx->boundCorners, built at upload) are projected through the lens onto the film: a ray through film
+// point F(u,v) and lens point o = position + offset reaches P = o + s (o - F), s > 0 (Camera::getRayPassingThrough,
+// core/Camera.cpp:140-144, d = -normalize(F - o)), so P is seen at F = o - (P - o) / s with s fixed by F lying in the film
+// plane. The projection of a convex set is the hull of its projected corners, for every lens offset inside the square
+// that holds the lens disk; the rectangle is their bounding box plus a pixel of margin. A path through a pixel outside it
+// misses every instance: it carries no radiance (the scene has no light that shines on rays that miss, else cullable is
+// false), needs no slot and no ray - it is only counted. Whole frame when any corner is not safely in front of the lens.
+static void cull_rect(const ne_b200_ctx* ctx, int* rx0, int* ry0, int* rw, int* rh) {
+	const int W = ctx->W, H = ctx->H;
+	*rx0 = 0; *ry0 = 0; *rw = W; *rh = H;
+	if (!ctx->cullable || getenv("NE_B200_NO_CULL")) return;
+	const DCamera& c = ctx->cam;
+	auto dot3 = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+	const double Hv[3] = {c.horizontal.x, c.horizontal.y, c.horizontal.z}, Vv[3] = {c.vertical.x, c.vertical.y, c.vertical.z};
+	const double n[3] = {Hv[1] * Vv[2] - Hv[2] * Vv[1], Hv[2] * Vv[0] - Hv[0] * Vv[2], Hv[0] * Vv[1] - Hv[1] * Vv[0]};
+	const double hh = dot3(Hv, Hv), vv = dot3(Vv, Vv);
+	if (!(hh > 0) || !(vv > 0)) return;
+	double u0 = INFINITY, u1 = -INFINITY, v0 = INFINITY, v1 = -INFINITY;
+	const double R = std::fabs(double(c.lens_radius)) * 1.001;
+	for (int k = 0; k < 4; k++) {  // the corners of the square around the lens disk
+		const double sx = (k & 1) ? R : -R, sy = (k & 2) ? R : -R;
+		const double o[3] = {c.position.x + sx * c.side.x + sy * c.up.x, c.position.y + sx * c.side.y + sy * c.up.y, c.position.z + sx * c.side.z + sy * c.up.z};
+		const double oll[3] = {o[0] - c.lower_left.x, o[1] - c.lower_left.y, o[2] - c.lower_left.z};
+		const double den = dot3(n, oll);
+		if (!(std::fabs(den) > 0)) return;
+		for (size_t i = 0; i + 2 < ctx->boundCorners.size(); i += 3) {
+			const double Po[3] = {ctx->boundCorners[i] - o[0], ctx->boundCorners[i + 1] - o[1], ctx->boundCorners[i + 2] - o[2]};
+			const double s = dot3(n, Po) / den;
+			// the corner must be well in front of the lens (s = distance along the view axis in units of the film distance)
+			if (!(s > 1e-3) || !std::isfinite(s)) return;
+			const double F[3] = {oll[0] - Po[0] / s, oll[1] - Po[1] / s, oll[2] - Po[2] / s};  // F - lower_left
+			const double u = dot3(F, Hv) / hh, v = dot3(F, Vv) / vv;
+			if (!std::isfinite(u) || !std::isfinite(v)) return;
+			u0 = std::min(u0, u); u1 = std::max(u1, u); v0 = std::min(v0, v); v1 = std::max(v1, v);
+		}
+	}
+	if (!(u0 <= u1)) {  // nothing hittable at all: one pixel keeps the bookkeeping uniform
+		*rw = 1; *rh = 1;
+		return;
+	}
+	// pixel x covers u in [x / W, (x + 1) / W): one pixel of margin plus a relative epsilon for the fp32 arithmetic of the kernel
+	const double eps = 1e-4;
+	int x0 = int(std::floor((u0 - eps) * W)) - 1, x1 = int(std::ceil((u1 + eps) * W)) + 1;
+	int y0 = int(std::floor((v0 - eps) * H)) - 1, y1 = int(std::ceil((v1 + eps) * H)) + 1;
+	x0 = std::max(0, std::min(W, x0)); x1 = std::max(x0, std::min(W, x1));
+	y0 = std::max(0, std::min(H, y0)); y1 = std::max(y0, std::min(H, y1));
+	if (W % 8 == 0 && H % 4 == 0) {  // keep the 8x4 tiling of the camera rays
+		x0 &= ~7; y0 &= ~3;
+		x1 = std::min(W, (x1 + 7) & ~7); y1 = std::min(H, (y1 + 3) & ~3);
+	}
+	if (x1 <= x0 || y1 <= y0) { x0 = 0; y0 = 0; x1 = 1; y1 = 1; }  // off-screen: as above
+	*rx0 = x0; *ry0 = y0; *rw = x1 - x0; *rh = y1 - y0;
+}
+
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
-	const unsigned long long work = (unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin);
-	if (work == 0 || bounces == 0) return NE_B200_OK;
+	if ((unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin) == 0 || bounces == 0) return NE_B200_OK;
+	int rx0, ry0, rw, rh;
+	cull_rect(ctx, &rx0, &ry0, &rw, &rh);
+	const unsigned long long work = (unsigned long long)rw * rh * (unsigned long long)(sppEnd - sppBegin);
+	ctx->pathsCulled += ((unsigned long long)ctx->W * ctx->H - (unsigned long long)rw * rh) * (unsigned long long)(sppEnd - sppBegin);
 	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 26));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
 	int rc = wavefront_ensure(ctx, nSlots);
@@ -1442,6 +1507,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	dyn.seed = seed;
 	dyn.sppBegin = sppBegin;
 	dyn.bounces = bounces;
+	dyn.rx0 = rx0; dyn.ry0 = ry0; dyn.rw = rw; dyn.rh = rh;
 
 	// ---- production: one graph launch, no host involvement until ne_b200_wait
 	const bool hostLoop = env_u32("NE_B200_HOST_LOOP", 0) != 0 || w->graphBroken;

@@ -435,3 +435,53 @@ def test_adaptive_stopping(ctx):
     from narvalengine_b200.abi import NarvalB200Error
     with pytest.raises(NarvalB200Error):
         ctx.render_adaptive(cam, W, H, 8, 8, 8, 1e-3, 6)
+
+
+@pytest.mark.parametrize("case", ["c2_small", "volume_offcentre", "camera_inside", "pointlit", "sphere_only"])
+def test_camera_ray_culling_changes_nothing(ctx, case, monkeypatch):
+    """Camera rays are generated only for the pixel rectangle that everything hittable projects into (cull_rect,
+    csrc/ne_wavefront.cu); the other paths are counted, not traced. The image must be the one rendered without culling
+    (NE_B200_NO_CULL=1) up to the order of fp32 splats, the path count must be the whole frame's, and fewer rays must be
+    traced when the scene covers part of the frame only."""
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    grid = scenes.c2_density(32)
+    if case == "c2_small":
+        b, cp, partial = scenes.c2_scene(grid), scenes.C2_CAMERA, True
+    elif case == "volume_offcentre":  # rotated, off-centre box, wide aperture: the lens offsets matter
+        b = scenes.SceneBuilder()
+        vol = b.add_volume_dense(grid)
+        b.add_volume_material("cloud", (1.1, 1.1, 1.1), (.01, .01, .01), 20.0, vol, "hg", 0.0)
+        b.add_emitter("light", (100, 100, 70))
+        b.add_volume("cloud", (1.5, 0.7, 0.5), (20, 35, 10), (2.0, 1.2, 1.6))
+        b.add_point("light", (0, 6, 0))
+        cp, partial = scenes.CameraParams((0, 0.5, -7), (0.4, 0.4, 0), 40.0, aperture=0.6, focus=6.0), True
+    elif case == "camera_inside":  # the camera sits inside the medium's box: nothing can be culled
+        b, cp, partial = scenes.c2_scene(grid), scenes.CameraParams((0.3, 0.2, -1.0), (0, 0, 0), 60.0), False
+    elif case == "pointlit":      # floor and wall run off the frame
+        b, cp, partial = scenes.point_lit_surface_scene(), scenes.CameraParams((0, 2, -5), (0, 1, 0), 45.0), False
+    else:  # an emitter sphere and a small rectangle in an otherwise empty frame
+        b = scenes.SceneBuilder()
+        b.add_microfacet("m", (.8, .6, .4), 0.7, 0.0)
+        b.add_emitter("bulb", (30, 25, 20))
+        b.add_rectangle("m", (-0.8, 0.2, 1.0), (60, 20, 0), (1.5, 1.0, 1))
+        b.add_sphere("bulb", (0.9, 0.8, 0.3), 0.35)
+        cp, partial = scenes.CameraParams((0, 0.5, -6), (0, 0.5, 0), 45.0), True
+    W, H, spp = 160, 88, 8   # W % 8 == 0, H % 4 == 0: tiled rectangle
+    a, ca = render_counted(ctx, b, cp, W, H, spp, seed=3)
+    monkeypatch.setenv("NE_B200_NO_CULL", "1")
+    n, cn = render_counted(ctx, b, cp, W, H, spp, seed=3)
+    assert n.mean() > 0
+    np.testing.assert_allclose(a, n, rtol=2e-4, atol=1e-5 * float(n.mean()))
+    assert ca["paths"] == cn["paths"] == W * H * spp
+    for k in ("scatter_events", "surface_events", "delta_steps", "shadow_rays"):
+        assert ca[k] == cn[k], k
+    if partial:
+        assert ca["extend_rays"] < 0.8 * cn["extend_rays"]
+    else:
+        assert ca["extend_rays"] == cn["extend_rays"]
+    # a frame whose size is not a multiple of the 8x4 tile
+    monkeypatch.delenv("NE_B200_NO_CULL")
+    a2 = render(ctx, b, cp, 150, 81, spp, seed=3)
+    monkeypatch.setenv("NE_B200_NO_CULL", "1")
+    n2 = render(ctx, b, cp, 150, 81, spp, seed=3)
+    np.testing.assert_allclose(a2, n2, rtol=2e-4, atol=1e-5 * float(n2.mean()))
