@@ -711,7 +711,7 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	ctx->l2Pool = nullptr;
 	ctx->l2PoolBytes = 0;
 	for (const DVolume& o : vols) {
-		ctx->majTableBytes += (size_t(o.bx) * o.by * o.bz * sizeof(unsigned short) + 15) & ~size_t(15);
+		ctx->majTableBytes += (size_t(o.bx + 2) * (o.by + 2) * (o.bz + 2) * sizeof(unsigned short) + 15) & ~size_t(15);
 		const size_t pb = size_t(o.n_slots) * BRICK_VOX * sizeof(float);
 		if (pb > ctx->l2PoolBytes) { ctx->l2PoolBytes = pb; ctx->l2Pool = o.pool; }
 	}

@@ -11,6 +11,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "ne_ctx.h"
 
 using namespace ne;
@@ -277,20 +279,53 @@ static __global__ void k_brick_skip_floor(unsigned short* __restrict__ t, int n,
 	if ((threadIdx.x & 31) == 0 && m) atomicAdd(nSkippable, (unsigned)__popc(m));
 }
 
+// The table the walks read (layout and encoding: ne_tracking.cuh, BrickTracker): the bricks with a one-brick apron, IEEE
+// halves. codes[] = the un-aproned 16-bit codes above (only "has a record" vs "empty, distance d" is taken from them; the
+// majorant itself comes from the cell, times K = 2^k, rounded UP to the next half).
+static __global__ void k_brick_table(const int2* __restrict__ cells, const unsigned short* __restrict__ codes, int nbx, int nby, int nbz, float K,
+                                     unsigned short* __restrict__ out) {
+	const int SY = nbx + 2, SZ = SY * (nby + 2);
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= SZ * (nbz + 2)) return;
+	const int x = i % SY - 1, y = (i / SY) % (nby + 2) - 1, z = i / SZ - 1;
+	unsigned short h = 0xFC00u;  // -inf: outside the grid
+	if (unsigned(x) < unsigned(nbx) && unsigned(y) < unsigned(nby) && unsigned(z) < unsigned(nbz)) {
+		const int b = (z * nby + y) * nbx + x;
+		const unsigned short c = codes[b];
+		const float inv = __int_as_float(cells[b].y);
+		if (!(c & 0x8000u) && cells[b].x >= 0 && inv > 0) {
+			h = __half_as_ushort(__float2half_ru((1.0f / inv) * K));
+			if (h == 0) h = 1;             // below the smallest subnormal half: still an upper bound
+			if (h >= 0x7C00u) h = 0x7BFFu;  // cannot happen: K puts the global maximum below 2^14
+		} else {
+			const float d = float(max(1u, unsigned(c & 0x7fffu)));
+			h = __half_as_ushort(__float2half_rn(-d));  // 1..16: exact
+		}
+	}
+	out[i] = h;
+}
+
 int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol) {
 	const int nb = vol.bx * vol.by * vol.bz;
+	const int nt = (vol.bx + 2) * (vol.by + 2) * (vol.bz + 2);
 	cudaStream_t st = ctx->stream;
-	unsigned short *d = nullptr, *tmp = nullptr;
+	unsigned short *d = nullptr, *tmp = nullptr, *table = nullptr;
+	NE_CUDA_OK(cudaMallocAsync(&d, size_t(std::max(1, nb)) * sizeof(unsigned short), st));
 	// padded to 16 bytes: the tracking kernels copy the table to shared memory with bulk async copies (16-byte granules)
-	NE_CUDA_OK(cudaMallocAsync(&d, ((size_t(std::max(1, nb)) * sizeof(unsigned short) + 15) & ~size_t(15)) + 16, st));
-	ctx->sceneAllocs.push_back(d);
-	// 32767 * scale exceeds the global maximum by a few ulps, so the largest brick majorant is still bounded from above
-	vol.maj_scale = vol.max_density > 0 ? vol.max_density * (1.0f / 32767.0f) * 1.000001f : 1.0f;
+	NE_CUDA_OK(cudaMallocAsync(&table, ((size_t(nt) * sizeof(unsigned short) + 15) & ~size_t(15)) + 16, st));
+	ctx->sceneAllocs.push_back(table);
+	// the scale of the intermediate 16-bit codes (only their empty / non-empty split and the distance field are used)
+	const float codeScale = vol.max_density > 0 ? vol.max_density * (1.0f / 32767.0f) * 1.000001f : 1.0f;
+	// majorant * 2^k as a half: k puts the global maximum into [2^13, 2^14), far from the half range's ends
+	int e = 0;
+	if (vol.max_density > 0 && std::isfinite(vol.max_density)) frexpf(vol.max_density, &e);
+	const float K = ldexpf(1.0f, 14 - e);
+	vol.maj_scale = ldexpf(1.0f, e - 14);
 	if (nb > 0) {
 		NE_CUDA_OK(cudaMallocAsync(&tmp, nb * sizeof(unsigned short), st));
 		const unsigned grid = unsigned((nb + 255) / 256);
 		// an odd number of relaxations, so the last one lands in `d`
-		k_brick_maj16<<<grid, 256, 0, st>>>(vol.cells, nb, vol.maj_scale, tmp);
+		k_brick_maj16<<<grid, 256, 0, st>>>(vol.cells, nb, codeScale, tmp);
 		unsigned short *src = tmp, *dst = d;
 		for (int i = 0; i < NE_SKIP_MAX - 1; i++) {
 			k_brick_skip<<<grid, 256, 0, st>>>(src, dst, vol.bx, vol.by, vol.bz);
@@ -313,7 +348,11 @@ int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol) {
 		// saves 20-25 % on a WDAS-scale sparse cloud: use it when a third of the table is far from any density
 		if (double(nSkippable) >= 0.33 * double(nb)) ctx->skipWorthwhile = true;
 	}
-	vol.maj16 = d;
+	k_brick_table<<<unsigned((nt + 255) / 256), 256, 0, st>>>(vol.cells, d, vol.bx, vol.by, vol.bz, K, table);
+	ctx->kernelLaunches++;
+	NE_CUDA_OK(cudaGetLastError());
+	NE_CUDA_OK(cudaFreeAsync(d, st));
+	vol.maj16 = table;
 	return NE_B200_OK;
 }
 

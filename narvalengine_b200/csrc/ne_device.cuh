@@ -707,58 +707,6 @@ NE_D float brick_density(const float* __restrict__ pool, int slot, V3 g, int bx,
 	return fmaf(fz, d1 - d0, d0);
 }
 
-// Brick DDA over the grid-space ray g(t) = g0 + t * gd. Branch-free step: the axis with the nearest crossing
-// advances; all lanes of a warp run the same instructions whatever axis each of them crosses.
-struct BrickDDA {
-	int bx, by, bz;       // current brick
-	float nx, ny, nz;     // ray parameter of the next boundary crossing per axis
-	float dx, dy, dz;     // parameter distance between crossings per axis (sign of gd folded into the step below)
-	NE_D void init(int nbx, int nby, int nbz, V3 g, V3 gd) {
-		bx = min(max(int(floorf(g.x * 0.125f)), 0), nbx - 1);
-		by = min(max(int(floorf(g.y * 0.125f)), 0), nby - 1);
-		bz = min(max(int(floorf(g.z * 0.125f)), 0), nbz - 1);
-		float ix = 1.0f / gd.x, iy = 1.0f / gd.y, iz = 1.0f / gd.z;  // +-inf for an axis-parallel ray
-		dx = gd.x != 0 ? 8.0f * fabsf(ix) : INFINITY;
-		dy = gd.y != 0 ? 8.0f * fabsf(iy) : INFINITY;
-		dz = gd.z != 0 ? 8.0f * fabsf(iz) : INFINITY;
-		nx = gd.x != 0 ? (float((gd.x > 0 ? bx + 1 : bx) << 3) - g.x) * ix : INFINITY;
-		ny = gd.y != 0 ? (float((gd.y > 0 ? by + 1 : by) << 3) - g.y) * iy : INFINITY;
-		nz = gd.z != 0 ? (float((gd.z > 0 ? bz + 1 : bz) << 3) - g.z) * iz : INFINITY;
-	}
-	NE_D float exit_t() const { return fminf(nx, fminf(ny, nz)); }
-	// advance to the next brick; false when the walk leaves the table
-	NE_D bool step(int nbx, int nby, int nbz, V3 gd) {
-		bool cx = nx <= ny && nx <= nz;
-		bool cy = !cx && ny <= nz;
-		bool cz = !cx && !cy;
-		bx += cx ? (gd.x > 0 ? 1 : -1) : 0;
-		by += cy ? (gd.y > 0 ? 1 : -1) : 0;
-		bz += cz ? (gd.z > 0 ? 1 : -1) : 0;
-		nx += cx ? dx : 0.0f;
-		ny += cy ? dy : 0.0f;
-		nz += cz ? dz : 0.0f;
-		return (unsigned(bx) < unsigned(nbx)) & (unsigned(by) < unsigned(nby)) & (unsigned(bz) < unsigned(nbz));
-	}
-	// Empty-space skip: every brick within Chebyshev distance r of the current one is empty (and inside the table). Move
-	// the DDA, in one go, to the LAST brick the ray visits inside that cube, so that exit_t() is where it leaves the cube
-	// and the next step() crosses the cube's face. Per axis the ray crosses at most r boundaries before that moment:
-	// the exit axis exactly r (its (r+1)-th crossing IS the exit), the others as many as lie before the exit time.
-	NE_D void jump(int r, V3 gd) {
-		const float fr = float(r);
-		const float tx = fmaf(fr, dx, nx), ty = fmaf(fr, dy, ny), tz = fmaf(fr, dz, nz);  // inf for an axis-parallel ray
-		const float tc = fminf(tx, fminf(ty, tz));
-		int kx = nx <= tc ? min(r, int(__fdividef(tc - nx, dx)) + 1) : 0;
-		int ky = ny <= tc ? min(r, int(__fdividef(tc - ny, dy)) + 1) : 0;
-		int kz = nz <= tc ? min(r, int(__fdividef(tc - nz, dz)) + 1) : 0;
-		bx += gd.x > 0 ? kx : -kx;
-		by += gd.y > 0 ? ky : -ky;
-		bz += gd.z > 0 ? kz : -kz;
-		nx = kx ? fmaf(float(kx), dx, nx) : nx;
-		ny = ky ? fmaf(float(ky), dy, ny) : ny;
-		nz = kz ? fmaf(float(kz), dz, nz) : nz;
-	}
-};
-
 }  // namespace ne
 #include "ne_tracking.cuh"  // Tracker, ratio_walk, delta_walk, grid_tr, grid_scatter, grid_sample
 namespace ne {

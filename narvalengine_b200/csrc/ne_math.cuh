@@ -10,6 +10,7 @@
 //   glm::min/max              (b<a)?b:a / (a<b)?b:a  (NaN behaviour differs from fminf/fmaxf)
 //   glm::mix / lerp           x*(1-a) + y*a                                        glm/detail/func_common.inl:104-112
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>

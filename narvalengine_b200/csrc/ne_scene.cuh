@@ -26,10 +26,12 @@ struct DVolume {
 	int n_slots;
 	const int2* cells;
 	const float* pool;
-	// per-brick majorant as a 16-bit multiple of maj_scale, rounded UP (any bound >= the brick's maximum keeps tracking
-	// unbiased): 2 bytes per brick, so the table a walk consults at every brick crossing stays in L1 (64 KB for 256^3)
+	// per-brick majorants as IEEE halves in a table with a one-brick apron, (bx+2) x (by+2) x (bz+2) entries (layout and
+	// encoding: ne_tracking.cuh, BrickTracker): majorant = float(half) * maj_scale, rounded UP (any bound >= the brick's
+	// maximum keeps tracking unbiased); negative = empty brick / outside. 2 bytes per brick: 79 KB for a 256^3 grid, copied
+	// to shared memory by the tracking kernels when it fits
 	const unsigned short* maj16;
-	float maj_scale;
+	float maj_scale;  // 2^-k
 	float max_density, inv_max_density;  // GridMedia::invMaxDensity, GridMedia.cpp:12
 };
 

@@ -78,34 +78,50 @@ struct Tracker<TRACK_GLOBAL> {
 	NE_D void after_candidate(W&) {}
 };
 
+// The per-brick majorant table a walk reads at every brick crossing (built by ne_bricks.cu, k_brick_table):
+//   layout   (nbx+2) x (nby+2) x (nbz+2) entries of 2 bytes, x fastest: the bricks with a ONE-BRICK APRON all round.
+//            Entry of brick (bx,by,bz) = table[(bz+1)*SZ + (by+1)*SY + (bx+1)], SY = nbx+2, SZ = SY*(nby+2).
+//   entry    an IEEE half:  h > 0   the brick's majorant times 2^k, rounded UP (k per volume, DVolume::maj_scale = 2^-k),
+//                                   so sigma_bar x majorant = (sig * maj_scale) * float(h): one conversion and one multiply
+//                           h = -d  empty brick; d = Chebyshev distance in bricks (1..16) to the nearest brick with a record
+//                                   or to the outside (TRACK_SKIP crosses the whole cube of empty bricks in one move)
+//                           -inf    the apron: the walk has left the grid. Stepping out is therefore detected by the value
+//                                   the step reads anyway - no per-axis bounds test in the loop.
+// One brick crossing (move()) is ~30 instructions: 2 compares pick the axis (equality with the exit time, which IS one of
+// nx/ny/nz), 3 predicated adds advance the brick and 3 the boundary times, 2 multiply-adds form the table index.
+NE_D float half_bits_to_float(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+
 template <int MODE>
 struct BrickTracker {
 	const int2* __restrict__ cells;
 	const float* __restrict__ pool;
-	const unsigned short* __restrict__ maj16;
-	uint32_t majS;  // TRACK_BRICK_SM: shared-window address of the table
-	float majScale;
-	int nbx, nby, nbz;
+	const unsigned short* __restrict__ tab;  // global-memory table (not TRACK_*_SM)
+	uint32_t tabS;  // TRACK_*_SM: shared-window address of the table
+	int SY, SZ;     // table strides (apron layout)
+	int nbx, nby;   // brick grid (the un-aproned cells[] index of a candidate's record)
 	V3 g0, gd;      // grid-space ray g(t) = g0 + t * gd
 	float t, tFar;
 	float tExit;    // where the ray leaves the current brick (clipped to tFar)
 	float sig;      // sigma_bar per unit density per unit t
-	float invSig;
-	float majQ;     // majorant of the current brick (the 16-bit upper bound), 0 = nothing to collide with
-	float invMaj;   // 1 / majQ, set when a candidate is proposed
+	float sigK;     // sig * 2^-k: times the table's half gives sigma_bar x majorant
 	float sigMaj;   // sigma_bar x majorant of the current brick: optical depth per unit t (0 in an empty brick)
+	float invMaj;   // 1 / majorant, set when a candidate is proposed
 	float tau;      // optical depth left before the next candidate
 	float cap;      // scratch of wants_candidate(): optical depth of the rest of the current brick
-	BrickDDA dda;
+	bool out;       // the last step left the grid
+	// brick DDA: current brick, step per axis (+-1), ray parameter of the next boundary crossing per axis and its period
+	int bx, by, bz, sx, sy, sz;
+	float nx, ny, nz, dx, dy, dz;
 
 	template <class W>
 	NE_D void init(const DVolume& v, const DMaterial& m, Ray rayOCS, float tStart, float tEnd, W& wr, Stats& st) {
 		cells = v.cells;
 		pool = v.pool;
-		maj16 = v.maj16;
-		if (NE_TRACK_IS_SM(MODE)) majS = uint32_t(__cvta_generic_to_shared(v.maj16));
-		majScale = v.maj_scale;
-		nbx = v.bx; nby = v.by; nbz = v.bz;
+		tab = v.maj16;
+		if (NE_TRACK_IS_SM(MODE)) tabS = uint32_t(__cvta_generic_to_shared(v.maj16));
+		nbx = v.bx; nby = v.by;
+		SY = v.bx + 2;
+		SZ = SY * (v.by + 2);
 		V3 res(float(v.W), float(v.H), float(v.D));
 		g0 = (rayOCS.o + V3(0.5f)) * res;
 		gd = rayOCS.d * res;
@@ -113,31 +129,37 @@ struct BrickTracker {
 		tFar = tEnd;
 		V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
 		sig = avg(ext * m.density_mult);
-		invSig = 1.0f / sig;
-		dda.init(nbx, nby, nbz, point(tStart), gd);
-		dda.nx += tStart; dda.ny += tStart; dda.nz += tStart;
+		sigK = sig * v.maj_scale;
+		// DDA set-up at the segment's first point
+		V3 g = point(tStart);
+		bx = min(max(int(floorf(g.x * 0.125f)), 0), v.bx - 1);
+		by = min(max(int(floorf(g.y * 0.125f)), 0), v.by - 1);
+		bz = min(max(int(floorf(g.z * 0.125f)), 0), v.bz - 1);
+		float ix = 1.0f / gd.x, iy = 1.0f / gd.y, iz = 1.0f / gd.z;  // +-inf for an axis-parallel ray
+		sx = gd.x > 0 ? 1 : -1; sy = gd.y > 0 ? 1 : -1; sz = gd.z > 0 ? 1 : -1;
+		dx = gd.x != 0 ? 8.0f * fabsf(ix) : INFINITY;
+		dy = gd.y != 0 ? 8.0f * fabsf(iy) : INFINITY;
+		dz = gd.z != 0 ? 8.0f * fabsf(iz) : INFINITY;
+		nx = gd.x != 0 ? (float((gd.x > 0 ? bx + 1 : bx) << 3) - g.x) * ix + tStart : INFINITY;
+		ny = gd.y != 0 ? (float((gd.y > 0 ? by + 1 : by) << 3) - g.y) * iy + tStart : INFINITY;
+		nz = gd.z != 0 ? (float((gd.z > 0 ? bz + 1 : bz) << 3) - g.z) * iz + tStart : INFINITY;
 		enter_brick(st);
 		tau = exp_variate_fast(wr);
 	}
 	NE_D V3 point(float tt) const { return V3(fmaf(gd.x, tt, g0.x), fmaf(gd.y, tt, g0.y), fmaf(gd.z, tt, g0.z)); }
-	// A brick crossing reads TWO BYTES: the brick's majorant from the compact table (L1-resident; the 8-byte
-	// {slot, 1/majorant} cells it replaced on this path were an L2 round trip per crossing, the walk's critical path).
-	// An EMPTY brick's entry holds how far the emptiness reaches instead: the walk then crosses the whole cube of empty
-	// bricks around it in this one move (nothing happens to tau in empty space, so the walk's law is untouched).
+	NE_D float exit_t() const { return fminf(nx, fminf(ny, nz)); }
+	// Reads the brick's table entry (see the layout above): two bytes from shared memory or L1.
 	NE_D void enter_brick(Stats& st) {
 		st.brick_visits++;
-		unsigned v;
-		if (NE_TRACK_IS_SM(MODE)) {
-			unsigned short h;
-			asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(majS + 2u * uint32_t((dda.bz * nby + dda.by) * nbx + dda.bx)));
-			v = h;
-		} else v = __ldg(maj16 + (dda.bz * nby + dda.by) * nbx + dda.bx);
-		const bool empty = (v & 0x8000u) != 0;
-		majQ = empty ? 0.0f : float(v) * majScale;
-		sigMaj = sig * majQ;
-		const int r = int(v & 0x7fffu) - 1;
-		if (NE_TRACK_IS_SKIP(MODE) && empty && r > 0) dda.jump(r, gd);
-		tExit = fminf(dda.exit_t(), tFar);
+		const int idx = (bz + 1) * SZ + (by + 1) * SY + (bx + 1);
+		unsigned short h;
+		if (NE_TRACK_IS_SM(MODE)) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(tabS + 2u * uint32_t(idx)));
+		else h = __ldg(tab + idx);
+		const float f = half_bits_to_float(h);
+		out = f == -INFINITY;
+		if (NE_TRACK_IS_SKIP(MODE) && f < -1.0f && !out) jump(int(-f) - 1);
+		sigMaj = fmaxf(sigK * f, 0.0f);  // empty bricks (negative entries) have nothing to collide with
+		tExit = fminf(exit_t(), tFar);
 	}
 	template <class W>
 	NE_D bool wants_candidate(W&) {
@@ -148,16 +170,41 @@ struct BrickTracker {
 		tau -= cap;
 		t = tExit;
 		if (tExit >= tFar) return TRACK_END;
-		if (!dda.step(nbx, nby, nbz, gd)) return TRACK_END;
+		// cross the nearest boundary: tExit < tFar here, so it IS one of nx / ny / nz
+		const bool cx = nx == tExit;
+		const bool cy = !cx && ny == tExit;
+		const bool cz = !cx && !cy;
+		if (cx) { bx += sx; nx += dx; }
+		if (cy) { by += sy; ny += dy; }
+		if (cz) { bz += sz; nz += dz; }
 		enter_brick(st);
-		return TRACK_MOVED;
+		return out ? TRACK_END : TRACK_MOVED;
 	}
-	// Only a candidate needs the brick's record: its slot is looked up here (majQ > 0, so the brick has one).
+	// Empty-space skip: every brick within Chebyshev distance r of the current one is empty (and inside the grid). Move the
+	// DDA, in one go, to the LAST brick the ray visits inside that cube, so that exit_t() is where it leaves the cube and the
+	// next move() crosses the cube's face. Per axis the ray crosses at most r boundaries before that moment: the exit axis
+	// exactly r (its (r+1)-th crossing IS the exit), the others as many as lie before the exit time.
+	NE_D void jump(int r) {
+		const float fr = float(r);
+		const float tx = fmaf(fr, dx, nx), ty = fmaf(fr, dy, ny), tz = fmaf(fr, dz, nz);  // inf for an axis-parallel ray
+		const float tc = fminf(tx, fminf(ty, tz));
+		int kx = nx <= tc ? min(r, int(__fdividef(tc - nx, dx)) + 1) : 0;
+		int ky = ny <= tc ? min(r, int(__fdividef(tc - ny, dy)) + 1) : 0;
+		int kz = nz <= tc ? min(r, int(__fdividef(tc - nz, dz)) + 1) : 0;
+		bx += sx * kx;
+		by += sy * ky;
+		bz += sz * kz;
+		nx = kx ? fmaf(float(kx), dx, nx) : nx;
+		ny = ky ? fmaf(float(ky), dy, ny) : ny;
+		nz = kz ? fmaf(float(kz), dz, nz) : nz;
+	}
+	// Only a candidate needs the brick's record: its slot is looked up here (sigMaj > 0, so the brick has one).
 	NE_D float candidate_density(const DVolume&) {
-		invMaj = __fdividef(1.0f, majQ);
-		t = fmaf(tau * invSig, invMaj, t);
-		int slot = __ldg(&cells[(dda.bz * nby + dda.by) * nbx + dda.bx].x);
-		return brick_density(pool, slot, point(t), dda.bx, dda.by, dda.bz);
+		const float r = __fdividef(1.0f, sigMaj);
+		invMaj = sig * r;
+		t = fmaf(tau, r, t);
+		int slot = __ldg(&cells[(bz * nby + by) * nbx + bx].x);
+		return brick_density(pool, slot, point(t), bx, by, bz);
 	}
 	template <class W>
 	NE_D void after_candidate(W& wr) { tau = exp_variate_fast(wr); }

@@ -496,7 +496,7 @@ struct WarpReserve {
 // these variants when the tables fit (wavefront_render); the kernels then run ONE 1024-thread block per SM, which is
 // the same 32 warps and 64 registers per thread as four 256-thread blocks, with one copy of the table instead of four.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ uint32_t maj_table_bytes(const DVolume& v) { return (uint32_t(v.bx * v.by * v.bz) * 2u + 15u) & ~15u; }
+__device__ __forceinline__ uint32_t maj_table_bytes(const DVolume& v) { return (uint32_t((v.bx + 2) * (v.by + 2) * (v.bz + 2)) * 2u + 15u) & ~15u; }
 __device__ __forceinline__ void stage_majorants(const DScene& g, SceneCache& sh, unsigned char* table, unsigned long long* bar) {
 	const uint32_t barS = smem_u32(bar);
 	if (threadIdx.x == 0) {
