@@ -57,7 +57,11 @@ struct ne_b200_ctx {
 	// in DCounters::stage_ns and are added by ne_b200_get_counters
 	double msRender = 0, msVolume = 0, msExtend = 0, msShade = 0, msOther = 0, msUpload = 0;
 	cudaEvent_t evA = nullptr, evB = nullptr;
-	ne_wavefront_state* wf = nullptr;
+	// the wavefront renderer's state, one per LANE: a render is split into up to two independent sample batches that run on
+	// two streams at once, so that one lane's kernels fill the tails of the other's (ne_wavefront.cu, wavefront_render)
+	ne_wavefront_state* wf[2] = {nullptr, nullptr};
+	cudaStream_t laneStream[2] = {nullptr, nullptr};
+	cudaEvent_t laneFork = nullptr, laneJoin[2] = {nullptr, nullptr};
 	void* scratch = nullptr;  // reusable device scratch (dense grid staging of the brick builder, resolve buffers)
 	size_t scratchBytes = 0;
 	void* pinned = nullptr;  // pinned host staging for large uploads from pageable caller memory (ne_bricks.cu h2d_staged)

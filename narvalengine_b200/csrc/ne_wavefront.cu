@@ -1116,7 +1116,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
 struct WfVariant {
 	unsigned long long sceneGen;
 	int W, H;
-	int trace, fuse, brick, skip, sm, genBlocks, scatBlocks, stamps, media, surfaces;
+	int trace, fuse, brick, skip, sm, genBlocks, scatBlocks, stamps, media, surfaces, foldTimes;
 	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist;
 	uint32_t nSlots;
 };
@@ -1161,8 +1161,16 @@ static void wavefront_free_state(ne_wavefront_state* w) {
 size_t wavefront_record_bytes() { return sizeof(PathSlot); }
 
 void wavefront_free(ne_b200_ctx* ctx) {
-	wavefront_free_state(ctx->wf);
-	ctx->wf = nullptr;
+	for (int l = 0; l < 2; l++) {
+		wavefront_free_state(ctx->wf[l]);
+		ctx->wf[l] = nullptr;
+		if (ctx->laneStream[l]) cudaStreamDestroy(ctx->laneStream[l]);
+		if (ctx->laneJoin[l]) cudaEventDestroy(ctx->laneJoin[l]);
+		ctx->laneStream[l] = nullptr;
+		ctx->laneJoin[l] = nullptr;
+	}
+	if (ctx->laneFork) cudaEventDestroy(ctx->laneFork);
+	ctx->laneFork = nullptr;
 }
 
 template <class T>
@@ -1208,16 +1216,18 @@ static cudaError_t wavefront_build(ne_b200_ctx* ctx, uint32_t nSlots, ne_wavefro
 
 // A pool that does not fit (a smaller or busy GPU: the default is 64 Mi slots, ~29 GB) is retried at half the size down
 // to a floor; the renderer then simply runs more, shorter iterations.
-static int wavefront_ensure(ne_b200_ctx* ctx, uint32_t nSlots) {
-	if (ctx->wf && ctx->wf->nSlots >= nSlots) return NE_B200_OK;
+static int wavefront_ensure(ne_b200_ctx* ctx, int lane, uint32_t nSlots) {
+	if (ctx->wf[lane] && ctx->wf[lane]->nSlots >= nSlots) return NE_B200_OK;
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-	wavefront_free(ctx);
+	if (ctx->laneStream[lane]) NE_CUDA_OK(cudaStreamSynchronize(ctx->laneStream[lane]));
+	wavefront_free_state(ctx->wf[lane]);
+	ctx->wf[lane] = nullptr;
 	const uint32_t floorSlots = std::min(nSlots, 1u << 16);
 	for (uint32_t n = nSlots;; n = std::max(floorSlots, n / 2)) {
 		ne_wavefront_state* w = nullptr;
 		cudaError_t e = wavefront_build(ctx, n, &w);
 		if (e == cudaSuccess) {
-			ctx->wf = w;
+			ctx->wf[lane] = w;
 			return NE_B200_OK;
 		}
 		cudaGetLastError();  // clear the sticky-less allocation error
@@ -1372,7 +1382,7 @@ static int graph_build(ne_b200_ctx* ctx, ne_wavefront_state* w, const WfParams& 
 		return NE_B200_ERR_CUDA;
 	}
 	DCounters* counters = ctx->dCounters;
-	int foldTimes = 1;
+	int foldTimes = V.foldTimes;
 	void* finArgs[] = {&b, &counters, &foldTimes};
 	kp.func = reinterpret_cast<void*>(k_wf_finish);
 	kp.kernelParams = finArgs;
@@ -1438,17 +1448,18 @@ static void cull_rect(const ne_b200_ctx* ctx, int* rx0, int* ry0, int* rw, int* 
 	*rx0 = x0; *ry0 = y0; *rw = x1 - x0; *rh = y1 - y0;
 }
 
-int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
-	if ((unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin) == 0 || bounces == 0) return NE_B200_OK;
+// One lane's render of samples [sppBegin, sppEnd) on stream `st` (see wavefront_render).
+static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStream_t st, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags,
+                                 bool hostLoopAsked) {
 	int rx0, ry0, rw, rh;
 	cull_rect(ctx, &rx0, &ry0, &rw, &rh);
 	const unsigned long long work = (unsigned long long)rw * rh * (unsigned long long)(sppEnd - sppBegin);
 	ctx->pathsCulled += ((unsigned long long)ctx->W * ctx->H - (unsigned long long)rw * rh) * (unsigned long long)(sppEnd - sppBegin);
-	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 26));
+	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 26) / uint32_t(nLanes));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
-	int rc = wavefront_ensure(ctx, nSlots);
+	int rc = wavefront_ensure(ctx, lane, nSlots);
 	if (rc) return rc;
-	ne_wavefront_state* w = ctx->wf;
+	ne_wavefront_state* w = ctx->wf[lane];
 	nSlots = std::min(nSlots, w->nSlots);  // a pool kept from a larger render is used up to what this one asks for
 	w->b.nSlots = nSlots;
 	WfParams P;
@@ -1494,7 +1505,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	V.surfaces = ctx->nSurfaces > 0 ? 1 : 0;
 	V.budget = P.budget; V.refill = P.refill; V.moves = P.moves; V.walkBudget = P.walkBudget; V.walkRefill = P.walkRefill; V.cutAlways = P.cutAlways;
 	V.l2persist = env_u32("NE_B200_L2_PERSIST", 0) ? 1 : 0;
-	cudaStream_t st = ctx->stream;
+	V.foldTimes = lane == 0 ? 1 : 0;  // concurrent lanes: lane 0's stage clock stands for the render
 	if (V.sm) {
 		static const void* smKernels[] = {(const void*)k_wf_track<TRACK_BRICK_SM, 1024, 1>, (const void*)k_wf_track<TRACK_SKIP_SM, 1024, 1>,
 		                                  (const void*)k_wf_tr<TRACK_BRICK_SM, 1024, 1>, (const void*)k_wf_tr<TRACK_SKIP_SM, 1024, 1>};
@@ -1510,7 +1521,7 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	dyn.rx0 = rx0; dyn.ry0 = ry0; dyn.rw = rw; dyn.rh = rh;
 
 	// ---- production: one graph launch, no host involvement until ne_b200_wait
-	const bool hostLoop = env_u32("NE_B200_HOST_LOOP", 0) != 0 || w->graphBroken;
+	const bool hostLoop = hostLoopAsked || w->graphBroken;
 	if (!hostLoop) {
 		if (!w->haveGraph || memcmp(&w->built, &V, sizeof(V)) != 0) {
 			rc = graph_build(ctx, w, P, V);
@@ -1585,6 +1596,46 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	// mode are the CUDA events above: the stamps were not launched, so k_wf_finish adds only the idle tail to "other")
 	k_wf_finish<<<1, 1, 0, st>>>(w->b, ctx->dCounters, 0);
 	ctx->renderPending = true;
+	return NE_B200_OK;
+}
+
+// Samples [sppBegin, sppEnd) of every pixel. The batch is split into TWO independent halves (different sample indices: Philox
+// keys make them independent paths) that run as two render graphs on two streams at once: while one lane's kernel drains
+// its tail - a persistent tracking kernel waiting for its longest walks, a nearly empty late iteration - the other lane's
+// blocks take the idle SMs. That matters most where a GPU's share of a frame is small (8 GPUs x 8 spp of a 1080p frame: 7
+// iterations x 9 kernels in 4 ms). Both lanes splat into the same accumulation buffer (atomic adds) and count into the same
+// counters. NE_B200_LANES=1 keeps one lane; the host-driven loop and single-sample batches always do.
+int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
+	if ((unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin) == 0 || bounces == 0) return NE_B200_OK;
+	const bool hostLoop = env_u32("NE_B200_HOST_LOOP", 0) != 0;
+	int lanes = int(std::min(2u, std::max(1u, env_u32("NE_B200_LANES", 2))));
+	{
+		// two lanes pay when each has enough paths to fill the GPU on its own; for small batches the doubled number of
+		// (small) launches costs more than the filled tails give back (measured: 64 spp of the C2 frame 28.6 -> 27.8 ms,
+		// 8 spp 4.34 -> 4.69 ms)
+		int rx0, ry0, rw, rh;
+		cull_rect(ctx, &rx0, &ry0, &rw, &rh);
+		const unsigned long long work = (unsigned long long)rw * rh * (unsigned long long)(sppEnd - sppBegin);
+		if (work < (unsigned long long)env_u32("NE_B200_LANES_MIN_WORK", 12u << 20)) lanes = 1;
+	}
+	if (hostLoop || sppEnd - sppBegin < 2) lanes = 1;
+	if (lanes == 1) return wavefront_render_lane(ctx, 0, 1, ctx->stream, sppBegin, sppEnd, bounces, seed, flags, hostLoop);
+	if (!ctx->laneFork) {
+		NE_CUDA_OK(cudaEventCreateWithFlags(&ctx->laneFork, cudaEventDisableTiming));
+		for (int l = 0; l < 2; l++) {
+			NE_CUDA_OK(cudaStreamCreateWithFlags(&ctx->laneStream[l], cudaStreamNonBlocking));
+			NE_CUDA_OK(cudaEventCreateWithFlags(&ctx->laneJoin[l], cudaEventDisableTiming));
+		}
+	}
+	const int mid = sppBegin + (sppEnd - sppBegin + 1) / 2;
+	NE_CUDA_OK(cudaEventRecord(ctx->laneFork, ctx->stream));  // after whatever the caller queued before (clear, uploads)
+	for (int l = 0; l < 2; l++) {
+		NE_CUDA_OK(cudaStreamWaitEvent(ctx->laneStream[l], ctx->laneFork, 0));
+		int rc = wavefront_render_lane(ctx, l, 2, ctx->laneStream[l], l == 0 ? sppBegin : mid, l == 0 ? mid : sppEnd, bounces, seed, flags, false);
+		if (rc) return rc;
+		NE_CUDA_OK(cudaEventRecord(ctx->laneJoin[l], ctx->laneStream[l]));
+		NE_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->laneJoin[l], 0));
+	}
 	return NE_B200_OK;
 }
 
