@@ -26,6 +26,7 @@
 // resident blocks): no host round trip sizes a launch; the host only polls a mapped "done" word every few iterations.
 // Every block stages the scene's instance / material / volume tables in shared memory first (stage_scene).
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -120,20 +121,19 @@ __device__ __forceinline__ void flush_stats_wf(const Stats& st, DCounters* c) {
 	if (threadIdx.x < NE_STAT_FIELDS) blockTotals_[threadIdx.x] = 0;
 	__syncthreads();
 	const unsigned lane = threadIdx.x & 31;
-	const uint32_t v[NE_STAT_FIELDS] = {st.extend_rays, st.shadow_rays, st.delta_steps, st.ratio_steps, st.brick_visits,
-	                                    st.bvh_nodes,   st.tri_tests,   st.prim_tests,  st.scatter_events, st.surface_events};
-#pragma unroll
-	for (int k = 0; k < NE_STAT_FIELDS; k++) {
-		unsigned w = __reduce_add_sync(0xffffffffu, v[k]);
-		if (lane == 0 && w) atomicAdd(&blockTotals_[k], (unsigned long long)w);
+#define NE_FLUSH(k, field)                                                          \
+	{                                                                               \
+		unsigned w = __reduce_add_sync(0xffffffffu, (unsigned)(st.field));          \
+		if (lane == 0 && w) atomicAdd(&blockTotals_[k], (unsigned long long)w);     \
 	}
+	NE_FLUSH(0, extend_rays) NE_FLUSH(1, shadow_rays) NE_FLUSH(2, delta_steps) NE_FLUSH(3, ratio_steps) NE_FLUSH(4, brick_visits)
+	NE_FLUSH(5, bvh_nodes) NE_FLUSH(6, tri_tests) NE_FLUSH(7, prim_tests) NE_FLUSH(8, scatter_events) NE_FLUSH(9, surface_events)
+#undef NE_FLUSH
 	__syncthreads();
-	if (threadIdx.x < NE_STAT_FIELDS && blockTotals_[threadIdx.x]) {
-		unsigned long long* dst[NE_STAT_FIELDS] = {&c->extend_rays, &c->shadow_rays, &c->delta_steps, &c->ratio_steps, &c->brick_visits,
-		                                           &c->bvh_nodes,   &c->tri_tests,   &c->prim_tests,  &c->scatter_events, &c->surface_events};
-		atomicAdd(dst[threadIdx.x], blockTotals_[threadIdx.x]);
-	}
+	// the ten counters are consecutive 64-bit fields of DCounters, in this order, after `paths`
+	if (threadIdx.x < NE_STAT_FIELDS && blockTotals_[threadIdx.x]) atomicAdd(&c->extend_rays + threadIdx.x, blockTotals_[threadIdx.x]);
 }
+static_assert(offsetof(DCounters, surface_events) - offsetof(DCounters, extend_rays) == 9 * sizeof(unsigned long long), "DCounters field order");
 
 __device__ __forceinline__ void splat(float* accum, uint32_t pixel, V3 v) {
 	if (v.x != 0) atomicAdd(accum + 3 * size_t(pixel), v.x);
@@ -344,7 +344,10 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	if (gen == 0) return;
 	const uint32_t freeN = b.c->freeN, freeTake = b.c->freeTake, bumpBase = b.c->bumpBase, par = b.c->par;
 	const unsigned long long workBase = b.c->workNext;
-	const DCamera cam = b.c->dyn.cam;
+	// the camera of this render, staged in shared memory (19 floats that would otherwise sit in registers for the whole kernel)
+	__shared__ DCamera cam;
+	if (threadIdx.x < sizeof(DCamera) / 4) reinterpret_cast<uint32_t*>(&cam)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&b.c->dyn.cam)[threadIdx.x];
+	__syncthreads();
 	float* const accum = b.c->dyn.accum;
 	const unsigned long long seed = b.c->dyn.seed;
 	const uint32_t sppBegin = uint32_t(b.c->dyn.sppBegin);
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_scatter(WfBuf b, WfParams P) {
 }
 
 // Surface hits: GGX shading, next-event setup, continuation (Li :262-283).
-__global__ void __launch_bounds__(256) k_wf_surface(WfBuf b, WfParams P) {
+__global__ void __launch_bounds__(256, 3) k_wf_surface(WfBuf b, WfParams P) {  // 3 resident blocks (80 registers), as measured best for the GGX shading chain
 	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->surf;

@@ -29,9 +29,7 @@ def c1():
 
 
 def c2():
-    grid = scenes.cloud_density((256,) * 3, seed=1337)
-    b = scenes.noise_volume_scene(res=(256,) * 3, density=100.0, light="point", scale=(5, 5, 5), pos=(0, 0, 0), li=(100, 100, 70), grid=grid)
-    return b, scenes.CameraParams((0, 0, -12), (0, 0, 0), 45.0), 1920, 1080, 64
+    return scenes.c2_scene(), scenes.C2_CAMERA, 1920, 1080, 64
 
 
 def c3():
@@ -81,7 +79,7 @@ def main():
         line = {"config": name, "resolution": [W, H], "spp": spp, "Mpaths_per_s": W * H * spp / dt / 1e6,
                 "Mrays_per_s": (c.extend_rays + c.shadow_rays) / dt / 1e6, "frame_ms": dt * 1e3, "device_ms": c.ms_render,
                 "upload_s": t_up, "scene_build_s": t_build, "mean_luminance": float(luminance(lin).mean()), "finite": bool(np.isfinite(lin).all()),
-                "kernel_ms": {"volume": c.ms_volume_kernel, "extend_shadow": c.ms_extend_kernel, "shade": c.ms_shade_kernel},
+                "kernel_ms": {"volume": c.ms_volume_kernel, "extend_shadow": c.ms_extend_kernel, "shade": c.ms_shade_kernel, "generate_plan": c.ms_other_kernel},
                 "counters": {k: int(getattr(c, k)) for k in ("paths", "extend_rays", "shadow_rays", "delta_steps", "ratio_steps", "brick_visits",
                                                               "bvh_nodes", "tri_tests", "scatter_events", "surface_events", "wavefront_iterations")}}
         if check:
