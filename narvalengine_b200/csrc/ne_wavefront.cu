@@ -100,6 +100,13 @@ struct WfParams {
 	DCounters* counters;
 };
 
+// Block barrier after code in which the lanes of a warp may have parted ways (a loop with per-thread trip counts, work done
+// by thread 0 only): the warp reconverges first, so every lane arrives at the barrier together (compute-sanitizer synccheck).
+__device__ __forceinline__ void block_sync() {
+	__syncwarp();
+	__syncthreads();
+}
+
 __device__ __forceinline__ uint32_t warp_push(uint32_t* counter) {
 	unsigned m = __activemask();
 	unsigned lane = threadIdx.x & 31;
@@ -119,7 +126,7 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t* counter) {
 __device__ __forceinline__ void flush_stats_wf(const Stats& st, DCounters* c) {
 	__shared__ unsigned long long blockTotals_[NE_STAT_FIELDS];
 	if (threadIdx.x < NE_STAT_FIELDS) blockTotals_[threadIdx.x] = 0;
-	__syncthreads();
+	block_sync();
 	const unsigned lane = threadIdx.x & 31;
 #define NE_FLUSH(k, field)                                                          \
 	{                                                                               \
@@ -129,7 +136,7 @@ __device__ __forceinline__ void flush_stats_wf(const Stats& st, DCounters* c) {
 	NE_FLUSH(0, extend_rays) NE_FLUSH(1, shadow_rays) NE_FLUSH(2, delta_steps) NE_FLUSH(3, ratio_steps) NE_FLUSH(4, brick_visits)
 	NE_FLUSH(5, bvh_nodes) NE_FLUSH(6, tri_tests) NE_FLUSH(7, prim_tests) NE_FLUSH(8, scatter_events) NE_FLUSH(9, surface_events)
 #undef NE_FLUSH
-	__syncthreads();
+	block_sync();
 	// the ten counters are consecutive 64-bit fields of DCounters, in this order, after `paths`
 	if (threadIdx.x < NE_STAT_FIELDS && blockTotals_[threadIdx.x]) atomicAdd(&c->extend_rays + threadIdx.x, blockTotals_[threadIdx.x]);
 }
@@ -210,7 +217,7 @@ __device__ __forceinline__ DScene stage_scene(const DScene& g, SceneCache& sh) {
 		for (uint32_t k = threadIdx.x; k < g.n_mat * (sizeof(DMaterial) / 4); k += blockDim.x) dst[k] = src[k];
 		src = reinterpret_cast<const uint32_t*>(g.vol); dst = reinterpret_cast<uint32_t*>(sh.vol);
 		for (uint32_t k = threadIdx.x; k < g.n_vol * (sizeof(DVolume) / 4); k += blockDim.x) dst[k] = src[k];
-		__syncthreads();
+		block_sync();
 		s.inst = sh.inst;
 		s.mat = sh.mat;
 		s.vol = sh.vol;
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	// the camera of this render, staged in shared memory (19 floats that would otherwise sit in registers for the whole kernel)
 	__shared__ DCamera cam;
 	if (threadIdx.x < sizeof(DCamera) / 4) reinterpret_cast<uint32_t*>(&cam)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&b.c->dyn.cam)[threadIdx.x];
-	__syncthreads();
+	block_sync();
 	float* const accum = b.c->dyn.accum;
 	const unsigned long long seed = b.c->dyn.seed;
 	const uint32_t sppBegin = uint32_t(b.c->dyn.sppBegin);
@@ -506,7 +513,7 @@ __device__ __forceinline__ void stage_majorants(const DScene& g, SceneCache& sh,
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barS), "r"(1));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncthreads();
+	block_sync();
 	if (threadIdx.x == 0) {
 		uint32_t total = 0;
 		for (int i = 0; i < g.n_vol; i++) total += maj_table_bytes(g.vol[i]);
@@ -525,7 +532,7 @@ __device__ __forceinline__ void stage_majorants(const DScene& g, SceneCache& sh,
 			off += bytes;
 		}
 	}
-	__syncthreads();  // the patched table pointers
+	block_sync();  // the patched table pointers
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
