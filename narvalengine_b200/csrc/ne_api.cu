@@ -704,6 +704,20 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 			}
 		}
 	}
+	{
+		// the scene's light set: every light instance's Light::primitive (Q7: the material's light_owner) of one analytic kind,
+		// all of them DiffuseLights, no medium without a grid (the specialised scatter kernel drops that branch too)
+		int set = -2;
+		for (size_t f = models.size(); f < fold.size(); f++) {
+			const DMaterial& lm = mats[insts[f].material];
+			const int kind = (lm.directional || lm.infinite || lm.light_owner < 0) ? -1 : insts[lm.light_owner].type;
+			const int k2 = (kind == PRIM_RECTANGLE || kind == PRIM_SPHERE || kind == PRIM_POINT) ? kind : -1;
+			set = set == -2 ? k2 : (set == k2 ? set : -1);
+		}
+		for (const DMaterial& m : mats)
+			if (m.has_medium && m.volume < 0) set = -1;
+		ctx->lightSet = set < 0 ? -1 : set;
+	}
 	ctx->nSurfaces = 0;
 	for (const DInstance& in : insts)
 		if (in.material >= 0 && mats[in.material].has_bsdf && !mats[in.material].transmissive) ctx->nSurfaces++;

@@ -717,33 +717,39 @@ namespace ne {
 // (Sphere.cpp:46-52,58-68), Point (Point.cpp:14-26). `prim` = the primitive Light::primitive points at (Q7),
 // `li` = the chosen light instance (its transform and scale are used).
 // ---------------------------------------------------------------------------------------------------------------
-template <class R>
+// LS: -1 = look the emitter's primitive type up at run time; PRIM_RECTANGLE / PRIM_SPHERE / PRIM_POINT = the host found
+// that EVERY light of the scene is a DiffuseLight on that kind of primitive (ctx->lightSet), so the shading kernels compile
+// the other kinds - and the directional / environment light code - out (k_wf_scatter was 17.6 K instructions, 280 KB of
+// code: instruction-cache misses were among its top stalls).
+template <int LS = -1, class R>
 NE_D V3 light_sample_point(const DInstance& prim, const DInstance& li, const Hit& isect, R& rng) {
-	if (prim.type == PRIM_RECTANGLE) {
+	const int type = LS >= 0 ? LS : prim.type;
+	if (type == PRIM_RECTANGLE) {
 		float e2 = rng.next(), e1 = rng.next(), e0 = rng.next();  // vec3(random(),random(),random()) right to left
 		V3 p(-0.5f + 1.0f * e0, -0.5f + 1.0f * e1, 0.0f + 0.0f * e2);
 		return xform_point(li.M, p);
 	}
-	if (prim.type == PRIM_SPHERE) {
+	if (type == PRIM_SPHERE) {
 		V3 c = xform_point(li.M, V3(0.0f, 0.0f, 0.0f));
 		V3 n = normalize(isect.p - c);
 		return c + n * prim.radius;
 	}
 	return xform_point(li.M, V3(prim.point[0], prim.point[1], prim.point[2]));
 }
-template <class R>
+template <int LS = -1, class R>
 NE_D float light_pdf(const DInstance& prim, const DInstance& li, const Hit& isect, R& rng) {
-	if (prim.type == PRIM_RECTANGLE) {
+	const int type = LS >= 0 ? LS : prim.type;
+	if (type == PRIM_RECTANGLE) {
 		V3 sizeW = V3(li.scale[0], li.scale[1], li.scale[2]) * V3(1.0f, 1.0f, 0.0f);
 		float area = 1;
 		if (sizeW.x != 0) area = area * sizeW.x;
 		if (sizeW.y != 0) area = area * sizeW.y;
 		if (sizeW.z != 0) area = area * sizeW.z;
-		return area_to_solid_angle(1.0f / area, isect.n, isect.p, light_sample_point(prim, li, isect, rng));  // Q10, Q11
+		return area_to_solid_angle(1.0f / area, isect.n, isect.p, light_sample_point<LS>(prim, li, isect, rng));  // Q10, Q11
 	}
-	if (prim.type == PRIM_SPHERE) {
+	if (type == PRIM_SPHERE) {
 		float pdfArea = float(double(1.0f / 4.0f) * NE_PI * double(prim.radius) * double(prim.radius));  // Q13
-		return area_to_solid_angle(pdfArea, isect.n, isect.p, light_sample_point(prim, li, isect, rng));
+		return area_to_solid_angle(pdfArea, isect.n, isect.p, light_sample_point<LS>(prim, li, isect, rng));
 	}
 	return 1;
 }

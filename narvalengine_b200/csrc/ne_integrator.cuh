@@ -99,7 +99,7 @@ struct ImmediateSink {
 
 // estimateDirect :74-157. `lightIdx` = fold index of the chosen light instance; `stream` names the side stream of
 // the BSDF-half transmittance walk.
-template <int KIND = -1, class R, class SINK>
+template <int KIND = -1, int LS = -1, class R, class SINK>
 NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int lightIdx, R& rng, SINK& sink, uint32_t stream, Stats& st) {
 	const DInstance& li = s.inst[lightIdx];
 	const DMaterial& lm = s.mat[li.material];
@@ -111,7 +111,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	wo.o = isect.p;
 	float lightPdf;
 	V3 Li;
-	if (lm.infinite) {
+	if (LS < 0 && lm.infinite) {
 		// InfiniteAreaLight::sampleLi, lights/InfiniteAreaLight.h:58-91. vec2(random(), random()): right to left (A.9)
 		const DEnvDist& env = s.env[lm.env];
 		float u1 = rng.next(), u0 = rng.next();
@@ -132,7 +132,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 			V4 t = tex_sample(s.tex[env.tex], d0, d1);
 			Li = V3(t.x, t.y, t.z);
 		}
-	} else if (lm.directional) {
+	} else if (LS < 0 && lm.directional) {
 		// DirectionalLight::sampleLi, lights/DirectionalLight.cpp:13-20: no draws, pdf 1, returns Light::li = 0 (Q23: the
 		// light half is dead; wo.d still feeds the medium's phase evaluation of the BSDF half, Q18)
 		wo.d = -V3(lm.direction[0], lm.direction[1], lm.direction[2]);
@@ -140,9 +140,9 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 		Li = V3(0.0f);
 	} else {
 		// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
-		V3 A = light_sample_point(lprim, li, isect, rng);
+		V3 A = light_sample_point<LS>(lprim, li, isect, rng);
 		wo.d = normalize(A - wo.o);
-		lightPdf = light_pdf(lprim, li, isect, rng);
+		lightPdf = light_pdf<LS>(lprim, li, isect, rng);
 		Li = Lrad;
 	}
 	V3 f(0.0f);
@@ -158,7 +158,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 			scatteringPdf = f.x;
 		}
 		if (!is_black(f)) {
-			V3 C = light_sample_point(lprim, li, isect, rng);
+			V3 C = light_sample_point<LS>(lprim, li, isect, rng);
 			sink.light_term(s, isect.p, C, f, Li, power_heuristic(lightPdf, scatteringPdf), lightPdf, rng, st);
 		}
 	}
@@ -175,7 +175,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	}
 
 	if (!is_black(f) && scatteringPdf > 0) {
-		lightPdf = light_pdf(lprim, li, isect, rng);
+		lightPdf = light_pdf<LS>(lprim, li, isect, rng);
 		if (lightPdf == 0) return;
 		float weight = power_heuristic(scatteringPdf, lightPdf);
 		Ray ray;
@@ -187,7 +187,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 
 // uniformSampleOneLight :159-174. Returns what the caller must add as L += T * value (zero for queueing sinks,
 // which splat T * value later themselves).
-template <int KIND = -1, class R, class SINK>
+template <int KIND = -1, int LS = -1, class R, class SINK>
 NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng, SINK& sink, uint32_t stream, Stats& st) {
 	float r = rng.next();
 	if (s.n_lights == 0) return V3(0.0f);  // the reference throws std::out_of_range here
@@ -197,7 +197,7 @@ NE_D V3 sample_one_light(const DScene& s, Ray incoming, const Hit& isect, R& rng
 	(void)rng.next();  // second getRandomLightPrimitive call
 	sink.begin();
 	sink.sel_pdf = lightPdf;
-	estimate_direct<KIND>(s, incoming, isect, s.n_models + i, rng, sink, stream, st);
+	estimate_direct<KIND, LS>(s, incoming, isect, s.n_models + i, rng, sink, stream, st);
 	return sink.end(lightPdf);
 }
 
@@ -248,10 +248,10 @@ NE_D int volume_escape(PathState& ps, const Hit& isect) {
 	if (++ps.guard > NE_MAX_NULL_SEGMENTS) return PATH_DONE;
 	return PATH_SAME_BOUNCE;
 }
-template <class R, class SINK>
+template <int LS = -1, class R, class SINK>
 NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray scattered, V3 a, R& rng, SINK& sink, Stats& st);
 // (2b) :215-236 real collision at parameter t of the OCS ray `rayO`.
-template <class R, class SINK>
+template <int LS = -1, class R, class SINK>
 NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const Ray& rayO, float t, R& rng, SINK& sink, Stats& st) {
 	const DInstance& in = s.inst[isect.inst];
 	const DMaterial& m = s.mat[in.material];
@@ -259,10 +259,10 @@ NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const 
 	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
 	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
 	V3 a = sc / ext;
-	return volume_collision(s, ps, isect, scattered, a, rng, sink, st);
+	return volume_collision<LS>(s, ps, isect, scattered, a, rng, sink, st);
 }
 // Li :209-236 once the medium has answered with `a` and `scattered`.
-template <class R, class SINK>
+template <int LS, class R, class SINK>
 NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray scattered, V3 a, R& rng, SINK& sink, Stats& st) {
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	if (all_one(a)) return volume_escape(ps, isect);  // Q1 / Q1b: an escape is recognised by the value (1,1,1)
@@ -272,7 +272,7 @@ NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray 
 	if (is_black(phaseFr) || phasePdf == 0.f) return PATH_DONE;
 	V3 Tnew = ps.T * (phaseFr / phasePdf);
 	sink.scale = Tnew;  // L += T * lightSample happens AFTER the throughput update (:228-232)
-	V3 lightSample = sample_one_light<1>(s, scattered, isect, rng, sink, 1u + ps.nee++, st);  // Q2
+	V3 lightSample = sample_one_light<1, LS>(s, scattered, isect, rng, sink, 1u + ps.nee++, st);  // Q2
 	ps.T = Tnew;
 	sink.emit(ps.T * lightSample);
 	ps.ray = scattered;
@@ -326,12 +326,12 @@ NE_D int shade_volume(const DScene& s, PathState& ps, Hit& isect, R& rng, SINK& 
 }
 
 // Li :262-283 — the surface branch.
-template <class R, class SINK>
+template <class R, int LS = -1, class SINK>
 NE_D int shade_surface(const DScene& s, PathState& ps, const Hit& isect, R& rng, SINK& sink, Stats& st) {
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	st.surface_events++;
 	sink.scale = ps.T;
-	V3 ls = sample_one_light<0>(s, ps.ray, isect, rng, sink, 1u + ps.nee++, st);
+	V3 ls = sample_one_light<0, LS>(s, ps.ray, isect, rng, sink, 1u + ps.nee++, st);
 	sink.emit(ps.T * ls);
 	Ray scattered;
 	scattered.o = isect.p;

@@ -660,8 +660,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P)
 // classified right here, so a path that goes on through a grid medium enters the NEXT iteration's volume queue
 // directly, one that reaches a surface enters this iteration's surface queue, and one that ends frees its slot: no
 // trip through the extend queue, i.e. one 128-byte record read and one hit write fewer per scatter event.
-template <bool FUSE, int MINB>  // MINB resident blocks per SM (2: 128, 3: 80, 4: 64 registers): swept per scene family
-__global__ void __launch_bounds__(256, MINB) k_wf_scatter(WfBuf b, WfParams P) {
+// LS: the scene's light set (-1 = any; else every light is a DiffuseLight on that primitive kind: the other kinds, the
+// directional / environment code and - with them - the HomogeneousMedia branch are compiled out; ne_device.cuh light_sample_point)
+template <bool FUSE, int LS>
+__global__ void __launch_bounds__(256, 2) k_wf_scatter(WfBuf b, WfParams P) {
 	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->scat;
@@ -685,11 +687,11 @@ __global__ void __launch_bounds__(256, MINB) k_wf_scatter(WfBuf b, WfParams P) {
 		sink.sample = r.sample;
 		sink.par = par;
 		int next;
-		if (S.mat[S.inst[h.inst].material].volume < 0) {
+		if (LS < 0 && S.mat[S.inst[h.inst].material].volume < 0) {  // the specialised variants run only in scenes without HomogeneousMedia
 			next = shade_volume_homog(S, r.ps, h, rng, sink, st);
 		} else {
 			Ray rayO = transform_ray(r.ps.ray, S.inst[h.inst].Mi);
-			next = volume_scatter(S, r.ps, h, rayO, r.tHit, rng, sink, st);
+			next = volume_scatter<LS>(S, r.ps, h, rayO, r.tHit, rng, sink, st);
 		}
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
 		if (next == PATH_DONE || r.ps.bounce >= bounces) {
@@ -732,6 +734,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_scatter(WfBuf b, WfParams P) {
 }
 
 // Surface hits: GGX shading, next-event setup, continuation (Li :262-283).
+template <int LS>  // the scene's light set, as for k_wf_scatter
 __global__ void __launch_bounds__(256, 3) k_wf_surface(WfBuf b, WfParams P) {  // 3 resident blocks (80 registers), as measured best for the GGX shading chain
 	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
@@ -755,7 +758,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_surface(WfBuf b, WfParams P) {  /
 		sink.pixel = r.pixel;
 		sink.sample = r.sample;
 		sink.par = par;
-		int next = shade_surface<PhiloxRng>(S, r.ps, h, rng, sink, st);
+		int next = shade_surface<PhiloxRng, LS>(S, r.ps, h, rng, sink, st);
 		if (next == PATH_NEXT_BOUNCE) r.ps.bounce++;
 		if (next == PATH_DONE || r.ps.bounce >= bounces) {
 			b.qFree[warp_push(&b.c->freeN)] = slot;
@@ -1126,7 +1129,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
 struct WfVariant {
 	unsigned long long sceneGen;
 	int W, H;
-	int trace, fuse, brick, skip, sm, genBlocks, scatBlocks, stamps, media, surfaces, foldTimes;
+	int trace, fuse, brick, skip, sm, genBlocks, lightSet, stamps, media, surfaces, foldTimes;
 	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist;
 	uint32_t nSlots;
 };
@@ -1297,18 +1300,21 @@ static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const
 		mark(STAGE_VOLUME);
 		next(STAGE_SHADE);
 		if (V.fuse) {
-			if (V.scatBlocks >= 4) k_wf_scatter<true, 4><<<G, B, 0, st>>>(b, P);
-			else if (V.scatBlocks == 3) k_wf_scatter<true, 3><<<G, B, 0, st>>>(b, P);
-			else k_wf_scatter<true, 2><<<G, B, 0, st>>>(b, P);
+			if (V.lightSet == PRIM_POINT) k_wf_scatter<true, PRIM_POINT><<<G, B, 0, st>>>(b, P);
+			else if (V.lightSet == PRIM_RECTANGLE) k_wf_scatter<true, PRIM_RECTANGLE><<<G, B, 0, st>>>(b, P);
+			else k_wf_scatter<true, -1><<<G, B, 0, st>>>(b, P);
 		} else {
-			if (V.scatBlocks >= 4) k_wf_scatter<false, 4><<<G, B, 0, st>>>(b, P);
-			else if (V.scatBlocks == 3) k_wf_scatter<false, 3><<<G, B, 0, st>>>(b, P);
-			else k_wf_scatter<false, 2><<<G, B, 0, st>>>(b, P);
+			if (V.lightSet == PRIM_POINT) k_wf_scatter<false, PRIM_POINT><<<G, B, 0, st>>>(b, P);
+			else if (V.lightSet == PRIM_RECTANGLE) k_wf_scatter<false, PRIM_RECTANGLE><<<G, B, 0, st>>>(b, P);
+			else k_wf_scatter<false, -1><<<G, B, 0, st>>>(b, P);
 		}
 	}
 	if (V.surfaces) {
 		next(STAGE_SHADE);
-		k_wf_surface<<<G, B, 0, st>>>(b, P);
+		if (V.lightSet == PRIM_POINT) k_wf_surface<PRIM_POINT><<<G, B, 0, st>>>(b, P);
+		else if (V.lightSet == PRIM_RECTANGLE) k_wf_surface<PRIM_RECTANGLE><<<G, B, 0, st>>>(b, P);
+		else if (V.lightSet == PRIM_SPHERE) k_wf_surface<PRIM_SPHERE><<<G, B, 0, st>>>(b, P);
+		else k_wf_surface<-1><<<G, B, 0, st>>>(b, P);
 	}
 	mark(STAGE_SHADE);
 	next(STAGE_TRACE);
@@ -1509,7 +1515,8 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 		const bool fits = V.brick && staged && ctx->majTableBytes > 0 && ctx->majTableBytes <= room;
 		V.sm = (fits && env_u32("NE_B200_SMEM_MAJ", 1) != 0) ? int(ctx->majTableBytes) : 0;
 	}
-	V.scatBlocks = int(env_u32("NE_B200_SCAT_BLOCKS", 2));
+	// shading kernels specialised for the scene's light set (NE_B200_LIGHT_SET=-1 forces the generic ones)
+	V.lightSet = getenv("NE_B200_LIGHT_SET") ? atoi(getenv("NE_B200_LIGHT_SET")) : ctx->lightSet;
 	V.stamps = getenv("NE_B200_NO_STAGE_TIMES") == nullptr;
 	V.media = ctx->scene.has_medium ? 1 : 0;
 	V.surfaces = ctx->nSurfaces > 0 ? 1 : 0;
