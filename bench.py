@@ -200,13 +200,32 @@ def cpu_reference_run(builder, cam, budget_s, threads=None, faithful=False):
 def run_reference(args, rank):
     if rank != 0:
         return
+    if args.cpu_faithful and not args.child:
+        # The reference's RNG as shipped is ONE global std::mt19937 shared by all rendering threads (utils/Math.h:59-66): a data
+        # race that can corrupt the generator's index and crash. Run that build in a child process; if it dies, fall back to
+        # one thread (no race) and say so.
+        cmd = [sys.executable, os.path.abspath(__file__)] + [a for a in sys.argv[1:]] + ["--child"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0 and r.stdout.strip():
+            print(r.stdout.strip().splitlines()[-1], flush=True)
+            return
+        r1 = subprocess.run(cmd + ["--ref-threads", "1"], capture_output=True, text=True)
+        if r1.returncode == 0 and r1.stdout.strip():
+            line = json.loads(r1.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"]["note"] = (f"the as-shipped build crashed with all host threads (exit {r.returncode}: racy global mt19937, Math.h:59-66); "
+                                            "this is the same build on ONE thread")
+            print(json.dumps(line), flush=True)
+        else:
+            print(json.dumps({"impl": "reference", "unavailable": f"the reference build with its RNG as shipped crashed (exit {r.returncode} / {r1.returncode})"}), flush=True)
+        return
     from refclient import RefOracle
     # the scene's transforms come from the oracle itself (getTransform + glm::inverse): the product library is not loaded here
-    b, cam, _, _ = build_scene(transform_fn=RefOracle().transform_fn())
+    # (one oracle build per process: the two builds export the same C++ inline variables, which the dynamic linker unifies)
+    b, cam, _, _ = build_scene(transform_fn=RefOracle(faithful=args.cpu_faithful).transform_fn())
     vals, ms, sample, cores = [], [], "", 0
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        v, sample, cores = cpu_reference_run(b, cam, budget_s=args.ref_seconds, faithful=args.cpu_faithful)
+        v, sample, cores = cpu_reference_run(b, cam, budget_s=args.ref_seconds, faithful=args.cpu_faithful, threads=args.ref_threads or None)
         if i >= args.warmup:
             vals.append(v)
             ms.append((time.time() - t0) * 1e3)
@@ -232,6 +251,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-faithful", action="store_true", help="CPU legs use the reference build with its RNG as shipped (racy global mt19937)")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling measurement at N > 1")
+    ap.add_argument("--ref-threads", type=int, default=0, help="host threads of the CPU legs (0 = all)")
+    ap.add_argument("--child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -404,10 +425,17 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sample, cores = cpu_reference_run(b, cam_params, budget_s=args.ref_seconds, faithful=args.cpu_faithful)
-        cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample,
-               "note": ("reference TUs compiled unmodified, RNG as shipped (one racy global mt19937)" if args.cpu_faithful else
-                        "reference TUs compiled unmodified except a thread_local patch of the global mt19937 (oracle/Makefile)")}
+        if args.cpu_faithful:  # the as-shipped RNG build may crash under threads: measured in a child process (run_reference)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-faithful", "--steps", "1", "--warmup", "0",
+                                "--ref-seconds", str(args.ref_seconds)], capture_output=True, text=True)
+            try:
+                cpu = json.loads(r.stdout.strip().splitlines()[-1]).get("cpu_baseline")
+            except (ValueError, IndexError):
+                cpu = None
+        else:
+            v, sample, cores = cpu_reference_run(b, cam_params, budget_s=args.ref_seconds)
+            cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample,
+                   "note": "reference TUs compiled unmodified except a thread_local patch of the global mt19937 (oracle/Makefile)"}
 
     if rank == 0:
         cfg = bench_config(world, spp)
