@@ -107,6 +107,9 @@ __device__ __forceinline__ void block_sync() {
 	__syncthreads();
 }
 
+#define NE_QCHUNK 64u             // entries a tracking warp reserves at a time in its hot queues (WarpChunk)
+#define NE_Q_INVALID 0xffffffffu  // a queue entry that holds no slot (the unused tail of a warp's last chunk): consumers skip it
+
 __device__ __forceinline__ uint32_t warp_push(uint32_t* counter) {
 	unsigned m = __activemask();
 	unsigned lane = threadIdx.x & 31;
@@ -437,6 +440,7 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		uint32_t slot = b.qExt[par][i];
+		if (slot == NE_Q_INVALID) continue;  // the unused tail of a tracking warp's last chunk (WarpChunk)
 		PathRec r = load_path(b, slot);
 		Hit h;
 		st.extend_rays++;
@@ -486,6 +490,41 @@ struct WarpReserve {
 	__device__ __forceinline__ uint32_t get() const {
 		uint32_t b0 = __shfl_sync(0xffffffffu, base, 0);
 		return b0 + __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
+	}
+};
+
+// The persistent kernels' hot queues, reserved in CHUNKS per warp. A refill used to cost one global atomic per queue for a
+// handful of entries (8 on average): with 4736 warps at it, the same-address atomics of volHead / scat / next queued up in L2
+// (18.7 % of k_wf_track's stall samples on its incoherent launches). A warp now reserves NE_QCHUNK entries at a time and hands
+// them to its lanes from registers; what is left of a chunk is used before the next one is touched. For an OUTPUT queue the
+// unused tail of a warp's last chunk is filled with NE_Q_INVALID at the end of the kernel (finish()): consumers skip such
+// entries (at most NE_QCHUNK - 1 per warp and queue, at the end of a chunk: a few partially filled consumer warps).
+struct WarpChunk {
+	uint32_t base = 0, left = 0;  // warp-uniform
+	// entries for the lanes in `mine`; all 32 lanes call it. Returns this lane's entry (meaningful for lanes in the mask).
+	__device__ __forceinline__ uint32_t take(uint32_t* counter, bool mine) {
+		const unsigned mask = __ballot_sync(0xffffffffu, mine);
+		const uint32_t m = __popc(mask);
+		if (m == 0) return 0;
+		const uint32_t rank = __popc(mask & ((1u << (threadIdx.x & 31)) - 1));
+		uint32_t idx = base + rank;  // from what is left of the current chunk
+		if (m > left) {
+			uint32_t nb = 0;
+			if ((threadIdx.x & 31) == 0) nb = atomicAdd(counter, NE_QCHUNK);
+			nb = __shfl_sync(0xffffffffu, nb, 0);
+			if (rank >= left) idx = nb + (rank - left);
+			base = nb + (m - left);
+			left = NE_QCHUNK - (m - left);
+		} else {
+			base += m;
+			left -= m;
+		}
+		return idx;
+	}
+	// output queues: the rest of the last chunk holds no slot
+	__device__ __forceinline__ void finish(uint32_t* queue) {
+		for (uint32_t i = threadIdx.x & 31; i < left; i += 32) queue[base + i] = NE_Q_INVALID;
+		left = 0;
 	}
 };
 
@@ -572,6 +611,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P)
 	Tracker<BRICKMAJ> trk;
 	const DVolume* vol = nullptr;
 	int budget = 0;
+	WarpChunk cScat, cNext, cFetch;  // the three queues every refill touches, reserved in chunks (WarpChunk)
 	while (true) {
 		unsigned walking = __ballot_sync(0xffffffffu, state == L_MOVING || state == L_CAND);
 		if (walking == 0 || (!exhausted && 32 - __popc(walking) >= P.refill)) {
@@ -580,14 +620,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P)
 			const bool esc = state == L_FIN_END;
 			const uint32_t bg2 = bg + 65536u;  // volume_escape (Li :209-213, Q1): the guard lives in bits 16..31
 			const bool dead = esc && (bg2 >> 16) > NE_MAX_NULL_SEGMENTS;
-			WarpReserve rScat, rVolNext, rNext, rFree, rFetch;
-			rScat.issue(&b.c->scat, state == L_FIN_HIT);
+			WarpReserve rVolNext, rFree;  // rare: walks cut in the tail, paths that ran out of null segments
 			rVolNext.issue(&b.c->volNext, state == L_FIN_BUDGET);  // (at most one entry per live slot: cannot overflow)
-			rNext.issue(&b.c->next, esc && !dead);
 			rFree.issue(&b.c->freeN, dead);
-			rFetch.issue(&b.c->volHead, !exhausted && (state == L_IDLE || fin));
 			// the shuffles are warp-wide: resolve every reservation before the lanes part ways
-			const uint32_t iScat = rScat.get(), iVolNext = rVolNext.get(), iNext = rNext.get(), iFree = rFree.get(), iFetch = rFetch.get();
+			const uint32_t iScat = cScat.take(&b.c->scat, state == L_FIN_HIT), iNext = cNext.take(&b.c->next, esc && !dead);
+			const uint32_t iFetch = cFetch.take(&b.c->volHead, !exhausted && (state == L_IDLE || fin));
+			const uint32_t iVolNext = rVolNext.get(), iFree = rFree.get();
 			if (fin) {
 				if (state == L_FIN_HIT) {
 					b.rec[slot].pA = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
@@ -652,6 +691,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P)
 			state = delta_candidate(trk, density, wr, st) == TRACK_CANDIDATE ? L_FIN_HIT : L_MOVING;
 		}
 	}
+	cScat.finish(b.qScat);
+	cNext.finish(b.qExt[par ^ 1u]);
 	flush_stats_wf(st, P.counters);
 }
 
@@ -676,6 +717,7 @@ __global__ void __launch_bounds__(256, 2) k_wf_scatter(WfBuf b, WfParams P) {
 	st.clear();
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		uint32_t slot = b.qScat[i];
+		if (slot == NE_Q_INVALID) continue;  // the unused tail of a tracking warp's last chunk (WarpChunk)
 		PathRec r = load_path(b, slot);
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
@@ -853,8 +895,9 @@ struct ExtendJob {
 	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->extHead; }
 	__device__ __forceinline__ static uint32_t first(const WfBuf&) { return 0; }
 	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return b.c->extend; }
-	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
+	__device__ __forceinline__ bool fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
 		slot = b.qExt[b.c->par][i];
+		if (slot == NE_Q_INVALID) return false;  // the unused tail of a tracking warp's last chunk (WarpChunk)
 		float4 A = b.rec[slot].pA, B = b.rec[slot].pB, C = b.rec[slot].pC;
 		bounce = int(b.rec[slot].pD.x & 0xffffu);
 		Ray ray;
@@ -864,6 +907,7 @@ struct ExtendJob {
 		pixel = __float_as_uint(C.y);
 		st.extend_rays++;
 		tr.begin(ray, float(NE_EPSILON12), INFINITY);
+		return true;
 	}
 	__device__ __forceinline__ bool consume(const DScene& S, const WfBuf& b, const WfParams& P, SceneTrace& tr, Stats&) {
 		PathState ps;
@@ -893,7 +937,7 @@ struct ShadowJob {
 	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->shHead; }
 	__device__ __forceinline__ static uint32_t first(const WfBuf&) { return 0; }
 	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return min(b.c->shadow, b.shadowCap); }
-	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
+	__device__ __forceinline__ bool fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
 		req = i;
 		float4 A = b.sA[i], B = b.sB[i];
 		Ray ray;
@@ -901,6 +945,7 @@ struct ShadowJob {
 		ray.d = V3(A.w, B.x, B.y) - ray.o;
 		st.shadow_rays++;
 		tr.begin(ray, float(NE_EPSILON3), INFINITY);
+		return true;
 	}
 	__device__ __forceinline__ bool consume(const DScene& S, const WfBuf& b, const WfParams& P, SceneTrace& tr, Stats&) {
 		bool vis = true;
@@ -924,7 +969,7 @@ struct TrFindJob {
 	__device__ __forceinline__ static uint32_t* head(const WfBuf& b) { return &b.c->trfHead; }
 	__device__ __forceinline__ static uint32_t first(const WfBuf& b) { return b.c->trNew0; }
 	__device__ __forceinline__ static uint32_t count(const WfBuf& b) { return min(b.c->tr, b.trCap) - b.c->trNew0; }
-	__device__ __forceinline__ void fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
+	__device__ __forceinline__ bool fetch(const WfBuf& b, uint32_t i, SceneTrace& tr, Stats& st) {
 		req = i;
 		seg = 0;
 		const uint32_t par = b.c->par;
@@ -934,6 +979,7 @@ struct TrFindJob {
 		ray.d = V3(A.w, B.x, B.y);
 		st.shadow_rays++;
 		tr.begin(ray, float(NE_EPSILON3), INFINITY);
+		return true;
 	}
 	__device__ __forceinline__ bool consume(const DScene& S, const WfBuf& b, const WfParams& P, SceneTrace& tr, Stats& st) {
 		Ray ray = tr.rayW;
@@ -997,11 +1043,9 @@ __global__ void __launch_bounds__(256, NE_TRACE_BLOCKS) k_wf_trace(WfBuf b, WfPa
 					WarpReserve rf;
 					rf.issue(JOB::head(b), state == T_IDLE);
 					const uint32_t i = rf.get();
-					if (state == T_IDLE && i < n) {
-						job.fetch(b, first + i, tr, st);
-						state = T_FOLD;
-					}
-					if (__ballot_sync(0xffffffffu, state == T_IDLE)) exhausted = true;  // a lane came back empty-handed
+					const bool wanted = state == T_IDLE;
+					if (wanted && i < n && job.fetch(b, first + i, tr, st)) state = T_FOLD;  // (an entry may hold no slot: the lane asks again)
+					if (__ballot_sync(0xffffffffu, wanted && i >= n)) exhausted = true;  // a lane came back empty-handed
 				}
 				if (state == T_FOLD) state = tr.fold(S, stack, st) ? T_WALK : T_FOLDED;
 				if (!__any_sync(0xffffffffu, state == T_FOLDED)) break;  // T_FOLD / T_WALKED cannot be pending here
@@ -1044,12 +1088,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
 	Tracker<BRICKMAJ> trk;
 	const DVolume* vol = nullptr;
 	int budget = 0;
+	WarpChunk cFetch;  // request indices, reserved in chunks
 	while (true) {
 		unsigned walking = __ballot_sync(0xffffffffu, state == L_MOVING || state == L_CAND);
 		if (walking == 0 || (!exhausted && 32 - __popc(walking) >= P.refill)) {
 			// ---- finish + refill
 			// walks are cut only in the kernel's tail (or always, in test mode): no atomic is issued here otherwise
-			WarpReserve rNext, rFetch;
+			WarpReserve rNext;
 			rNext.issue(&b.c->trNext, state == L_FIN_BUDGET);
 			const uint32_t iNext = rNext.get();
 			if (state == L_FIN_BUDGET && iNext >= b.carryCap) {
@@ -1058,8 +1103,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
 				state = L_MOVING;
 			}
 			const bool fin = state >= L_FIN_HIT;
-			rFetch.issue(&b.c->trHead, !exhausted && (state == L_IDLE || fin));
-			const uint32_t iFetch = rFetch.get();  // warp-wide shuffles: before the lanes part ways
+			const uint32_t iFetch = cFetch.take(&b.c->trHead, !exhausted && (state == L_IDLE || fin));  // warp-wide: before the lanes part ways
 			if (fin) {
 				float4 B = b.tB[par][req], C = b.tC[par][req];
 				if (state == L_FIN_BUDGET) {
@@ -1203,13 +1247,16 @@ static cudaError_t wavefront_build(ne_b200_ctx* ctx, uint32_t nSlots, ne_wavefro
 	b.carryCap = std::max(nSlots / 4, 1u << 18);
 	b.trCap = nSlots + b.carryCap;
 	cudaError_t e = cudaSuccess;
+	// queues the tracking kernels fill in per-warp chunks (WarpChunk) hold, beside one entry per live slot, the unused tails of
+	// the warps' last chunks: at most NE_QCHUNK per warp of the largest persistent grid (a few hundred thousand entries)
+	const size_t slack = size_t(NE_QCHUNK) * 64 * 256;
 #define A(field, n) if (e == cudaSuccess) e = wf_alloc(w, &b.field, n);
 	A(rec, nSlots) A(sA, b.shadowCap) A(sB, b.shadowCap) A(sC, b.shadowCap)
 	for (int k = 0; k < 2; k++) {
 		A(tA[k], b.trCap) A(tB[k], b.trCap) A(tC[k], b.trCap) A(tD[k], b.trCap)
-		A(qExt[k], nSlots) A(qVol[k], nSlots)
+		A(qExt[k], nSlots + slack) A(qVol[k], nSlots)
 	}
-	A(qScat, nSlots) A(qSurf, nSlots) A(qFree, nSlots) A(c, 1)
+	A(qScat, nSlots + slack) A(qSurf, nSlots) A(qFree, nSlots) A(c, 1)
 #undef A
 	if (e == cudaSuccess) e = cudaHostAlloc(&w->hostDone, sizeof(uint32_t), cudaHostAllocMapped);
 	if (e == cudaSuccess) e = cudaHostGetDevicePointer(&w->devDone, w->hostDone, 0);
