@@ -226,7 +226,7 @@ int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out)
 //                         q * maj_scale bounds the brick's maximum from above: tracking stays unbiased)
 //   empty brick:          0x8000 | d, d = Chebyshev distance (in bricks, capped at NE_SKIP_MAX) to the nearest brick with
 //                         a record OR to the outside of the table: every brick closer than d is empty and inside, so a
-//                         walk standing here may cross the whole (2d-1)^3 cube in one move (BrickDDA::jump)
+//                         walk standing here may cross the whole (2d-1)^3 cube in one move (BrickTracker::jump)
 #define NE_SKIP_MAX 16
 static __global__ void k_brick_maj16(const int2* __restrict__ cells, int n, float scale, unsigned short* __restrict__ out) {
 	int b = blockIdx.x * blockDim.x + threadIdx.x;

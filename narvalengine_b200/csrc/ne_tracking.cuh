@@ -1,6 +1,6 @@
 // ne_tracking.cuh — GridMedia::Tr (ratio tracking, materials/GridMedia.cpp:45-69) and GridMedia::sample (delta
 // tracking, :71-100) as RESUMABLE walks made of single EVENTS. Included by ne_device.cuh (needs density_at,
-// brick_density, BrickDDA, bsdf_sample).
+// brick_density, bsdf_sample).
 //
 // A Tracker walks the OCS ray segment [tStart, tFar]:
 //   Tracker<false>  the reference's walk: t -= log(1 - xi) * invMaxDensity / sigma_bar against the single global majorant,

@@ -3,27 +3,33 @@
 //
 //   pool      N path slots (one 128-byte record each: 64 B path state + 48 B hit) that are refilled with new camera
 //             samples as paths terminate, so the wavefront stays full until the work runs out. 64 Mi slots by default
-//             (21 GB with the request arrays: HBM is plentiful, and a wide wavefront means few, long launches)
+//             (HBM is plentiful, and a wide wavefront means few, long launches); never initialised: slots come from a
+//             bump counter until the first ones return through the free stack
 //   queues    arrays of slot indices: {generate, extend} -> {volume, scatter (homogeneous media), surface};
 //             volume -> {scatter, volume (walk not finished), next extend}; free slots. Pushes are warp-aggregated
-//             (one atomicAdd per warp per queue; the persistent tracking kernels batch theirs per phase)
-//   kernels   plan / commit (1 thread: queue bookkeeping)
-//             · generate (camera ray + the path's first Scene::intersectScene: paths that end at once never enter the pool)
+//             (one atomicAdd per warp per queue; the persistent tracking kernels reserve theirs in chunks, WarpChunk)
+//   kernels   init / plan / commit / finish (1 thread: bookkeeping; plan also sets the render graph's loop condition)
+//             · generate (camera ray + the path's first Scene::intersectScene, for the pixels of the culling rectangle
+//               only: paths that end at once never enter the pool)
 //             · extend (Scene::intersectScene fold, BVH, for continuing paths)
-//             · track (delta tracking: persistent warps in finish+refill / move / candidate phases, bounded events per pass)
+//             · track (delta tracking: persistent warps in finish+refill / move / candidate phases)
 //             · scatter (phase function + next-event setup) · surface (GGX shading + next-event setup)
 //             · shadow (visibilityTr requests) · trfind (intersectTr: walk through surfaces to the first medium)
 //             · tr (ratio tracking through that medium, persistent warps like track)
 //             · trace<Extend|Shadow|TrFind job> (scenes with meshes: the three ray-casting stages as persistent warps over
 //               a resumable intersectScene, so a warp is not held by its longest BVH walk)
 //             variants chosen per scene by the host: scatter<FUSE> traces its own continuation ray in mesh-free scenes;
-//             track/tr<TRACK_SKIP> cross cubes of empty bricks in one move where the brick table is sparse
+//             scatter / surface<LS> are specialised for the scene's light set; track/tr<TRACK_*_SM> keep the majorant tables
+//             in shared memory (bulk async copy) when they fit, <TRACK_SKIP*> cross cubes of empty bricks in one move
+//   driver    a whole render is ONE CUDA graph: first plan -> WHILE(not done){ iteration; plan } -> finish, the loop condition set
+//             on the device (graph_build); ne_b200_render is asynchronous. Large batches run as two such graphs on two streams
+//             (wavefront_render). NE_B200_HOST_LOOP=1: the same kernels launched one by one with per-stage CUDA events.
 //   output    fp32 atomicAdd splats into the context's linear accumulation buffer
 //
-// The two tracking kernels stop a walk after `budget` events (brick crossings + density look-ups) and queue the
-// remainder for the next pass: exponential free flights are memoryless, so the estimate is unchanged, and a warp is
-// never held hostage by its longest walk. Every kernel runs over a device-side count with a fixed grid of (SM count x
-// resident blocks): no host round trip sizes a launch; the host only polls a mapped "done" word every few iterations.
+// The two tracking kernels may stop a walk after `budget` events (brick crossings + density look-ups) once their queue has
+// run dry and queue the remainder for the next pass: exponential free flights are memoryless, so the estimate is unchanged,
+// and the tail of a launch is not held hostage by its longest walks. Every kernel runs over a device-side count with a fixed
+// grid of (SM count x resident blocks): no host round trip sizes a launch.
 // Every block stages the scene's instance / material / volume tables in shared memory first (stage_scene).
 #include <algorithm>
 #include <cstddef>
