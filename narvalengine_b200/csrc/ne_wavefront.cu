@@ -220,12 +220,14 @@ __device__ __forceinline__ DScene stage_scene(const DScene& g, SceneCache& sh) {
 	if (g.n_inst <= NE_CACHE_INST && g.n_mat <= NE_CACHE_MAT && g.n_vol <= NE_CACHE_VOL) {
 		const uint32_t* src;
 		uint32_t* dst;
-		src = reinterpret_cast<const uint32_t*>(g.inst); dst = reinterpret_cast<uint32_t*>(sh.inst);
-		for (uint32_t k = threadIdx.x; k < g.n_inst * (sizeof(DInstance) / 4); k += blockDim.x) dst[k] = src[k];
-		src = reinterpret_cast<const uint32_t*>(g.mat); dst = reinterpret_cast<uint32_t*>(sh.mat);
-		for (uint32_t k = threadIdx.x; k < g.n_mat * (sizeof(DMaterial) / 4); k += blockDim.x) dst[k] = src[k];
-		src = reinterpret_cast<const uint32_t*>(g.vol); dst = reinterpret_cast<uint32_t*>(sh.vol);
-		for (uint32_t k = threadIdx.x; k < g.n_vol * (sizeof(DVolume) / 4); k += blockDim.x) dst[k] = src[k];
+		// (block-uniform trip counts with a predicated body: every warp reaches the barrier below converged)
+		uint32_t n;
+		src = reinterpret_cast<const uint32_t*>(g.inst); dst = reinterpret_cast<uint32_t*>(sh.inst); n = g.n_inst * (sizeof(DInstance) / 4);
+		for (uint32_t k0 = 0; k0 < n; k0 += blockDim.x) if (k0 + threadIdx.x < n) dst[k0 + threadIdx.x] = src[k0 + threadIdx.x];
+		src = reinterpret_cast<const uint32_t*>(g.mat); dst = reinterpret_cast<uint32_t*>(sh.mat); n = g.n_mat * (sizeof(DMaterial) / 4);
+		for (uint32_t k0 = 0; k0 < n; k0 += blockDim.x) if (k0 + threadIdx.x < n) dst[k0 + threadIdx.x] = src[k0 + threadIdx.x];
+		src = reinterpret_cast<const uint32_t*>(g.vol); dst = reinterpret_cast<uint32_t*>(sh.vol); n = g.n_vol * (sizeof(DVolume) / 4);
+		for (uint32_t k0 = 0; k0 < n; k0 += blockDim.x) if (k0 + threadIdx.x < n) dst[k0 + threadIdx.x] = src[k0 + threadIdx.x];
 		block_sync();
 		s.inst = sh.inst;
 		s.mat = sh.mat;

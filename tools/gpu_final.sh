@@ -17,4 +17,18 @@ for K in k_wf_track k_wf_tr k_wf_scatter k_wf_generate k_wf_extend; do
   tail -1 gpurun_out/r02_$K.log | cut -c1-120
 done
 NE_B200_LANES=1 timeout 1500 python tools/run_configs.py c1 c3 c4 c5 --check > gpurun_out/r02_configs.jsonl 2> gpurun_out/r02_configs.err; cut -c1-160 gpurun_out/r02_configs.jsonl
-ls -la gpurun_out | head -60
+# compute-sanitizer on small frames of three scene families (render graph + host-driven loop)
+for T in memcheck initcheck synccheck; do
+  NE_B200_POOL=4096 timeout 600 compute-sanitizer --tool $T --print-limit 5 python tools/sanity_graph.py small > gpurun_out/sanitizer_$T.log 2>&1; tail -1 gpurun_out/sanitizer_$T.log
+done
+# racecheck: on the compiled C++ adapter program (no Python in the process)
+python - <<'PY' > gpurun_out/racecheck_scene.log 2>&1
+import json, sys
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from test_cpp_adapter import SCENE
+open("gpurun_out/rc_scene.json", "w").write(json.dumps(SCENE))
+PY
+g++ -std=c++17 -O1 -pthread -I include tests/cpp/offline_engine_test.cpp -L narvalengine_b200/lib -lnarval_b200 -Wl,-rpath,$PWD/narvalengine_b200/lib -o gpurun_out/offline_engine_test 2>> gpurun_out/racecheck_scene.log
+NE_B200_POOL=4096 timeout 900 compute-sanitizer --tool racecheck --print-limit 5 gpurun_out/offline_engine_test gpurun_out/rc_scene.json gpurun_out gpurun_out/rc_frame > gpurun_out/sanitizer_racecheck.log 2>&1; tail -3 gpurun_out/sanitizer_racecheck.log
+rm -f gpurun_out/offline_engine_test
+ls -la gpurun_out | head -70
