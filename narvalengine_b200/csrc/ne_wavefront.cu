@@ -26,9 +26,9 @@
 //             (wavefront_render). NE_B200_HOST_LOOP=1: the same kernels launched one by one with per-stage CUDA events.
 //   output    fp32 atomicAdd splats into the context's linear accumulation buffer
 //
-// The two tracking kernels may stop a walk after `budget` events (brick crossings + density look-ups) once their queue has
-// run dry and queue the remainder for the next pass: exponential free flights are memoryless, so the estimate is unchanged,
-// and the tail of a launch is not held hostage by its longest walks. Every kernel runs over a device-side count with a fixed
+// The two tracking kernels stop a walk after `budget` events (brick crossings + density look-ups) and queue the remainder
+// for the next pass: exponential free flights are memoryless, so the estimate is unchanged, and a launch is not held hostage
+// by its longest walks. Every kernel runs over a device-side count with a fixed
 // grid of (SM count x resident blocks): no host round trip sizes a launch.
 // Every block stages the scene's instance / material / volume tables in shared memory first (stage_scene).
 #include <algorithm>
@@ -1538,14 +1538,15 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 	P.s = ctx->scene;
 	P.W = ctx->W;
 	P.H = ctx->H;
-	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 64)));
+	P.budget = int(std::max(1u, env_u32("NE_B200_TRACK_BUDGET", 128)));
 	P.moves = int(std::max(1u, env_u32("NE_B200_TRACK_MOVES", 4)));  // brick crossings per lane between two candidate phases
 	P.refill = int(std::min(32u, std::max(1u, env_u32("NE_B200_TRACK_REFILL", 20))));  // refill a warp once this many lanes are idle
 	P.walkBudget = int(std::max(1u, env_u32("NE_B200_WALK_BUDGET", 24)));  // inner-node visits per walking lane between two votes
 	P.walkRefill = int(std::min(32u, std::max(1u, env_u32("NE_B200_WALK_REFILL", 12))));  // refill a trace warp once this many lanes are not walking
-	// a walk over its event budget is cut (and queued for the next pass) only once its kernel's queue has run dry, i.e. in
-	// the tail, where redistributing long walks over all SMs pays; NE_B200_TRACK_CUT_ALWAYS=1 cuts everywhere (tests)
-	P.cutAlways = env_u32("NE_B200_TRACK_CUT_ALWAYS", 0) ? 1 : 0;
+	// a walk over its event budget is cut and queued for the next pass. Cutting by the event count alone keeps the set of paths
+	// a pure function of (seed, pixel, sample) - which walks get cut does not depend on timing. NE_B200_TRACK_CUT_ALWAYS=0 cuts
+	// only once the kernel's queue has run dry (the tail): the same speed on C2 (26.8 vs 26.7 ms), but run-to-run different paths
+	P.cutAlways = env_u32("NE_B200_TRACK_CUT_ALWAYS", 1) ? 1 : 0;
 	P.counters = ctx->dCounters;
 	WfVariant V;
 	memset(&V, 0, sizeof(V));
