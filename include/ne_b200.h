@@ -357,9 +357,9 @@ typedef struct ne_b200_counters {
 	uint64_t surface_events;      /* surface shading events */
 	uint64_t wavefront_iterations;
 	uint64_t kernel_launches;     /* CUDA kernels launched by the library */
-	double ms_render;             /* device time of ne_b200_render calls: the sum of the stage accounts below (stamps of the
-	                                 GPU's %globaltimer between the stages of the render graph; CUDA events in the megakernel
-	                                 and with NE_B200_HOST_LOOP=1) */
+	double ms_render;             /* device time of ne_b200_render calls (CUDA events around each on the context's stream). The stage
+	                                 accounts below are stamps of the GPU's %globaltimer taken by the kernels of the render graph
+	                                 (lane 0's clock when two lanes overlap) or, with NE_B200_HOST_LOOP=1, CUDA events */
 	double ms_volume_kernel;      /* device time of the volume tracking kernels (delta + ratio tracking) */
 	double ms_extend_kernel;      /* ray casting: extend, shadow, transmittance-search */
 	double ms_shade_kernel;       /* scatter + surface shading */

@@ -422,6 +422,7 @@ int ne_b200_create(int cuda_device, ne_b200_ctx** out) {
 	}
 	NE_CUDA_OK(cudaMalloc(&ctx->dCounters, sizeof(DCounters)));
 	NE_CUDA_OK(cudaMemset(ctx->dCounters, 0, sizeof(DCounters)));
+	ctx->spansPending = 0;
 	*out = ctx.release();
 	return NE_B200_OK;
 }
@@ -439,6 +440,7 @@ void ne_b200_destroy(ne_b200_ctx* ctx) {
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->evA) cudaEventDestroy(ctx->evA);
 	if (ctx->evB) cudaEventDestroy(ctx->evB);
+	for (cudaEvent_t e : ctx->spanEvents) cudaEventDestroy(e);
 	if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 }
@@ -965,6 +967,12 @@ int ne_b200_get_counters(ne_b200_ctx* ctx, ne_b200_counters* out) {
 	if (rc) return rc;
 	if (!out) { set_error("null out"); return NE_B200_ERR_INVALID; }
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	for (size_t k = 0; k < ctx->spansPending; k++) {  // device time of the asynchronous renders since the last call
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, ctx->spanEvents[2 * k], ctx->spanEvents[2 * k + 1]) == cudaSuccess) ctx->msRender += ms;
+	}
+	ctx->spansPending = 0;
+	cudaGetLastError();
 	DCounters c;
 	NE_CUDA_OK(cudaMemcpy(&c, ctx->dCounters, sizeof(c), cudaMemcpyDeviceToHost));
 	memset(out, 0, sizeof(*out));
@@ -979,7 +987,7 @@ int ne_b200_get_counters(ne_b200_ctx* ctx, ne_b200_counters* out) {
 	out->ms_volume_kernel = ctx->msVolume + double(c.stage_ns[1]) * ns;
 	out->ms_shade_kernel = ctx->msShade + double(c.stage_ns[2]) * ns;
 	out->ms_other_kernel = ctx->msOther + double(c.stage_ns[3]) * ns;
-	out->ms_render = ctx->msRender + double(c.stage_ns[0] + c.stage_ns[1] + c.stage_ns[2] + c.stage_ns[3]) * ns;
+	out->ms_render = ctx->msRender;  // CUDA events around every render (with two overlapped lanes the stage accounts above are lane 0's clock)
 	out->ms_upload = ctx->msUpload;
 	// SURVEY 8d's algorithmic figures: 8 voxels x 4 B + brick-table entry 4 B + majorant 4 B per tracking step (this
 	// layout reads 8 x 4 B + a 4-byte slot + a 2-byte majorant per brick crossing); 36 B of vertex data per triangle test
@@ -995,6 +1003,7 @@ int ne_b200_counters_reset(ne_b200_ctx* ctx) {
 	if (rc) return rc;
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	NE_CUDA_OK(cudaMemset(ctx->dCounters, 0, sizeof(DCounters)));
+	ctx->spansPending = 0;
 	ctx->kernelLaunches = ctx->wavefrontIterations = 0;
 	ctx->pathsCulled = 0;
 	ctx->msRender = ctx->msVolume = ctx->msExtend = ctx->msShade = ctx->msOther = 0;

@@ -65,6 +65,10 @@ struct ne_b200_ctx {
 	ne_wavefront_state* wf[2] = {nullptr, nullptr};
 	cudaStream_t laneStream[2] = {nullptr, nullptr};
 	cudaEvent_t laneFork = nullptr, laneJoin[2] = {nullptr, nullptr};
+	// device time of asynchronous renders: event pairs recorded around each one on the context's stream, read (and recycled) the
+	// next time the counters are fetched
+	std::vector<cudaEvent_t> spanEvents;  // pairs: begin, end
+	size_t spansPending = 0;               // pairs recorded and not yet folded into msRender
 	void* scratch = nullptr;  // reusable device scratch (dense grid staging of the brick builder, resolve buffers)
 	size_t scratchBytes = 0;
 	void* pinned = nullptr;  // pinned host staging for large uploads from pageable caller memory (ne_bricks.cu h2d_staged)

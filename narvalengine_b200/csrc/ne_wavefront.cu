@@ -1681,6 +1681,24 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags) {
 	if ((unsigned long long)ctx->W * ctx->H * (unsigned long long)(sppEnd - sppBegin) == 0 || bounces == 0) return NE_B200_OK;
 	const bool hostLoop = env_u32("NE_B200_HOST_LOOP", 0) != 0;
+	// the render's device time (ms_render): an event pair around it on the context's stream, folded in by ne_b200_get_counters.
+	// (The host-driven loop adds up its own per-stage events instead.)
+	cudaEvent_t spanEnd = nullptr;
+	if (!hostLoop) {
+		// at most 64 pairs wait for a reader: a caller that never fetches the counters re-uses the last pair (and loses those times)
+		const size_t k = std::min<size_t>(ctx->spansPending, 63);
+		while (ctx->spanEvents.size() < 2 * (k + 1)) {
+			cudaEvent_t e;
+			NE_CUDA_OK(cudaEventCreate(&e));
+			ctx->spanEvents.push_back(e);
+		}
+		NE_CUDA_OK(cudaEventRecord(ctx->spanEvents[2 * k], ctx->stream));
+		spanEnd = ctx->spanEvents[2 * k + 1];
+	}
+	struct SpanClose {  // records the closing event on every way out
+		ne_b200_ctx* c; cudaEvent_t e;
+		~SpanClose() { if (e) { cudaEventRecord(e, c->stream); c->spansPending = std::min<size_t>(c->spansPending + 1, 64); } }
+	} spanClose{ctx, spanEnd};
 	int lanes = int(std::min(2u, std::max(1u, env_u32("NE_B200_LANES", 2))));
 	{
 		// two lanes pay when each has enough paths to fill the GPU on its own; for small batches the doubled number of
