@@ -1702,12 +1702,13 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 	int lanes = int(std::min(2u, std::max(1u, env_u32("NE_B200_LANES", 2))));
 	{
 		// two lanes pay when each has enough paths to fill the GPU on its own; for small batches the doubled number of
-		// (small) launches costs more than the filled tails give back (measured: 64 spp of the C2 frame 28.6 -> 27.8 ms,
-		// 8 spp 4.34 -> 4.69 ms)
+		// (small) launches costs more than the filled tails give back (measured on the C2 frame: 64 spp 27.0 -> 26.7 ms, 32 spp
+		// 14.80 -> 14.66, 16 spp 7.84 -> 8.00, 8 spp 4.34 -> 4.69 ms; and with two devices driven from one process, 32 spp per
+		// device ran 14.6 -> 17-21 ms with two lanes each): one lane below 24 Mi paths
 		int rx0, ry0, rw, rh;
 		cull_rect(ctx, &rx0, &ry0, &rw, &rh);
 		const unsigned long long work = (unsigned long long)rw * rh * (unsigned long long)(sppEnd - sppBegin);
-		if (work < (unsigned long long)env_u32("NE_B200_LANES_MIN_WORK", 12u << 20)) lanes = 1;
+		if (work < (unsigned long long)env_u32("NE_B200_LANES_MIN_WORK", 24u << 20)) lanes = 1;
 	}
 	if (hostLoop || sppEnd - sppBegin < 2) lanes = 1;
 	if (lanes == 1) return wavefront_render_lane(ctx, 0, 1, ctx->stream, sppBegin, sppEnd, bounces, seed, flags, hostLoop);
