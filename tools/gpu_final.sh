@@ -13,7 +13,8 @@ ARGS="--steps 1 --warmup 0 --no-cpu-baseline --no-e2e"
 NE_B200_HOST_LOOP=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py $ARGS > gpurun_out/launches_bench.log 2>&1
 NE_B200_HOST_LOOP=1 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv --log-file gpurun_out/bytes.csv python bench.py $ARGS > gpurun_out/bytes_bench.log 2>&1
 for K in k_wf_track k_wf_tr k_wf_scatter k_wf_generate k_wf_extend; do
-  NE_B200_HOST_LOOP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -s 1 -c 1 -f -o gpurun_out/r02_$K python bench.py $ARGS > gpurun_out/r02_$K.log 2>&1
+  S=1; [ "$K" == "k_wf_generate" ] && S=0   # camera rays are generated in the first iteration only
+  NE_B200_HOST_LOOP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -s $S -c 1 -f -o gpurun_out/r02_$K python bench.py $ARGS > gpurun_out/r02_$K.log 2>&1
   tail -1 gpurun_out/r02_$K.log | cut -c1-120
 done
 NE_B200_LANES=1 timeout 1500 python tools/run_configs.py c1 c3 c4 c5 --check > gpurun_out/r02_configs.jsonl 2> gpurun_out/r02_configs.err; cut -c1-160 gpurun_out/r02_configs.jsonl

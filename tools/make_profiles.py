@@ -39,7 +39,8 @@ def main():
         rep = os.path.join(OUT, f"{R}_{k}.ncu-rep")
         if not os.path.exists(rep):
             continue
-        text = STAMP + f"# ncu --set full --import-source on, launch #2 of the kernel in the frame (host-driven loop, NE_B200_HOST_LOOP=1)\n"
+        which = "launch #1 (the only one with camera rays)" if k == "k_wf_generate" else "launch #2 (the first incoherent iteration)"
+        text = STAMP + f"# ncu --set full --import-source on, {which} of the kernel in the frame (host-driven loop, NE_B200_HOST_LOOP=1)\n"
         text += run(sys.executable, "tools/ncu_summary.py", rep) + "\n== hottest source lines (stall samples, share of warp instructions, lanes per instruction)\n"
         text += run(sys.executable, "tools/ncu_lines.py", rep, "40")
         open(os.path.join(PRO, f"{R}_{k}.txt"), "w").write(text)
