@@ -435,6 +435,13 @@ int ne_b200_test_density(ne_b200_ctx* ctx, int n, int instance, const float* ocs
 int ne_b200_test_read_bricks(ne_b200_ctx* ctx, int volume, int32_t dims[4], int32_t* table, float* inv_majorant, float* pool,
                              float* max_density);
 
+/* on != 0: ne_b200_test_bsdf, ne_b200_test_sample_one_light and ne_b200_test_li_tape run the medium shading production
+ * renders use ("FAST medium shading", csrc/ne_device.cuh: hardware reciprocal / rsqrt / sine / cosine in the phase-function
+ * code instead of IEEE divisions; geometry untouched) so that the same reference vectors hold it to the same tolerances
+ * (BSDF.h:100-142 through VolumeBSDF / HG / IsotropicPhaseFunction, Medium.h:73-130). The instances / hits given to those
+ * hooks must then carry a medium. Renders: on by default, NE_B200_EXACT_SHADING=1 selects the reference-order arithmetic. */
+int ne_b200_test_set_fast_shading(ne_b200_ctx* ctx, int on);
+
 /* Philox4x32-10 uniforms: out[i] = u(seed, pixel, sample, dimension i), for KATs of the generator. */
 int ne_b200_test_philox(ne_b200_ctx* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, int n, float* out);
 

@@ -149,6 +149,7 @@ SYMBOLS = {
     "ne_b200_test_sample_one_light": (C.c_int, [_ctx, C.c_int, pf32, C.POINTER(Hit), pf32, C.c_int, pf32, pi32]),
     "ne_b200_test_density": (C.c_int, [_ctx, C.c_int, C.c_int, pf32, pf32, pf32]),
     "ne_b200_test_read_bricks": (C.c_int, [_ctx, C.c_int, pi32, pi32, pf32, pf32, pf32]),
+    "ne_b200_test_set_fast_shading": (C.c_int, [_ctx, C.c_int]),
     "ne_b200_test_philox": (C.c_int, [_ctx, u64, u32, u32, C.c_int, pf32]),
 }
 

@@ -71,7 +71,7 @@ __device__ __forceinline__ void flush_stats(const Stats& st, DCounters* c, unsig
 // ---------------------------------------------------------------------------------------------------------------
 // Kernels: megakernel render (one thread per pixel, loops over its samples), resolve, test hooks
 // ---------------------------------------------------------------------------------------------------------------
-template <bool BRICKMAJ>
+template <bool BRICKMAJ, bool FAST>  // FAST: medium shading as k_wf_scatter<.., FASTSH> does it (ne_device.cuh "FAST medium shading")
 __global__ void __launch_bounds__(128) k_render_mega(DScene s, DCamera cam, float* accum, int W, int H, int sppBegin, int sppEnd, int bounces,
                                                      uint64_t seed, DCounters* counters) {
 	// 8x4 pixel tiles per warp for ray coherence
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_render_mega(DScene s, DCamera cam, floa
 			float u = float(float(x) + rng.next()) / float(W);  // OfflineEngine.cpp:65-66
 			float v = float(float(y) + rng.next()) / float(H);
 			Ray r = camera_ray(cam, u, v, rng);
-			sum = sum + li_path<PhiloxRng, false, BRICKMAJ>(s, r, bounces, rng, st);
+			sum = sum + li_path<PhiloxRng, false, BRICKMAJ, FAST>(s, r, bounces, rng, st);
 			paths++;
 		}
 		accum[3 * size_t(pixel)] += sum.x;
@@ -184,6 +184,7 @@ __device__ Hit make_hit(const ne_b200_hit& q) {
 	return h;
 }
 
+template <bool FAST>  // FAST: the production versions of the medium's phase function (instance must carry a medium)
 __global__ void k_test_bsdf(DScene s, int n, int instance, const float* in, const float* sc, const float* nrm, const float* uv,
                             const float* tape, float* eval, float* pdf, float* sampled) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,14 +200,14 @@ __global__ void k_test_bsdf(DScene s, int n, int instance, const float* in, cons
 	h.prim = 0;
 	V3 a(in[3 * i], in[3 * i + 1], in[3 * i + 2]), b(sc[3 * i], sc[3 * i + 1], sc[3 * i + 2]);
 	if (eval) {
-		V3 e = bsdf_eval(s, m, a, b, h);
+		V3 e = FAST ? bsdf_eval<1, FAST>(s, m, a, b, h) : bsdf_eval(s, m, a, b, h);
 		eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
 	}
-	if (pdf) pdf[i] = bsdf_pdf(s, m, a, b, h.n, h);
+	if (pdf) pdf[i] = FAST ? bsdf_pdf<1, FAST>(s, m, a, b, h.n, h) : bsdf_pdf(s, m, a, b, h.n, h);
 	if (tape && sampled) {
 		TapeRng rng;
 		rng.init(tape + 2 * i, 2);
-		V3 w = bsdf_sample(s, m, a, h.n, h, rng);
+		V3 w = FAST ? bsdf_sample<1, FAST>(s, m, a, h.n, h, rng) : bsdf_sample(s, m, a, h.n, h, rng);
 		sampled[3 * i] = w.x; sampled[3 * i + 1] = w.y; sampled[3 * i + 2] = w.z;
 	}
 }
@@ -251,6 +252,7 @@ __global__ void k_test_grid_sample(DScene s, int n, int instance, const float* o
 	if (used) used[i] = rng.overflow ? -1 : rng.pos;
 }
 
+template <bool FAST>
 __global__ void k_test_li_tape(DScene s, int n, const float* o, const float* d, int bounces, const float* tape, int stride, float* L, int* used) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -261,7 +263,7 @@ __global__ void k_test_li_tape(DScene s, int n, const float* o, const float* d, 
 	rng.init(tape + size_t(stride) * i, stride);
 	Stats st;
 	st.clear();
-	V3 v = li_path<TapeRng, true, false>(s, r, bounces, rng, st);
+	V3 v = li_path<TapeRng, true, false, FAST>(s, r, bounces, rng, st);
 	L[3 * i] = v.x; L[3 * i + 1] = v.y; L[3 * i + 2] = v.z;
 	if (used) used[i] = rng.overflow ? -1 : rng.pos;
 }
@@ -283,6 +285,7 @@ __global__ void k_test_li_philox(DScene s, int n, const float* o, const float* d
 	flush_stats(st, counters, i < n ? 1u : 0u);
 }
 
+template <bool FAST>  // FAST: every hit must lie in a medium
 __global__ void k_test_one_light(DScene s, int n, const float* dirs, const ne_b200_hit* hits, const float* tape, int stride, float* L, int* used) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -294,9 +297,9 @@ __global__ void k_test_one_light(DScene s, int n, const float* dirs, const ne_b2
 	rng.init(tape + size_t(stride) * i, stride);
 	Stats st;
 	st.clear();
-	ImmediateSink<TapeRng, true, false> sink;
+	ImmediateSink<TapeRng, true, false, FAST> sink;
 	sink.L = V3(0.0f);
-	V3 v = sample_one_light(s, in, h, rng, sink, 1u, st);
+	V3 v = sample_one_light<FAST ? 1 : -1, -1>(s, in, h, rng, sink, 1u, st);
 	L[3 * i] = v.x; L[3 * i + 1] = v.y; L[3 * i + 2] = v.z;
 	if (used) used[i] = rng.overflow ? -1 : rng.pos;
 }
@@ -779,12 +782,16 @@ int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int s
 		int tilesX = (width + 7) / 8, tilesY = (height + 3) / 4;
 		size_t threads = size_t(tilesX) * tilesY * 32;
 		int bs = 128;
-		if (flags & NE_B200_RENDER_GLOBAL_MAJORANT)
-			k_render_mega<false><<<blocks(threads, bs), bs, 0, ctx->stream>>>(ctx->scene, ctx->cam, ctx->accum, width, height, spp_begin, spp_end, bounces,
-			                                                                   seed, ctx->dCounters);
-		else
-			k_render_mega<true><<<blocks(threads, bs), bs, 0, ctx->stream>>>(ctx->scene, ctx->cam, ctx->accum, width, height, spp_begin, spp_end, bounces,
-			                                                                  seed, ctx->dCounters);
+		const char* exactShading = getenv("NE_B200_EXACT_SHADING");  // as in the wavefront renderer: the check renderer takes the same decisions
+		const bool fast = !(exactShading && atoi(exactShading) != 0);
+#define NE_MEGA(BM, FAST) \
+	k_render_mega<BM, FAST><<<blocks(threads, bs), bs, 0, ctx->stream>>>(ctx->scene, ctx->cam, ctx->accum, width, height, spp_begin, spp_end, bounces, seed, ctx->dCounters)
+		if (flags & NE_B200_RENDER_GLOBAL_MAJORANT) {
+			if (fast) NE_MEGA(false, true); else NE_MEGA(false, false);
+		} else {
+			if (fast) NE_MEGA(true, true); else NE_MEGA(true, false);
+		}
+#undef NE_MEGA
 		ctx->kernelLaunches++;
 		NE_CUDA_OK(cudaGetLastError());
 		NE_CUDA_OK(cudaEventRecord(ctx->evB, ctx->stream));
@@ -1061,6 +1068,23 @@ static int check_instance(ne_b200_ctx* ctx, int instance, bool needVolume, std::
 	return NE_B200_OK;
 }
 
+// FAST medium shading in the hooks (ne_b200_test_set_fast_shading): the instance must carry a medium's phase function
+static bool instance_is_medium(ne_b200_ctx* ctx, int instance) {
+	if (instance < 0 || instance >= ctx->scene.n_inst) return false;
+	DInstance in;
+	if (cudaMemcpy(&in, ctx->scene.inst + instance, sizeof(in), cudaMemcpyDeviceToHost) != cudaSuccess || in.material < 0) return false;
+	DMaterial m;
+	if (cudaMemcpy(&m, ctx->scene.mat + in.material, sizeof(m), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+	return m.has_bsdf && m.transmissive;
+}
+
+int ne_b200_test_set_fast_shading(ne_b200_ctx* ctx, int on) {
+	int rc = check_ctx(ctx, false);
+	if (rc) return rc;
+	ctx->testFastShading = on != 0;
+	return NE_B200_OK;
+}
+
 int ne_b200_test_bsdf(ne_b200_ctx* ctx, int n, int instance, const float* incoming, const float* scattered, const float* normals, const float* uvs,
                       const float* tape, float* eval, float* pdf, float* sampled) {
 	int rc = check_ctx(ctx, true);
@@ -1073,8 +1097,13 @@ int ne_b200_test_bsdf(ne_b200_ctx* ctx, int n, int instance, const float* incomi
 	if (uvs) NE_UP(u, uvs, 2 * size_t(n));
 	if (tape) NE_UP(t, tape, 2 * size_t(n));
 	NE_CUDA_OK(e.alloc(3 * size_t(n))); NE_CUDA_OK(p.alloc(n)); NE_CUDA_OK(s.alloc(3 * size_t(n)));
-	k_test_bsdf<<<blocks(n, 128), 128, 0, ctx->stream>>>(ctx->scene, n, instance, a.p, b.p, c.p, uvs ? u.p : nullptr, tape ? t.p : nullptr,
-	                                                      eval ? e.p : nullptr, pdf ? p.p : nullptr, sampled ? s.p : nullptr);
+	if (ctx->testFastShading) {
+		if (!instance_is_medium(ctx, instance)) { set_error("fast shading exists for media only"); return NE_B200_ERR_INVALID; }
+		k_test_bsdf<true><<<blocks(n, 128), 128, 0, ctx->stream>>>(ctx->scene, n, instance, a.p, b.p, c.p, uvs ? u.p : nullptr, tape ? t.p : nullptr,
+		                                                            eval ? e.p : nullptr, pdf ? p.p : nullptr, sampled ? s.p : nullptr);
+	} else
+		k_test_bsdf<false><<<blocks(n, 128), 128, 0, ctx->stream>>>(ctx->scene, n, instance, a.p, b.p, c.p, uvs ? u.p : nullptr, tape ? t.p : nullptr,
+		                                                             eval ? e.p : nullptr, pdf ? p.p : nullptr, sampled ? s.p : nullptr);
 	NE_FINISH();
 	if (eval) NE_CUDA_OK(e.download(eval));
 	if (pdf) NE_CUDA_OK(p.download(pdf));
@@ -1134,7 +1163,8 @@ int ne_b200_test_li_tape(ne_b200_ctx* ctx, int n, const float* origins, const fl
 	DevBuf<int> u;
 	NE_UP(o, origins, 3 * size_t(n)); NE_UP(d, directions, 3 * size_t(n)); NE_UP(t, tape, size_t(n) * tape_stride);
 	NE_CUDA_OK(L.alloc(3 * size_t(n))); NE_CUDA_OK(u.alloc(n));
-	k_test_li_tape<<<blocks(n, 64), 64, 0, ctx->stream>>>(ctx->scene, n, o.p, d.p, bounces, t.p, tape_stride, L.p, u.p);
+	if (ctx->testFastShading) k_test_li_tape<true><<<blocks(n, 64), 64, 0, ctx->stream>>>(ctx->scene, n, o.p, d.p, bounces, t.p, tape_stride, L.p, u.p);
+	else k_test_li_tape<false><<<blocks(n, 64), 64, 0, ctx->stream>>>(ctx->scene, n, o.p, d.p, bounces, t.p, tape_stride, L.p, u.p);
 	NE_FINISH();
 	NE_CUDA_OK(L.download(radiance));
 	if (used) NE_CUDA_OK(u.download(used));
@@ -1172,7 +1202,16 @@ int ne_b200_test_sample_one_light(ne_b200_ctx* ctx, int n, const float* incoming
 	DevBuf<int> u;
 	NE_UP(d, incoming_dirs, 3 * size_t(n)); NE_UP(h, hits, n); NE_UP(t, tape, size_t(n) * tape_stride);
 	NE_CUDA_OK(L.alloc(3 * size_t(n))); NE_CUDA_OK(u.alloc(n));
-	k_test_one_light<<<blocks(n, 64), 64, 0, ctx->stream>>>(ctx->scene, n, d.p, h.p, t.p, tape_stride, L.p, u.p);
+	if (ctx->testFastShading) {
+		int lastChecked = -1;
+		for (int i = 0; i < n; i++) {
+			if (hits[i].instance == lastChecked) continue;
+			if (!instance_is_medium(ctx, hits[i].instance)) { set_error("fast shading exists for media only"); return NE_B200_ERR_INVALID; }
+			lastChecked = hits[i].instance;
+		}
+		k_test_one_light<true><<<blocks(n, 64), 64, 0, ctx->stream>>>(ctx->scene, n, d.p, h.p, t.p, tape_stride, L.p, u.p);
+	} else
+		k_test_one_light<false><<<blocks(n, 64), 64, 0, ctx->stream>>>(ctx->scene, n, d.p, h.p, t.p, tape_stride, L.p, u.p);
 	NE_FINISH();
 	NE_CUDA_OK(L.download(radiance));
 	if (used) NE_CUDA_OK(u.download(used));

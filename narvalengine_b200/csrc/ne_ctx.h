@@ -48,6 +48,7 @@ struct ne_b200_ctx {
 	size_t majTableBytes = 0;  // sum of the volumes' 2-byte majorant tables, each padded to 16 bytes (shared-memory staging)
 	const void* l2Pool = nullptr;  // the largest brick pool (optional L2 persisting window, NE_B200_L2_PERSIST)
 	size_t l2PoolBytes = 0;
+	bool testFastShading = false;  // the bsdf / one-light / Li-tape hooks run the FAST medium shading (ne_b200_test_set_fast_shading)
 	bool renderPending = false;  // an asynchronous ne_b200_render is in flight: ne_b200_wait checks its outcome
 	ne::DCamera cam{};
 	bool haveCamera = false;

@@ -577,6 +577,67 @@ NE_D V3 ggx_sample_microfacet(float alpha, R& rng) {
 	return V3(float(st * cp), float(st * sp), float(ct));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FAST medium shading (template parameter FAST of the phase-function entry points below).
+// The reference-order code divides and takes square roots in IEEE arithmetic and evaluates a phase function in a local
+// frame built with generateOrthonormalCS - 57 % of k_wf_scatter's instructions on the headline frame. Production renders
+// (sinks with kFast: the wavefront's volume shading and the one-thread-per-path check renderer alike) use the versions below
+// instead: hardware reciprocal / reciprocal square root / sine / cosine (relative error <= 2^-21), the cosine between the
+// two directions taken directly (the local frame is a rotation: it cannot change it), values that are exact by
+// construction not computed at all (HG with g = 0, fr / pdf of a phase function). Only quantities that the per-function
+// tests hold to 1e-5 are touched; every comparison, epsilon and ray-primitive test keeps the reference's arithmetic.
+// The tape tests against the reference run FAST = false; test_fast_medium_shading_* hold FAST = true to the same oracle.
+// ---------------------------------------------------------------------------------------------------------------
+NE_D float rcp_fast(float x) { return __fdividef(1.0f, x); }
+NE_D float sqrt_fast(float x) {
+	float r;
+	asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+NE_D V3 normalize_fast(V3 a) { return a * rsqrtf(dot(a, a)); }
+NE_D void onb_fast(V3 n, V3& v, V3& u) {  // generateOrthonormalCS, as onb()
+	if (fabsf(n.x) > fabsf(n.y))
+		v = V3(-n.z, 0.0f, n.x) * rsqrtf(n.x * n.x + n.z * n.z);
+	else
+		v = V3(0.0f, n.z, -n.y) * rsqrtf(n.y * n.y + n.z * n.z);
+	u = normalize_fast(cross(n, v));
+}
+// Phase function value for the pair of WORLD directions bsdf_eval / bsdf_pdf are given (wo = -incoming, wi = scattered).
+NE_D float phase_eval_fast(const DMaterial& m, V3 incoming, V3 scattered) {
+	if (m.phase != 1) return float(1.0 / NE_FOUR_PI);
+	const float g = m.g;
+	if (g == 0.0f) return NE_INV4PI;  // what hg_eval yields bit for bit: denom = 1
+	float c = -dot(incoming, scattered) * rsqrtf(dot(incoming, incoming) * dot(scattered, scattered));
+	float denom = 1.0f + g * g - 2.0f * g * c;
+	return NE_INV4PI * (1.0f - g * g) * rcp_fast(denom) * rsqrtf(denom);
+}
+template <class R>
+NE_D V3 phase_sample_fast(const DMaterial& m, R& rng) {
+	float cosT, turn;  // turn: the azimuth in [0, 1)
+	if (m.phase == 1) {
+		float u1 = rng.next(), u0 = rng.next();
+		float g = m.g;
+		if (fabsf(g) < 1e-3f)
+			cosT = 1.0f - 2.0f * u0;
+		else {
+			float sqr = (1.0f - g * g) * rcp_fast(1.0f + g - 2.0f * g * u0);
+			sqr = sqr * sqr;
+			cosT = -rcp_fast(2.0f * g) * (1.0f + g * g - sqr);
+		}
+		turn = u1;
+	} else {
+		float e2 = rng.next(), e1 = rng.next();  // sampleUnitSphere(e1, e2): cos(acos(1 - 2 e2)) = 1 - 2 e2
+		cosT = 1.0f - 2.0f * e2;
+		turn = e1;
+	}
+	// (the reference takes sqrt(1 - cos^2) of a cosine that rounding can put a hair beyond 1: a NaN direction about once in
+	// 1e7 draws, tests/test_gpu_render.py CASES; clamped here)
+	float sinT = sqrt_fast(fmaxf(0.0f, 1.0f - cosT * cosT));
+	float sn, cs;
+	__sincosf(float(NE_TWO_PI) * (turn - 0.5f), &sn, &cs);  // argument in [-pi, pi): where the hardware sine is most accurate
+	return V3(-cs * sinT, -sn * sinT, cosT);  // cos(phi) = -cos(phi - pi)
+}
+
 NE_D float hg_eval(float g, V3 in, V3 out) {
 	float c = dot(normalize(in), normalize(out));
 	float denom = 1.0f + g * g - 2.0f * g * c;
@@ -608,9 +669,15 @@ NE_D V3 phase_sample(const DMaterial& m, R& rng) {
 
 // KIND: -1 = look the material's kind up at run time; 0 = known surface (GGX); 1 = known medium (phase function). A
 // kernel that only ever sees one kind (k_wf_scatter: media, k_wf_surface: surfaces) compiles the other half out.
-template <int KIND = -1, class R>
+// FAST (media only, KIND = 1): see "FAST medium shading" above.
+template <int KIND = -1, bool FAST = false, class R>
 NE_D V3 bsdf_sample(const DScene& s, const DMaterial& m, V3 incoming, V3 normal, const Hit& ri, R& rng) {
+	static_assert(!FAST || KIND == 1, "FAST shading exists for media only");
 	V3 ss, ts;
+	if (FAST) {
+		onb_fast(normal, ss, ts);
+		return to_world(phase_sample_fast(m, rng), normal, ss, ts);
+	}
 	onb(normal, ss, ts);
 	V3 wo = to_lcs(-normalize(incoming), normal, ss, ts);
 	V3 sc;
@@ -625,8 +692,10 @@ NE_D V3 bsdf_sample(const DScene& s, const DMaterial& m, V3 incoming, V3 normal,
 	}
 	return to_world(sc, normal, ss, ts);
 }
-template <int KIND = -1>
+template <int KIND = -1, bool FAST = false>
 NE_D float bsdf_pdf(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered, V3 normal, const Hit& ri) {
+	static_assert(!FAST || KIND == 1, "FAST shading exists for media only");
+	if (FAST) return phase_eval_fast(m, incoming, scattered);
 	const bool transmissive = KIND < 0 ? bool(m.transmissive) : KIND == 1;
 	if (!transmissive && (!(dot(-incoming, normal) > 0) || !(dot(scattered, normal) > 0))) return 0;
 	V3 ss, ts;
@@ -637,8 +706,10 @@ NE_D float bsdf_pdf(const DScene& s, const DMaterial& m, V3 incoming, V3 scatter
 	float rough = material_sample(s, m.roughness_tex, ri.u, ri.v).x;
 	return ggx_pdf(rough * rough, wi, h);
 }
-template <int KIND = -1>
+template <int KIND = -1, bool FAST = false>
 NE_D V3 bsdf_eval(const DScene& s, const DMaterial& m, V3 incoming, V3 scattered, const Hit& ri) {
+	static_assert(!FAST || KIND == 1, "FAST shading exists for media only");
+	if (FAST) return V3(phase_eval_fast(m, incoming, scattered));
 	const bool transmissive = KIND < 0 ? bool(m.transmissive) : KIND == 1;
 	if (!transmissive && (!(dot(-incoming, ri.n) > 0) || !(dot(scattered, ri.n) > 0))) return V3(0.0f);
 	V3 ss, ts;

@@ -72,8 +72,11 @@ NE_D bool intersect_tr(const DScene& s, Ray ray, V3& Tr, R& rng, Stats& st) {
 }
 
 // Resolves next-event queries in place and sums Ld in the reference's order.
-template <class R, bool FAITHFUL, bool BRICKMAJ>
+// FAST: medium shading through the hardware-approximation versions (ne_device.cuh "FAST medium shading"): on for production
+// arithmetic (the check renderer must take the wavefront's decisions), off for the draw-for-draw tape tests.
+template <class R, bool FAITHFUL, bool BRICKMAJ, bool FAST = !FAITHFUL>
 struct ImmediateSink {
+	static constexpr bool kFast = FAST;
 	V3 L;           // radiance of the path so far
 	V3 Ld;          // estimateDirect accumulator
 	V3 scale;       // unused here: the throughput a queueing sink folds into its requests
@@ -106,6 +109,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	const DInstance& lprim = s.inst[lm.light_owner];
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	V3 Lrad(lm.li[0], lm.li[1], lm.li[2]);
+	constexpr bool FAST = SINK::kFast && KIND == 1;
 
 	Ray wo;
 	wo.o = isect.p;
@@ -141,7 +145,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 	} else {
 		// DiffuseLight::sampleLi, lights/DiffuseLight.cpp:8-20
 		V3 A = light_sample_point<LS>(lprim, li, isect, rng);
-		wo.d = normalize(A - wo.o);
+		wo.d = FAST ? normalize_fast(A - wo.o) : normalize(A - wo.o);  // (a medium uses it for the phase function only)
 		lightPdf = light_pdf<LS>(lprim, li, isect, rng);
 		Li = Lrad;
 	}
@@ -154,7 +158,7 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 			f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect) * fabsf(dot(wo.d, isect.n));
 			scatteringPdf = bsdf_pdf<KIND>(s, m, incoming.d, wo.d, isect.n, isect);
 		} else {
-			f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect);
+			f = bsdf_eval<KIND, FAST>(s, m, incoming.d, wo.d, isect);
 			scatteringPdf = f.x;
 		}
 		if (!is_black(f)) {
@@ -169,8 +173,8 @@ NE_D void estimate_direct(const DScene& s, Ray incoming, const Hit& isect, int l
 		f = f * fabsf(dot(wo.d, isect.n));
 		scatteringPdf = bsdf_pdf<KIND>(s, m, incoming.d, wo.d, isect.n, isect);
 	} else {
-		f = bsdf_eval<KIND>(s, m, incoming.d, wo.d, isect);                            // Q18: f for the light-half direction ...
-		wo.d = bsdf_sample<KIND>(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
+		f = bsdf_eval<KIND, FAST>(s, m, incoming.d, wo.d, isect);                            // Q18: f for the light-half direction ...
+		wo.d = bsdf_sample<KIND, FAST>(s, m, incoming.d, V3(0.0f, 1.0f, 0.0f), isect, rng);  // ... then a fresh direction
 		scatteringPdf = f.x;
 	}
 
@@ -255,7 +259,7 @@ template <int LS = -1, class R, class SINK>
 NE_D int volume_scatter(const DScene& s, PathState& ps, const Hit& isect, const Ray& rayO, float t, R& rng, SINK& sink, Stats& st) {
 	const DInstance& in = s.inst[isect.inst];
 	const DMaterial& m = s.mat[in.material];
-	Ray scattered = grid_scatter(s, in, m, rayO, t, isect, rng, st);
+	Ray scattered = grid_scatter<SINK::kFast>(s, in, m, rayO, t, isect, rng, st);
 	V3 sc(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
 	V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + sc;
 	V3 a = sc / ext;
@@ -267,10 +271,18 @@ NE_D int volume_collision(const DScene& s, PathState& ps, const Hit& isect, Ray 
 	const DMaterial& m = s.mat[s.inst[isect.inst].material];
 	if (all_one(a)) return volume_escape(ps, isect);  // Q1 / Q1b: an escape is recognised by the value (1,1,1)
 	ps.T = ps.T * a;
-	V3 phaseFr = bsdf_eval<1>(s, m, ps.ray.d, scattered.d, isect);
-	float phasePdf = bsdf_pdf<1>(s, m, ps.ray.d, scattered.d, isect.n, isect);
-	if (is_black(phaseFr) || phasePdf == 0.f) return PATH_DONE;
-	V3 Tnew = ps.T * (phaseFr / phasePdf);
+	V3 Tnew;
+	if (SINK::kFast) {
+		// a phase function is its own pdf: fr / pdf is x / x = 1 in IEEE arithmetic too, unless x is 0, inf or NaN
+		float ph = phase_eval_fast(m, ps.ray.d, scattered.d);
+		if (!(ph > 0.0f) || isinf(ph)) return PATH_DONE;
+		Tnew = ps.T;
+	} else {
+		V3 phaseFr = bsdf_eval<1>(s, m, ps.ray.d, scattered.d, isect);
+		float phasePdf = bsdf_pdf<1>(s, m, ps.ray.d, scattered.d, isect.n, isect);
+		if (is_black(phaseFr) || phasePdf == 0.f) return PATH_DONE;
+		Tnew = ps.T * (phaseFr / phasePdf);
+	}
 	sink.scale = Tnew;  // L += T * lightSample happens AFTER the throughput update (:228-232)
 	V3 lightSample = sample_one_light<1, LS>(s, scattered, isect, rng, sink, 1u + ps.nee++, st);  // Q2
 	ps.T = Tnew;
@@ -296,7 +308,7 @@ NE_D int shade_volume_homog(const DScene& s, PathState& ps, Hit& isect, R& rng, 
 	if (sampled) {
 		st.scatter_events++;
 		scattered.o = ps.ray.at(t);
-		scattered.d = bsdf_sample<1>(s, m, ps.ray.d, isect.n, isect, rng);
+		scattered.d = bsdf_sample<1, SINK::kFast>(s, m, ps.ray.d, isect.n, isect, rng);
 	} else {
 		scattered.o = ps.ray.at(dist + 0.001f);
 		scattered.d = ps.ray.d;
@@ -345,9 +357,9 @@ NE_D int shade_surface(const DScene& s, PathState& ps, const Hit& isect, R& rng,
 }
 
 // Li :176-301, one thread start to finish.
-template <class R, bool FAITHFUL, bool BRICKMAJ>
+template <class R, bool FAITHFUL, bool BRICKMAJ, bool FAST = !FAITHFUL>
 NE_D V3 li_path(const DScene& s, Ray incoming, int bounces, R& rng, Stats& st) {
-	ImmediateSink<R, FAITHFUL, BRICKMAJ> sink;
+	ImmediateSink<R, FAITHFUL, BRICKMAJ, FAST> sink;
 	sink.L = V3(0.0f);
 	PathState ps;
 	ps.ray = incoming;

@@ -303,12 +303,12 @@ NE_D float grid_tr(const DInstance& in, const DMaterial& m, const DVolume& v, Ra
 
 // The scattering vertex of GridMedia::sample (:90-95) at parameter t of the OCS ray: phase sample about +Y of the
 // OCS (Q19: ignores the incoming direction), mapped to WCS by M (the direction keeps the instance scale).
-template <class R>
+template <bool FAST = false, class R>
 NE_D Ray grid_scatter(const DScene& s, const DInstance& in, const DMaterial& m, const Ray& rayOCS, float t, const Hit& isect, R& rng, Stats& st) {
 	st.scatter_events++;
 	Ray so;
 	so.o = rayOCS.at(t);
-	so.d = bsdf_sample<1>(s, m, rayOCS.d, V3(0.0f, 1.0f, 0.0f), isect, rng);
+	so.d = bsdf_sample<1, FAST>(s, m, rayOCS.d, V3(0.0f, 1.0f, 0.0f), isect, rng);
 	return transform_ray(so, in.M);
 }
 

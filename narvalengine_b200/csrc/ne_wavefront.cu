@@ -241,7 +241,11 @@ __device__ __forceinline__ DScene stage_scene(const DScene& g, SceneCache& sh) {
 
 // Turns the two next-event queries of estimateDirect into requests; emission and request weights go straight to
 // the accumulation buffer / request arrays.
+// FAST (k_wf_scatter): medium shading through the hardware-approximation versions (ne_device.cuh "FAST medium shading"), and
+// the request weight formed with two reciprocals instead of six IEEE divisions.
+template <bool FAST>
 struct QueueSink {
+	static constexpr bool kFast = FAST;
 	V3 scale;
 	float sel_pdf;
 	const WfBuf* b;
@@ -251,7 +255,7 @@ struct QueueSink {
 	__device__ __forceinline__ void emit(V3 v) { splat(accum, pixel, v); }
 	__device__ __forceinline__ V3 end(float) { return V3(0.0f); }
 	__device__ __forceinline__ void light_term(const DScene&, V3 p, V3 C, V3 f, V3 Li, float weight, float pdf, PhiloxRng&, Stats&) {
-		V3 w = scale * ((f * Li * weight / pdf) / sel_pdf);
+		V3 w = FAST ? scale * (f * Li * (weight * rcp_fast(pdf) * rcp_fast(sel_pdf))) : scale * ((f * Li * weight / pdf) / sel_pdf);
 		if (is_black(w)) return;
 		uint32_t i = warp_push(&b->c->shadow);
 		if (i >= b->shadowCap) { b->c->overflow = 1u; return; }
@@ -261,7 +265,7 @@ struct QueueSink {
 	}
 	__device__ __forceinline__ void bsdf_term(const DScene& s, Ray ray, V3 f, V3 Li, float weight, float pdf, PhiloxRng&, uint32_t stream, Stats&) {
 		if (!s.has_medium) return;  // intersectTr can only succeed through a medium (Q12)
-		V3 w = scale * ((f * Li * weight / pdf) / sel_pdf);
+		V3 w = FAST ? scale * (f * Li * (weight * rcp_fast(pdf) * rcp_fast(sel_pdf))) : scale * ((f * Li * weight / pdf) / sel_pdf);
 		if (is_black(w)) return;
 		uint32_t i = warp_push(&b->c->tr);
 		if (i >= b->trCap) { b->c->overflow = 1u; return; }
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 		Hit h;
 		st.extend_rays++;
 		bool did = intersect_scene(S, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
-		QueueSink sink;
+		QueueSink<false> sink;
 		sink.accum = accum;
 		sink.pixel = pixel;
 		int kind = classify_hit(S, did, h, r.ps, sink);
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(256) k_wf_extend(WfBuf b, WfParams P) {
 		Hit h;
 		st.extend_rays++;
 		bool did = intersect_scene(S, r.ps.ray, h, float(NE_EPSILON12), INFINITY, st);
-		QueueSink sink;
+		QueueSink<false> sink;
 		sink.accum = accum;
 		sink.pixel = r.pixel;
 		int kind = classify_hit(S, did, h, r.ps, sink);
@@ -711,8 +715,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_track(WfBuf b, WfParams P)
 // trip through the extend queue, i.e. one 128-byte record read and one hit write fewer per scatter event.
 // LS: the scene's light set (-1 = any; else every light is a DiffuseLight on that primitive kind: the other kinds, the
 // directional / environment code and - with them - the HomogeneousMedia branch are compiled out; ne_device.cuh light_sample_point)
-template <bool FUSE, int LS>
-__global__ void __launch_bounds__(256, 2) k_wf_scatter(WfBuf b, WfParams P) {
+// FASTSH: FAST medium shading (ne_device.cuh), the default; NE_B200_EXACT_SHADING=1 runs the reference-order arithmetic.
+#ifndef NE_SCATTER_BLOCKS
+#define NE_SCATTER_BLOCKS 2  // resident blocks per SM k_wf_scatter is compiled for
+#endif
+template <bool FUSE, int LS, bool FASTSH>
+__global__ void __launch_bounds__(256, NE_SCATTER_BLOCKS) k_wf_scatter(WfBuf b, WfParams P) {
 	stage_stamp(b, P.prevStage);
 	NE_STAGE_SCENE();
 	const uint32_t n = b.c->scat;
@@ -730,7 +738,7 @@ __global__ void __launch_bounds__(256, 2) k_wf_scatter(WfBuf b, WfParams P) {
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
 		rng.init(seed, r.pixel, r.sample, r.dim);
-		QueueSink sink;
+		QueueSink<FASTSH> sink;
 		sink.b = &b;
 		sink.accum = accum;
 		sink.pixel = r.pixel;
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__(256, 3) k_wf_surface(WfBuf b, WfParams P) {  /
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
 		rng.init(seed, r.pixel, r.sample, r.dim);
-		QueueSink sink;
+		QueueSink<false> sink;
 		sink.b = &b;
 		sink.accum = accum;
 		sink.pixel = r.pixel;
@@ -922,7 +930,7 @@ struct ExtendJob {
 		ps.ray = tr.rayW;
 		ps.T = T;
 		ps.bounce = bounce;
-		QueueSink sink;
+		QueueSink<false> sink;
 		sink.accum = b.c->dyn.accum;
 		sink.pixel = pixel;
 		int kind = classify_hit(S, tr.did, tr.hit, ps, sink);
@@ -1181,7 +1189,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_wf_tr(WfBuf b, WfParams P) {
 struct WfVariant {
 	unsigned long long sceneGen;
 	int W, H;
-	int trace, fuse, brick, skip, sm, genBlocks, lightSet, stamps, media, surfaces, foldTimes;
+	int trace, fuse, brick, skip, sm, genBlocks, lightSet, stamps, media, surfaces, foldTimes, fastShade;
 	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist;
 	uint32_t nSlots;
 };
@@ -1354,15 +1362,17 @@ static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const
 		else k_wf_track<TRACK_BRICK, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
 		mark(STAGE_VOLUME);
 		next(STAGE_SHADE);
-		if (V.fuse) {
-			if (V.lightSet == PRIM_POINT) k_wf_scatter<true, PRIM_POINT><<<G, B, 0, st>>>(b, P);
-			else if (V.lightSet == PRIM_RECTANGLE) k_wf_scatter<true, PRIM_RECTANGLE><<<G, B, 0, st>>>(b, P);
-			else k_wf_scatter<true, -1><<<G, B, 0, st>>>(b, P);
-		} else {
-			if (V.lightSet == PRIM_POINT) k_wf_scatter<false, PRIM_POINT><<<G, B, 0, st>>>(b, P);
-			else if (V.lightSet == PRIM_RECTANGLE) k_wf_scatter<false, PRIM_RECTANGLE><<<G, B, 0, st>>>(b, P);
-			else k_wf_scatter<false, -1><<<G, B, 0, st>>>(b, P);
-		}
+#define NE_SCATTER(FUSE, FAST)                                                                                     \
+	{                                                                                                              \
+		if (V.lightSet == PRIM_POINT) k_wf_scatter<FUSE, PRIM_POINT, FAST><<<G, B, 0, st>>>(b, P);                 \
+		else if (V.lightSet == PRIM_RECTANGLE) k_wf_scatter<FUSE, PRIM_RECTANGLE, FAST><<<G, B, 0, st>>>(b, P);    \
+		else k_wf_scatter<FUSE, -1, FAST><<<G, B, 0, st>>>(b, P);                                                  \
+	}
+		if (V.fuse && V.fastShade) NE_SCATTER(true, true)
+		else if (V.fuse) NE_SCATTER(true, false)
+		else if (V.fastShade) NE_SCATTER(false, true)
+		else NE_SCATTER(false, false)
+#undef NE_SCATTER
 	}
 	if (V.surfaces) {
 		next(STAGE_SHADE);
@@ -1573,6 +1583,7 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 	}
 	// shading kernels specialised for the scene's light set (NE_B200_LIGHT_SET=-1 forces the generic ones)
 	V.lightSet = getenv("NE_B200_LIGHT_SET") ? atoi(getenv("NE_B200_LIGHT_SET")) : ctx->lightSet;
+	V.fastShade = env_u32("NE_B200_EXACT_SHADING", 0) ? 0 : 1;  // FAST medium shading in k_wf_scatter (ne_device.cuh)
 	V.stamps = getenv("NE_B200_NO_STAGE_TIMES") == nullptr;
 	V.media = ctx->scene.has_medium ? 1 : 0;
 	V.surfaces = ctx->nSurfaces > 0 ? 1 : 0;

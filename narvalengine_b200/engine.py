@@ -204,6 +204,10 @@ class Context:
         check(self.lib, self.lib.ne_b200_test_density(self.h, len(p), instance, _p(p), _p(out), C.byref(inv)), "test_density")
         return out, inv.value
 
+    def set_fast_shading(self, on):
+        """The bsdf / sample_one_light / li_tape hooks run the production ("FAST") medium shading (csrc/ne_device.cuh)."""
+        check(self.lib, self.lib.ne_b200_test_set_fast_shading(self.h, 1 if on else 0), "test_set_fast_shading")
+
     def philox(self, seed, pixel, sample, n):
         out = np.zeros(n, np.float32)
         check(self.lib, self.lib.ne_b200_test_philox(self.h, seed, pixel, sample, n, _p(out)), "test_philox")

@@ -595,3 +595,91 @@ def test_li_tape_normal_mapped_mesh(ctx, oracle):
     assert same.mean() > 0.98, f"Li(normal-mapped mesh) draw-count agreement {same.mean()}"
     assert_close(L[same], rL[same], what="Li normal-mapped mesh", rtol=2e-4, atol=1e-5, frac=0.99)
     assert rL.mean() > 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FAST medium shading (csrc/ne_device.cuh): what production renders run in the phase-function code instead of the
+# reference-order IEEE divisions / local frames. Held to the SAME reference vectors and tolerances as the exact code.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def fast_ctx(ctx):
+    ctx.set_fast_shading(True)
+    yield ctx
+    ctx.set_fast_shading(False)
+
+
+def test_fast_medium_shading_phase_function(fast_ctx, oracle):
+    """VolumeBSDF eval / pdf / sample (HG g = 0, 0.7, -0.3, isotropic) of the FAST versions against the reference: 1e-5
+    relative on values, the reference test's tolerance on sampled directions."""
+    ctx = fast_ctx
+    for phase, g in (("hg", 0.0), ("hg", 0.7), ("hg", -0.3), ("isotropic", 0.0)):
+        b = scenes.s2_volume(phase=phase, g=g)
+        ctx.upload(b)
+        rs = oracle.scene(b)
+        rng = np.random.default_rng(6)
+        n = 4000
+        nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        nrm[:8] = np.eye(3)[[0, 1, 2, 0, 1, 2, 0, 1]] * np.array([1, 1, 1, -1, -1, -1, 1, -1])[:, None]  # axis-aligned normals
+        inc = rng.normal(size=(n, 3))
+        sc = rng.normal(size=(n, 3)) * 2
+        seeds = np.arange(n, dtype=np.uint32) + 7
+        tape = np.stack([oracle.tape(int(s), 2) for s in seeds])
+        re, rp, rsmp = rs.bsdf(0, inc, sc, nrm, seeds=seeds)
+        e, p, smp = ctx.bsdf(0, inc, sc, nrm, tape=tape)
+        assert_close(e, re, what=f"fast phase eval {phase} {g}", rtol=1e-5, atol=1e-8)
+        assert_close(p, rp, what=f"fast phase pdf {phase} {g}", rtol=1e-5, atol=1e-8)
+        assert_close(smp, rsmp, what=f"fast phase sample {phase} {g}", rtol=2e-5, atol=2e-6)
+        assert np.abs(np.linalg.norm(smp, axis=1) - 1).max() < 1e-5
+
+
+def test_fast_medium_shading_rejects_surfaces(fast_ctx):
+    fast_ctx.upload(scenes.s1_cornell(with_sphere=False))
+    one = np.array([[0.0, 1.0, 0.0]], np.float32)
+    with pytest.raises(abi.NarvalB200Error):
+        fast_ctx.bsdf(0, one, one, one)
+
+
+@pytest.mark.parametrize("light", ["point", "rect"])
+def test_fast_medium_shading_one_light_tape(fast_ctx, oracle, light):
+    """uniformSampleOneLight at medium hits through the FAST versions, draw for draw against the reference."""
+    ctx = fast_ctx
+    b = scenes.noise_volume_scene(res=(24, 24, 24), density=12.0, light=light)
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    o, d = random_rays(3000, 33, center=(0, 1, -4), spread=0.8)
+    d[:, 2] = np.abs(d[:, 2])
+    hits = rs.intersect(o, d)
+    keep = [i for i in range(len(o)) if hits[i].hit and not hits[i].is_light]
+    assert len(keep) > 200
+    hh = (abi.Hit * len(keep))(*[hits[i] for i in keep])
+    dirs = d[keep]
+    seeds = np.arange(len(keep), dtype=np.uint32) + 800
+    tape = np.stack([oracle.tape(int(s), 4096) for s in seeds])
+    rL, rused = rs.sample_one_light(dirs, hh, seeds)
+    L, used = ctx.sample_one_light(dirs, hh, tape)
+    same = used == rused
+    assert same.mean() > 0.995, f"draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what=f"fast uniformSampleOneLight({light})", rtol=5e-5, atol=1e-6, frac=0.998)
+    assert (rL.sum(axis=1) > 0).mean() > 0.1
+
+
+@pytest.mark.parametrize("light", ["point", "rect"])
+def test_fast_medium_shading_li_tape(fast_ctx, oracle, light):
+    """Whole Li paths through a heterogeneous medium with FAST shading against the reference, tape for tape: the few
+    ulps of difference in a scattered direction must not change what a path does (same draw counts, same radiance)."""
+    ctx = fast_ctx
+    b = scenes.noise_volume_scene(res=(24, 24, 24), density=12.0, light=light)
+    ctx.upload(b)
+    rs = oracle.scene(b)
+    rng = np.random.default_rng(41)
+    n = 1500
+    o = np.tile([0, 1, -6], (n, 1)).astype(np.float32)
+    tgt = np.stack([rng.uniform(-1, 1, n), 1 + rng.uniform(-1, 1, n), np.zeros(n)], 1)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    seeds = np.arange(n, dtype=np.uint32) + 150000
+    L, used, rL, rused = _tape_li(ctx, oracle, rs, o, d, 6, seeds, stride=16384)
+    same = used == rused
+    assert same.mean() > 0.97, f"fast Li({light}, volume) draw-count agreement {same.mean()}"
+    assert_close(L[same], rL[same], what=f"fast Li {light}-lit volume", rtol=2e-4, atol=1e-6, frac=0.99)
+    assert (rL.sum(axis=1) > 0).mean() > 0.05
