@@ -43,6 +43,9 @@ NE_D float exp_variate_fast(W& wr) {
 // kernels stage it with a bulk async copy when it fits, and point DVolume::maj16 of their staged scene at it).
 // 4: the same with empty-space skipping.
 enum { TRACK_GLOBAL = 0, TRACK_BRICK = 1, TRACK_SKIP = 2, TRACK_BRICK_SM = 3, TRACK_SKIP_SM = 4 };
+#ifndef NE_TRACK_FAST_INIT
+#define NE_TRACK_FAST_INIT 1  // hardware reciprocals in the DDA set-up of production walks (C2: 23.85 -> 23.71 ms)
+#endif
 #define NE_TRACK_IS_SM(MODE) ((MODE) == TRACK_BRICK_SM || (MODE) == TRACK_SKIP_SM)
 #define NE_TRACK_IS_SKIP(MODE) ((MODE) == TRACK_SKIP || (MODE) == TRACK_SKIP_SM)
 template <int MODE>
@@ -128,14 +131,27 @@ struct BrickTracker {
 		t = tStart;
 		tFar = tEnd;
 		V3 ext = V3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]) + V3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+#if NE_TRACK_FAST_INIT
+		{
+			V3 e = ext * m.density_mult;
+			sig = (e.x + e.y + e.z) * (1.0f / 3.0f);
+		}
+#else
 		sig = avg(ext * m.density_mult);
+#endif
 		sigK = sig * v.maj_scale;
 		// DDA set-up at the segment's first point
 		V3 g = point(tStart);
 		bx = min(max(int(floorf(g.x * 0.125f)), 0), v.bx - 1);
 		by = min(max(int(floorf(g.y * 0.125f)), 0), v.by - 1);
 		bz = min(max(int(floorf(g.z * 0.125f)), 0), v.bz - 1);
+#if NE_TRACK_FAST_INIT
+		// (production walks only: where a DDA boundary falls by an ulp is immaterial to the estimate; the reference-order walk
+		// is Tracker<TRACK_GLOBAL>)
+		float ix = __fdividef(1.0f, gd.x), iy = __fdividef(1.0f, gd.y), iz = __fdividef(1.0f, gd.z);  // +-inf for an axis-parallel ray
+#else
 		float ix = 1.0f / gd.x, iy = 1.0f / gd.y, iz = 1.0f / gd.z;  // +-inf for an axis-parallel ray
+#endif
 		sx = gd.x > 0 ? 1 : -1; sy = gd.y > 0 ? 1 : -1; sz = gd.z > 0 ? 1 : -1;
 		dx = gd.x != 0 ? 8.0f * fabsf(ix) : INFINITY;
 		dy = gd.y != 0 ? 8.0f * fabsf(iy) : INFINITY;
@@ -203,7 +219,7 @@ struct BrickTracker {
 		const float r = __fdividef(1.0f, sigMaj);
 		invMaj = sig * r;
 		t = fmaf(tau, r, t);
-		int slot = __ldg(&cells[(bz * nby + by) * nbx + bx].x);
+		const int slot = __ldg(&cells[(bz * nby + by) * nbx + bx].x);
 		return brick_density(pool, slot, point(t), bx, by, bz);
 	}
 	template <class W>

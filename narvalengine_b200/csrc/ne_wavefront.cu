@@ -243,7 +243,11 @@ __device__ __forceinline__ DScene stage_scene(const DScene& g, SceneCache& sh) {
 // the accumulation buffer / request arrays.
 // FAST (k_wf_scatter): medium shading through the hardware-approximation versions (ne_device.cuh "FAST medium shading"), and
 // the request weight formed with two reciprocals instead of six IEEE divisions.
-template <bool FAST>
+// INLINE (k_wf_scatter<FUSE> in mesh-free scenes, where intersectScene is a handful of analytic tests): the two next-event
+// queries are answered where they arise instead of being queued for k_wf_shadow / k_wf_trfind - visibilityTr outright (no
+// request, no atomic), intersectTr as far as finding the medium: the transmittance request is written with its instance,
+// entry point and segment length (what k_wf_trfind would have filled in), or not at all when there is no medium to walk.
+template <bool FAST, bool INLINE = false>
 struct QueueSink {
 	static constexpr bool kFast = FAST;
 	V3 scale;
@@ -254,25 +258,62 @@ struct QueueSink {
 	__device__ __forceinline__ void begin() {}
 	__device__ __forceinline__ void emit(V3 v) { splat(accum, pixel, v); }
 	__device__ __forceinline__ V3 end(float) { return V3(0.0f); }
-	__device__ __forceinline__ void light_term(const DScene&, V3 p, V3 C, V3 f, V3 Li, float weight, float pdf, PhiloxRng&, Stats&) {
+	__device__ __forceinline__ void light_term(const DScene& s, V3 p, V3 C, V3 f, V3 Li, float weight, float pdf, PhiloxRng&, Stats& st) {
 		V3 w = FAST ? scale * (f * Li * (weight * rcp_fast(pdf) * rcp_fast(sel_pdf))) : scale * ((f * Li * weight / pdf) / sel_pdf);
 		if (is_black(w)) return;
+		if (INLINE) {  // visibilityTr :34-72, as k_wf_shadow runs it (visibility_tr<.., FAITHFUL = false>)
+			Ray ray;
+			ray.o = p;
+			ray.d = C - p;
+			Hit h;
+			st.shadow_rays++;
+			bool visible = true;
+			if (intersect_scene_nomesh(s, ray, h, float(NE_EPSILON3), INFINITY, st)) {
+				const int mi = s.inst[h.inst].material;
+				visible = mi >= 0 && s.mat[mi].has_light;
+			}
+			if (visible) splat(accum, pixel, w);
+			return;
+		}
 		uint32_t i = warp_push(&b->c->shadow);
 		if (i >= b->shadowCap) { b->c->overflow = 1u; return; }
 		b->sA[i] = make_float4(p.x, p.y, p.z, C.x);
 		b->sB[i] = make_float4(C.y, C.z, w.x, w.y);
 		b->sC[i] = make_float2(w.z, __uint_as_float(pixel));
 	}
-	__device__ __forceinline__ void bsdf_term(const DScene& s, Ray ray, V3 f, V3 Li, float weight, float pdf, PhiloxRng&, uint32_t stream, Stats&) {
+	__device__ __forceinline__ void bsdf_term(const DScene& s, Ray ray, V3 f, V3 Li, float weight, float pdf, PhiloxRng&, uint32_t stream, Stats& st) {
 		if (!s.has_medium) return;  // intersectTr can only succeed through a medium (Q12)
 		V3 w = FAST ? scale * (f * Li * (weight * rcp_fast(pdf) * rcp_fast(sel_pdf))) : scale * ((f * Li * weight / pdf) / sel_pdf);
 		if (is_black(w)) return;
+		int inst = -1;  // -1: k_wf_trfind has yet to look for the medium
+		float tRemain = 0.0f;
+		if (INLINE) {  // intersectTr :13-31 up to the medium, as k_wf_trfind runs it
+			inst = -2;
+			for (int seg = 0; seg < NE_MAX_TR_SEGMENTS; seg++) {
+				Hit hh;
+				st.shadow_rays++;
+				if (!intersect_scene_nomesh(s, ray, hh, float(NE_EPSILON3), INFINITY, st)) break;
+				const int mi = s.inst[hh.inst].material;
+				if (mi >= 0 && s.mat[mi].has_medium && s.mat[mi].volume >= 0) {
+					inst = hh.inst;
+					ray.o = ray.at(hh.tNear);
+					tRemain = hh.tFar - hh.tNear;
+					break;
+				}
+				if (mi >= 0 && s.mat[mi].has_medium) {  // HomogeneousMedia: closed-form transmittance, nothing to walk
+					splat(accum, pixel, w * homog_tr(s.mat[mi], hh.tFar - hh.tNear));
+					break;
+				}
+				ray.o = hh.p;
+			}
+			if (inst < 0) return;  // no grid medium along the ray: nothing for k_wf_tr to do
+		}
 		uint32_t i = warp_push(&b->c->tr);
 		if (i >= b->trCap) { b->c->overflow = 1u; return; }
 		b->tA[par][i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
 		b->tB[par][i] = make_float4(ray.d.y, ray.d.z, w.x, w.y);
 		b->tC[par][i] = make_float4(w.z, __uint_as_float(pixel), __uint_as_float(sample), __uint_as_float(stream));
-		b->tD[par][i] = make_float4(1.0f, 0.0f, __int_as_float(-1), __uint_as_float(0u));
+		b->tD[par][i] = make_float4(1.0f, tRemain, __int_as_float(inst), __uint_as_float(0u));
 	}
 };
 
@@ -738,7 +779,7 @@ __global__ void __launch_bounds__(256, NE_SCATTER_BLOCKS) k_wf_scatter(WfBuf b, 
 		Hit h = load_hit(b, slot);
 		PhiloxRng rng;
 		rng.init(seed, r.pixel, r.sample, r.dim);
-		QueueSink<FASTSH> sink;
+		QueueSink<FASTSH, FUSE> sink;
 		sink.b = &b;
 		sink.accum = accum;
 		sink.pixel = r.pixel;
@@ -860,6 +901,7 @@ __global__ void __launch_bounds__(256) k_wf_trfind(WfBuf b, WfParams P) {
 	Stats st;
 	st.clear();
 	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (__float_as_int(b.tD[par][i].z) != -1) continue;  // k_wf_scatter<FUSE> found the medium itself (QueueSink<.., INLINE>)
 		float4 A = b.tA[par][i], B = b.tB[par][i];
 		Ray ray;
 		ray.o = V3(A.x, A.y, A.z);
@@ -989,6 +1031,7 @@ struct TrFindJob {
 		req = i;
 		seg = 0;
 		const uint32_t par = b.c->par;
+		if (__float_as_int(b.tD[par][i].z) != -1) return false;  // k_wf_scatter<FUSE> found the medium itself (QueueSink<.., INLINE>)
 		float4 A = b.tA[par][i], B = b.tB[par][i];
 		Ray ray;
 		ray.o = V3(A.x, A.y, A.z);
@@ -1324,8 +1367,10 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 // k_wf_surface). `mark(kind)` closes a stage in the host-driven loop (a CUDA event); inside the graph the kernels stamp
 // the device clock themselves (stage_stamp) and `mark` does nothing.
 static uint32_t launches_per_iteration(const WfVariant& V) {
-	// generate, commit, extend, shadow, plan + (track, scatter, trfind, tr with media) + (surface with shadeable surfaces)
-	return 5u + (V.media ? 4u : 0u) + (V.surfaces ? 1u : 0u);
+	// generate, commit, extend, plan + (track, scatter, tr with media) + (surface with shadeable surfaces) + (shadow, and trfind
+	// with media, unless k_wf_scatter<FUSE> answers its queries in place and no other kernel queues any)
+	const bool cast = V.trace || !V.fuse || V.surfaces;
+	return 4u + (V.media ? 3u : 0u) + (V.surfaces ? 1u : 0u) + (cast ? (V.media ? 2u : 1u) : 0u);
 }
 
 template <class MARK>
@@ -1382,13 +1427,20 @@ static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const
 		else k_wf_surface<-1><<<G, B, 0, st>>>(b, P);
 	}
 	mark(STAGE_SHADE);
-	next(STAGE_TRACE);
-	if (V.trace) k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
-	else k_wf_shadow<<<G, B, 0, st>>>(b, P);
-	if (V.media) {
+	// the shadow / medium-search kernels run only if some kernel queued such requests: k_wf_scatter<FUSE> (mesh-free scenes)
+	// answers its own in place, k_wf_surface queues them
+	const bool cast = V.trace || !V.fuse || V.surfaces;
+	if (cast) {
 		next(STAGE_TRACE);
-		if (V.trace) k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
-		else k_wf_trfind<<<G, B, 0, st>>>(b, P);
+		if (V.trace) k_wf_trace<ShadowJob><<<GR, 256, 0, st>>>(b, P);
+		else k_wf_shadow<<<G, B, 0, st>>>(b, P);
+	}
+	if (V.media) {
+		if (cast) {
+			next(STAGE_TRACE);
+			if (V.trace) k_wf_trace<TrFindJob><<<GR, 256, 0, st>>>(b, P);
+			else k_wf_trfind<<<G, B, 0, st>>>(b, P);
+		}
 		mark(STAGE_TRACE);
 		next(STAGE_VOLUME);
 		if (!V.brick) k_wf_tr<TRACK_GLOBAL, NE_TRACK_THREADS, NE_TRACK_BLOCKS><<<GT, NE_TRACK_THREADS, 0, st>>>(b, P);
