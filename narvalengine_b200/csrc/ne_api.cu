@@ -457,6 +457,7 @@ int ne_b200_set_stream(ne_b200_ctx* ctx, void* cuda_stream) {
 }
 
 int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
+	ne_host_span span_("scene_upload");
 	int rc = check_ctx(ctx, false);
 	if (rc) return rc;
 	if (!d) { set_error("null scene"); return NE_B200_ERR_INVALID; }
@@ -753,6 +754,7 @@ int ne_b200_camera_set(ne_b200_ctx* ctx, const ne_b200_camera* c) {
 }
 
 int ne_b200_clear(ne_b200_ctx* ctx) {
+	ne_host_span span_("clear");
 	int rc = check_ctx(ctx, false);
 	if (rc) return rc;
 	if (ctx->accum) NE_CUDA_OK(cudaMemsetAsync(ctx->accum, 0, size_t(ctx->W) * ctx->H * 3 * sizeof(float), ctx->stream));
@@ -761,6 +763,7 @@ int ne_b200_clear(ne_b200_ctx* ctx) {
 }
 
 int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int spp_end, int bounces, uint64_t seed, uint32_t flags) {
+	ne_host_span span_("render (call)");
 	int rc = check_ctx(ctx, true);
 	if (rc) return rc;
 	if (!ctx->haveCamera) { set_error("no camera set"); return NE_B200_ERR_STATE; }
@@ -809,6 +812,7 @@ int ne_b200_render(ne_b200_ctx* ctx, int width, int height, int spp_begin, int s
 }
 
 int ne_b200_wait(ne_b200_ctx* ctx) {
+	ne_host_span span_("wait");
 	int rc = check_ctx(ctx, false);
 	if (rc) return rc;
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -871,6 +875,7 @@ int ne_b200_accum_upload(ne_b200_ctx* ctx, int width, int height, const float* s
 }
 
 static int read_resolved(ne_b200_ctx* ctx, float* linear, float* tonemapped) {
+	ne_host_span span_("read_resolved");
 	int rc = check_ctx(ctx, false);
 	if (rc) return rc;
 	if (!ctx->accum || ctx->samples <= 0) { set_error("nothing rendered yet"); return NE_B200_ERR_STATE; }

@@ -177,6 +177,7 @@ int h2d_staged(ne_b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 // dense (host) -> DVolume in HBM. Allocations that belong to the scene are pushed to ctx->sceneAllocs.
 int device_build_bricks(ne_b200_ctx* ctx, const ne_b200_volume& v, DVolume& out) {
+	ne_host_span span_("  device_build_bricks");
 	const size_t nvox = size_t(v.width) * v.height * v.depth;
 	const int nbx = (v.width + 7) / 8, nby = (v.height + 7) / 8, nbz = (v.depth + 7) / 8;
 	const size_t nb = size_t(nbx) * nby * nbz;
@@ -306,6 +307,7 @@ static __global__ void k_brick_table(const int2* __restrict__ cells, const unsig
 }
 
 int device_build_majorants(ne_b200_ctx* ctx, DVolume& vol) {
+	ne_host_span span_("  device_build_majorants");
 	const int nb = vol.bx * vol.by * vol.bz;
 	const int nt = (vol.bx + 2) * (vol.by + 2) * (vol.bz + 2);
 	cudaStream_t st = ctx->stream;

@@ -22,6 +22,22 @@ void set_error(const std::string& s);
 		}                                                                                                     \
 	} while (0)
 
+// NE_B200_TRACE_HOST=1: host time of the named scopes on stderr (where an end-to-end frame spends its time outside the kernels)
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+struct ne_host_span {
+	const char* name;
+	std::chrono::steady_clock::time_point t0;
+	bool on;
+	explicit ne_host_span(const char* n) : name(n), on(getenv("NE_B200_TRACE_HOST") != nullptr) {
+		if (on) t0 = std::chrono::steady_clock::now();
+	}
+	~ne_host_span() {
+		if (on) fprintf(stderr, "[ne_b200] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+
 struct ne_wavefront_state;
 
 struct ne_b200_ctx {

@@ -1336,6 +1336,7 @@ static cudaError_t wavefront_build(ne_b200_ctx* ctx, uint32_t nSlots, ne_wavefro
 // A pool that does not fit (a smaller or busy GPU: the default is 64 Mi slots, ~29 GB) is retried at half the size down
 // to a floor; the renderer then simply runs more, shorter iterations.
 static int wavefront_ensure(ne_b200_ctx* ctx, int lane, uint32_t nSlots) {
+	ne_host_span span_("  wavefront_ensure");
 	if (ctx->wf[lane] && ctx->wf[lane]->nSlots >= nSlots) return NE_B200_OK;
 	NE_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	if (ctx->laneStream[lane]) NE_CUDA_OK(cudaStreamSynchronize(ctx->laneStream[lane]));
@@ -1479,6 +1480,7 @@ static void set_l2_window(ne_b200_ctx* ctx, cudaStream_t st, bool on) {
 // device by k_wf_plan, so a whole render is ONE graph launch: no host round trip, no empty iteration after the last one,
 // and ne_b200_render returns while the GPU works.
 static int graph_build(ne_b200_ctx* ctx, ne_wavefront_state* w, const WfParams& P, const WfVariant& V) {
+	ne_host_span span_("  graph_build");
 	graph_free(w);
 	NE_CUDA_OK(cudaGraphCreate(&w->graph, 0));
 	cudaGraphConditionalHandle loop;
@@ -1581,13 +1583,16 @@ static void cull_rect(const ne_b200_ctx* ctx, int* rx0, int* ry0, int* rw, int* 
 	*rx0 = x0; *ry0 = y0; *rw = x1 - x0; *rh = y1 - y0;
 }
 
-// One lane's render of samples [sppBegin, sppEnd) on stream `st` (see wavefront_render).
+// One lane's render of samples [sppBegin, sppEnd) on stream `st` (see wavefront_render). prepareOnly: everything up to the
+// launch - the lane's pool and its render graph, rebuilt if the scene or a knob changed - so that a two-lane render can get
+// BOTH graphs ready before it launches either: instantiating a graph waits for the work already running on the device (the
+// second lane of the first frame after an upload used to start when the first was over: 1.3 ms per end-to-end frame).
 static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStream_t st, int sppBegin, int sppEnd, int bounces, uint64_t seed, uint32_t flags,
-                                 bool hostLoopAsked) {
+                                 bool hostLoopAsked, bool prepareOnly = false) {
 	int rx0, ry0, rw, rh;
 	cull_rect(ctx, &rx0, &ry0, &rw, &rh);
 	const unsigned long long work = (unsigned long long)rw * rh * (unsigned long long)(sppEnd - sppBegin);
-	ctx->pathsCulled += ((unsigned long long)ctx->W * ctx->H - (unsigned long long)rw * rh) * (unsigned long long)(sppEnd - sppBegin);
+	if (!prepareOnly) ctx->pathsCulled += ((unsigned long long)ctx->W * ctx->H - (unsigned long long)rw * rh) * (unsigned long long)(sppEnd - sppBegin);
 	uint32_t pool = std::max(1024u, env_u32("NE_B200_POOL", 1u << 26) / uint32_t(nLanes));
 	uint32_t nSlots = uint32_t(std::min<unsigned long long>(work, pool));
 	int rc = wavefront_ensure(ctx, lane, nSlots);
@@ -1671,6 +1676,7 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 				w->graphBroken = true;
 			}
 		}
+		if (prepareOnly) return NE_B200_OK;
 		if (w->haveGraph) {
 			k_wf_init<<<1, 1, 0, st>>>(w->b, work, dyn);
 			NE_CUDA_OK(cudaGetLastError());
@@ -1680,6 +1686,7 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 		}
 	}
 
+	if (prepareOnly) return NE_B200_OK;
 	// ---- host-driven loop over the same kernels (NE_B200_HOST_LOOP=1: per-stage CUDA events)
 	set_l2_window(ctx, st, V.l2persist != 0);
 	size_t evUsed = 0;
@@ -1783,6 +1790,10 @@ int wavefront_render(ne_b200_ctx* ctx, int sppBegin, int sppEnd, int bounces, ui
 		}
 	}
 	const int mid = sppBegin + (sppEnd - sppBegin + 1) / 2;
+	for (int l = 0; l < 2; l++) {
+		int rc = wavefront_render_lane(ctx, l, 2, ctx->laneStream[l], l == 0 ? sppBegin : mid, l == 0 ? mid : sppEnd, bounces, seed, flags, false, true);
+		if (rc) return rc;
+	}
 	NE_CUDA_OK(cudaEventRecord(ctx->laneFork, ctx->stream));  // after whatever the caller queued before (clear, uploads)
 	for (int l = 0; l < 2; l++) {
 		NE_CUDA_OK(cudaStreamWaitEvent(ctx->laneStream[l], ctx->laneFork, 0));
