@@ -727,6 +727,11 @@ int ne_b200_scene_upload(ne_b200_ctx* ctx, const ne_b200_scene_desc* d) {
 	ctx->nSurfaces = 0;
 	for (const DInstance& in : insts)
 		if (in.material >= 0 && mats[in.material].has_bsdf && !mats[in.material].transmissive) ctx->nSurfaces++;
+	// every surviving camera path enters the volume queue: nothing shadeable but grid media (k_wf_generate then needs one reservation
+	// per survivor, not two)
+	ctx->onlyGridMedia = ctx->nSurfaces == 0 && !vols.empty();
+	for (const DMaterial& m : mats)
+		if (m.has_medium && m.volume < 0) ctx->onlyGridMedia = false;
 	ctx->majTableBytes = 0;
 	ctx->l2Pool = nullptr;
 	ctx->l2PoolBytes = 0;

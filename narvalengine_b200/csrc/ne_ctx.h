@@ -53,6 +53,7 @@ struct ne_b200_ctx {
 	// -1, or the primitive kind (PRIM_RECTANGLE / PRIM_SPHERE / PRIM_POINT) when EVERY light of the scene is a DiffuseLight on
 	// that kind and no HomogeneousMedia exists: the shading kernels then run their variant specialised for it
 	int lightSet = -1;
+	bool onlyGridMedia = false;  // no shadeable surface, no HomogeneousMedia: a camera path that survives its first intersectScene is in a grid medium
 	int nSurfaces = 0;  // fold instances a path can be shaded on (a BSDF that is not a medium's): none -> k_wf_surface is never launched
 	// world-space corner points (xyz) of everything a camera ray can hit, for the camera-ray culling rectangle
 	// (ne_wavefront.cu cull_rect); cullable = false when some instance cannot be bounded or the scene has lights that

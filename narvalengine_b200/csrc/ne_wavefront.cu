@@ -102,6 +102,7 @@ struct WfBuf {
 struct WfParams {
 	DScene s;
 	int W, H, budget, refill, moves, walkBudget, walkRefill, cutAlways;
+	int genToVol;   // every camera path that survives goes to the volume queue (ctx->onlyGridMedia): its queue entry is its reservation
 	int prevStage;  // stage kind of the kernel launched before this one, or -1: no stage accounting (see stage_stamp)
 	DCounters* counters;
 };
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	const uint32_t gen = b.c->gen;
 	if (gen == 0) return;
 	const uint32_t freeN = b.c->freeN, freeTake = b.c->freeTake, bumpBase = b.c->bumpBase, par = b.c->par;
+	const uint32_t vol0 = b.c->vol;  // (read only where it is constant for the whole kernel: P.genToVol)
 	const unsigned long long workBase = b.c->workNext;
 	// the camera of this render, staged in shared memory (19 floats that would otherwise sit in registers for the whole kernel)
 	__shared__ DCamera cam;
@@ -459,7 +461,12 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 		const uint32_t slot = j < freeTake ? b.qFree[freeN + freeTake - 1u - j] : bumpBase + (j - freeTake);
 		store_path(b, slot, r);
 		store_hit(b, slot, h);
-		if (kind == HIT_VOLUME) {
+		if (P.genToVol) {
+			// the j-th survivor is also the j-th new entry of the volume queue (nobody else appends to it during this kernel;
+			// k_wf_commit adds genTaken to the count): one same-address atomic per warp instead of two (41 % of this kernel's
+			// stall samples sat on them)
+			b.qVol[par][vol0 + j] = slot;
+		} else if (kind == HIT_VOLUME) {
 			if (S.mat[S.inst[h.inst].material].volume >= 0) b.qVol[par][warp_push(&b.c->vol)] = slot;
 			else b.qScat[warp_push(&b.c->scat)] = slot;
 		} else b.qSurf[warp_push(&b.c->surf)] = slot;
@@ -467,9 +474,10 @@ __global__ void __launch_bounds__(256, MINB) k_wf_generate(WfBuf b, WfParams P) 
 	flush_stats_wf(st, P.counters);
 }
 // One thread: publish the refill (after generate has read the old counts); reserved slots no survivor took go back.
-__global__ void k_wf_commit(WfBuf b, DCounters* counters, int prevStage) {
+__global__ void k_wf_commit(WfBuf b, DCounters* counters, int prevStage, int genToVol) {
 	stage_stamp(b, prevStage);
 	WfCounts& c = *b.c;
+	if (genToVol) c.vol += c.genTaken;  // k_wf_generate wrote the survivors' queue entries itself
 	if (c.genTaken <= c.freeTake) {  // the untouched part of the free-stack reservation is still in place; no fresh slot was used
 		c.freeN += c.freeTake - c.genTaken;
 		c.bump = c.bumpBase;
@@ -1233,7 +1241,7 @@ struct WfVariant {
 	unsigned long long sceneGen;
 	int W, H;
 	int trace, fuse, brick, skip, sm, genBlocks, lightSet, stamps, media, surfaces, foldTimes, fastShade;
-	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist;
+	int budget, refill, moves, walkBudget, walkRefill, cutAlways, l2persist, genToVol;
 	uint32_t nSlots;
 };
 
@@ -1393,7 +1401,7 @@ static void launch_iteration(cudaStream_t st, const ne_wavefront_state* w, const
 	else if (V.genBlocks == 3) k_wf_generate<3><<<G, B, 0, st>>>(b, P);
 	else k_wf_generate<2><<<G, B, 0, st>>>(b, P);
 	next(STAGE_OTHER);
-	k_wf_commit<<<1, 1, 0, st>>>(b, counters, P.prevStage);
+	k_wf_commit<<<1, 1, 0, st>>>(b, counters, P.prevStage, P.genToVol);
 	mark(STAGE_OTHER);
 	next(STAGE_TRACE);
 	if (V.trace) k_wf_trace<ExtendJob><<<GR, 256, 0, st>>>(b, P);
@@ -1646,6 +1654,7 @@ static int wavefront_render_lane(ne_b200_ctx* ctx, int lane, int nLanes, cudaStr
 	V.surfaces = ctx->nSurfaces > 0 ? 1 : 0;
 	V.budget = P.budget; V.refill = P.refill; V.moves = P.moves; V.walkBudget = P.walkBudget; V.walkRefill = P.walkRefill; V.cutAlways = P.cutAlways;
 	V.l2persist = env_u32("NE_B200_L2_PERSIST", 0) ? 1 : 0;
+	P.genToVol = V.genToVol = (ctx->onlyGridMedia && env_u32("NE_B200_GEN_TO_VOL", 1)) ? 1 : 0;
 	V.foldTimes = lane == 0 ? 1 : 0;  // concurrent lanes: lane 0's stage clock stands for the render
 	if (V.sm) {
 		static const void* smKernels[] = {(const void*)k_wf_track<TRACK_BRICK_SM, 1024, 1>, (const void*)k_wf_track<TRACK_SKIP_SM, 1024, 1>,

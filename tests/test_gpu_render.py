@@ -117,6 +117,22 @@ def test_fused_scatter_equals_separate_extend(ctx, name, monkeypatch):
     np.testing.assert_allclose(img, ref, rtol=2e-4, atol=1e-5 * float(ref.mean()))
 
 
+def test_generate_with_one_reservation_per_survivor(ctx, monkeypatch):
+    """Where nothing is shadeable but grid media (the headline scene), a surviving camera path's volume-queue entry is its slot
+    reservation (NE_B200_GEN_TO_VOL, default on): same paths, same counters, same image as with the two separate pushes."""
+    b, cam = scenes.c2_scene(n=64), scenes.C2_CAMERA
+    monkeypatch.setenv("NE_B200_TRACK_BUDGET", "100000000")
+    monkeypatch.setenv("NE_B200_GEN_TO_VOL", "0")
+    ref, cref = render_counted(ctx, b, cam, 160, 88, 8)
+    assert cref["delta_steps"] > 0
+    for pool in ("67108864", "4096"):  # the small pool refills from the free stack over many iterations
+        monkeypatch.setenv("NE_B200_GEN_TO_VOL", "1")
+        monkeypatch.setenv("NE_B200_POOL", pool)
+        img, c = render_counted(ctx, b, cam, 160, 88, 8)
+        assert c == cref, pool
+        np.testing.assert_allclose(img, ref, rtol=2e-4, atol=1e-5 * float(ref.mean()))
+
+
 def test_trace_kernels_on_a_mesh_free_scene(ctx, monkeypatch):
     """NE_B200_TRACE=1 forced where there is no BVH: the jobs' folds finish without ever walking."""
     mk, cam = CASES["volume"]
