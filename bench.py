@@ -438,11 +438,12 @@ def main():
                    "note": "reference TUs compiled unmodified except a thread_local patch of the global mt19937 (oracle/Makefile)"}
 
     if rank == 0:
-        cfg = bench_config(world, spp)
-        cfg.update({"majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 26)), "csrc_sha16": csrc_sha16()})
+        cfg = bench_config(world, spp)  # the workload, key for key what the reference arm prints
+        # what is specific to this arm stays out of `config`: tracking variant, pool size, hash of the kernel sources
+        build_info = {"majorant": "per-brick (8^3) DDA", "pool_slots": int(os.environ.get("NE_B200_POOL", 1 << 26)), "csrc_sha16": csrc_sha16()}
         line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": cfg,
+                "data": "synthetic", "config": cfg, "build": build_info,
                 "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
                 "weak": weak, "counters": counters, "kernel_ms": stage_ms}
         print(json.dumps(line), flush=True)
